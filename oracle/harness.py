@@ -1,0 +1,264 @@
+"""Harness for running the compiled reference (oracle/_ref) and reading its outputs.
+
+TEST INFRASTRUCTURE, NOT PRODUCT: only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs import this module.
+
+It writes the reference's own input formats (par JSON, .src, .station — formats from
+/root/reference/example/cgfd3d.example.sh:77-379, parser forward/par_t.c:84-1044), runs a
+binary built by oracle/Makefile, and parses SAC seismograms (lib/sacLib.c:343-377: 632-byte
+header + npts float32) and the dense "CGNC1" container our NetCDF stand-in writes
+(oracle/shims/netcdf_shim.c).
+"""
+from __future__ import annotations
+
+import json
+import os
+import struct
+import subprocess
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(HERE, "_ref")
+
+
+def ref_binary(name: str = "ref_main_zero") -> str:
+    return os.path.join(REF_DIR, name)
+
+
+def have_ref(name: str = "ref_main_zero") -> bool:
+    return os.path.isfile(ref_binary(name))
+
+
+CFSPML = {"number_of_layers": 10, "alpha_max": 3.14, "beta_max": 2.0, "ref_vel": 7000.0}
+
+
+def make_par(
+    workdir: str,
+    nx: int,
+    ny: int,
+    nz: int,
+    nt: int,
+    dt: float,
+    *,
+    pml_layers: int = 10,
+    pml_sides=("x_left", "x_right", "y_front", "y_back", "z_bottom"),
+    ablexp_sides=(),
+    free_top: bool = True,
+    grid: dict | None = None,
+    medium_type: str = "elastic_iso",
+    visco: dict | None = None,
+    src_spatial: str = "point",
+    lines: list | None = None,
+    snapshots: list | None = None,
+    slices: dict | None = None,
+    export: bool = False,
+    check_stability: int = 1,
+) -> dict:
+    """Build the par dict. Paths are relative to workdir/cwd."""
+    par = {
+        "number_of_total_grid_points_x": nx,
+        "number_of_total_grid_points_y": ny,
+        "number_of_total_grid_points_z": nz,
+        "number_of_mpiprocs_x": 1,
+        "number_of_mpiprocs_y": 1,
+        "size_of_time_step": dt,
+        "number_of_time_steps": nt,
+        "check_stability": check_stability,
+    }
+    names = {
+        "x_left": "boundary_x_left", "x_right": "boundary_x_right",
+        "y_front": "boundary_y_front", "y_back": "boundary_y_back",
+        "z_bottom": "boundary_z_bottom", "z_top": "boundary_z_top",
+    }
+    for s in pml_sides:
+        c = dict(CFSPML)
+        c["number_of_layers"] = pml_layers
+        par[names[s]] = {"cfspml": c}
+    for s in ablexp_sides:
+        par[names[s]] = {"ablexp": {"number_of_layers": pml_layers, "ref_vel": 7000.0}}
+    if free_top:
+        par["boundary_z_top"] = {"free": "timg"}
+    if grid is None:
+        grid = {"cartesian": {"origin": [0.0, 0.0, -(nz - 1) * 100.0], "inteval": [100.0, 100.0, 100.0]}}
+    par["grid_generation_method"] = grid
+    par["is_export_grid"] = 1 if export else 0
+    par["grid_export_dir"] = "OUT"
+    par["metric_calculation_method"] = {"calculate": 1}
+    par["is_export_metric"] = 1 if export else 0
+    par["medium"] = {"type": medium_type, "input_way": "code", "code": "x", "equivalent_medium_method": "loc"}
+    if visco is not None:
+        par["visco_config"] = visco
+    par["is_export_media"] = 1 if export else 0
+    par["media_export_dir"] = "OUT"
+    par["in_source_file"] = "case.src"
+    par["is_export_source"] = 0
+    par["source_export_dir"] = "OUT"
+    par["source_spatial_distribution_type"] = src_spatial
+    par["output_dir"] = "OUT"
+    par["tmp_dir"] = "OUT"
+    par["in_station_file"] = "case.station"
+    if lines:
+        par["receiver_line"] = lines
+    if snapshots:
+        par["snapshot"] = snapshots
+    if slices:
+        par["slice"] = slices
+    par["check_nan_every_nummber_of_steps"] = 0
+    par["output_all"] = 0
+    return par
+
+
+def write_case(workdir: str, par: dict, src_text: str, stations: list) -> str:
+    """stations: list of (name, is_coord, is_depth, x, y, z)."""
+    os.makedirs(os.path.join(workdir, "OUT"), exist_ok=True)
+    with open(os.path.join(workdir, "case.json"), "w") as f:
+        json.dump(par, f, indent=1)
+    with open(os.path.join(workdir, "case.src"), "w") as f:
+        f.write(src_text)
+    with open(os.path.join(workdir, "case.station"), "w") as f:
+        f.write("%d\n" % len(stations))
+        for s in stations:
+            f.write("%s %d %d %g %g %g\n" % tuple(s))
+    return os.path.join(workdir, "case.json")
+
+
+def moment_src(i, j, depth_k, m=(1e16, 1e16, 1e16, 0, 0, 0), f0=2.0, t0=0.5, stf_len=1.0) -> str:
+    """One moment-tensor point source by grid index, Ricker STF (example.sh:79-112)."""
+    return (
+        "evt1\n1\n0 %g\n2 0\n0 1\n%d %d %d\n0.0 ricker %g %g\n%g %g %g %g %g %g\n"
+        % ((stf_len, i, j, depth_k, f0, t0) + tuple(m))
+    )
+
+
+def force_src(i, j, depth_k, fvec=(0.0, 0.0, 1e16), f0=2.0, t0=0.5, stf_len=1.0) -> str:
+    """One force point source by grid index, Ricker STF."""
+    return (
+        "evt1\n1\n0 %g\n1 0\n0 1\n%d %d %d\n0.0 ricker %g %g\n%g %g %g\n"
+        % ((stf_len, i, j, depth_k, f0, t0) + tuple(fvec))
+    )
+
+
+def run(binary: str, workdir: str, verbose: int = 1, timeout: float = 3600, env=None) -> tuple[float, str]:
+    """Run `<binary> case.json <verbose>` in workdir. Returns (wall seconds, stdout)."""
+    t0 = time.time()
+    p = subprocess.run(
+        [binary, "case.json", str(verbose)], cwd=workdir, capture_output=True, text=True, timeout=timeout, env=env
+    )
+    wall = time.time() - t0
+    if p.returncode != 0:
+        raise RuntimeError(
+            "%s failed (rc=%d)\nstdout tail:\n%s\nstderr tail:\n%s"
+            % (binary, p.returncode, p.stdout[-3000:], p.stderr[-3000:])
+        )
+    return wall, p.stdout
+
+
+def read_sac(path: str) -> np.ndarray:
+    return np.fromfile(path, dtype="<f4", offset=632)
+
+
+def read_sac_dir(outdir: str) -> dict:
+    out = {}
+    for fn in sorted(os.listdir(outdir)):
+        if fn.endswith(".sac"):
+            out[fn[:-4]] = read_sac(os.path.join(outdir, fn))
+    return out
+
+
+def read_cgnc(path: str) -> dict:
+    """Parse the CGNC1 container (netcdf_shim.c). Returns {'dims':{}, 'vars':{name: ndarray}, 'atts':{}}."""
+    with open(path, "rb") as f:
+        buf = f.read()
+    assert buf[:6] == b"CGNC1\n", "%s is not a CGNC1 container" % path
+    pos = 6
+
+    def i32():
+        nonlocal pos
+        v = struct.unpack_from("<i", buf, pos)[0]
+        pos += 4
+        return v
+
+    def i64():
+        nonlocal pos
+        v = struct.unpack_from("<q", buf, pos)[0]
+        pos += 8
+        return v
+
+    def s():
+        nonlocal pos
+        n = i32()
+        v = buf[pos:pos + n].decode()
+        pos += n
+        return v
+
+    def atts():
+        nonlocal pos
+        out = {}
+        for _ in range(i32()):
+            name = s()
+            n = i32()
+            out[name] = np.frombuffer(buf, "<i4", n, pos).copy()
+            pos += 4 * n
+        return out
+
+    dims = []
+    for _ in range(i32()):
+        name = s()
+        ln = i64()
+        unl = i32()
+        dims.append((name, ln, unl))
+    res = {"dims": {d[0]: d[1] for d in dims}, "vars": {}, "var_atts": {}}
+    for _ in range(i32()):
+        name = s()
+        typ = i32()
+        nd = i32()
+        dimids = [i32() for _ in range(nd)]
+        res["var_atts"][name] = atts()
+        n = i64()
+        dt = "<f4" if typ == 5 else "<i4"
+        arr = np.frombuffer(buf, dt, n, pos).copy()
+        pos += 4 * n
+        shape = [dims[d][1] for d in dimids]
+        res["vars"][name] = arr.reshape(shape) if nd else arr
+    res["atts"] = atts()
+    return res
+
+
+def write_cgnc(path: str, dims: dict, variables: dict, atts: dict | None = None) -> None:
+    """Write a CGNC1 container the shim's nc_open can import.
+    dims: ordered {name: len}; variables: {name: (dim-name tuple, float32 ndarray)}."""
+    names = list(dims)
+    with open(path, "wb") as f:
+        f.write(b"CGNC1\n")
+        f.write(struct.pack("<i", len(names)))
+        for n in names:
+            b = n.encode()
+            f.write(struct.pack("<i", len(b)) + b + struct.pack("<qi", dims[n], 0))
+        f.write(struct.pack("<i", len(variables)))
+        for vn, (vd, arr) in variables.items():
+            b = vn.encode()
+            arr = np.ascontiguousarray(arr, dtype="<f4")
+            f.write(struct.pack("<i", len(b)) + b + struct.pack("<ii", 5, len(vd)))
+            for d in vd:
+                f.write(struct.pack("<i", names.index(d)))
+            f.write(struct.pack("<i", 0))
+            f.write(struct.pack("<q", arr.size))
+            f.write(arr.tobytes())
+        atts = atts or {}
+        f.write(struct.pack("<i", len(atts)))
+        for an, av in atts.items():
+            b = an.encode()
+            av = np.asarray(av, dtype="<i4").ravel()
+            f.write(struct.pack("<i", len(b)) + b + struct.pack("<i", av.size) + av.tobytes())
+
+
+def rel_l2(a: np.ndarray, b: np.ndarray) -> float:
+    """||a-b||_2 / ||b||_2 (b = reference). 0 if both are identically zero."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    nb = np.linalg.norm(b)
+    if nb == 0.0:
+        return 0.0 if np.linalg.norm(a) == 0.0 else float("inf")
+    return float(np.linalg.norm(a - b) / nb)
