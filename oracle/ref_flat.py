@@ -1,0 +1,107 @@
+"""ctypes wrapper over oracle/_ref/libcgfd_ref_flat.so (oracle/ref_flat_adapter.c): the UNMODIFIED
+reference functions of the hot path, callable on the flat problem description of the C ABI.
+
+TEST INFRASTRUCTURE, NOT PRODUCT: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "_ref", "libcgfd_ref_flat.so")
+fptr = C.POINTER(C.c_float)
+
+
+def available() -> bool:
+    return os.path.isfile(LIB)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(LIB)
+        L.cgfd_ref_create.restype = C.c_void_p
+        L.cgfd_ref_create.argtypes = [C.c_void_p]
+        L.cgfd_ref_ncmp.argtypes = [C.c_void_p]
+        L.cgfd_ref_pml_aux_size.restype = C.c_size_t
+        L.cgfd_ref_pml_aux_size.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.cgfd_ref_set_pml_aux.argtypes = [C.c_void_p, C.c_int, C.c_int, fptr]
+        L.cgfd_ref_get_pml_aux.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, fptr]
+        L.cgfd_ref_dvh2dvz.argtypes = [C.c_void_p, fptr, fptr, fptr, fptr]
+        L.cgfd_ref_onestage.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, fptr, fptr]
+        L.cgfd_ref_run.argtypes = [C.c_void_p, C.c_int, fptr, C.c_int, C.POINTER(C.c_int64), fptr, C.c_char_p,
+                                   C.POINTER(C.c_double)]
+        _lib = L
+    return _lib
+
+
+def _f(a):
+    assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(fptr)
+
+
+class RefSolver:
+    """The reference CPU implementation behind the same calls as cgfd3d_b200.solver.Solver."""
+
+    def __init__(self, prob):
+        self.prob = prob
+        self._c = prob.to_c()
+        self.h = lib().cgfd_ref_create(C.byref(self._c))
+        if not self.h:
+            raise RuntimeError("cgfd_ref_create failed")
+        self.ncmp = lib().cgfd_ref_ncmp(self.h)
+        self.shape = (self.ncmp, prob.nz, prob.ny, prob.nx)
+
+    def pml_aux_size(self, idim, iside):
+        return lib().cgfd_ref_pml_aux_size(self.h, idim, iside)
+
+    def set_pml_aux(self, idim, iside, aux):
+        aux = np.ascontiguousarray(aux, np.float32)
+        assert aux.size == self.pml_aux_size(idim, iside)
+        assert lib().cgfd_ref_set_pml_aux(self.h, idim, iside, _f(aux)) == 0
+
+    def get_pml_aux(self, idim, iside, level=0):
+        out = np.zeros(self.pml_aux_size(idim, iside), np.float32)
+        assert lib().cgfd_ref_get_pml_aux(self.h, idim, iside, level, _f(out)) == 0
+        return out
+
+    def get_pml_aux_rhs(self, idim, iside):
+        return self.get_pml_aux(idim, iside, 2)
+
+    def dvh2dvz(self):
+        n = self.prob.nx * self.prob.ny * 9
+        outs = [np.zeros(n, np.float32) for _ in range(4)]
+        assert lib().cgfd_ref_dvh2dvz(self.h, *[_f(o) for o in outs]) == 0
+        return dict(matVx2Vz=outs[0], matVy2Vz=outs[1], matF2Vz=outs[2], matD=outs[3])
+
+    def onestage(self, it, ipair, istage, w_cur):
+        w_cur = np.ascontiguousarray(w_cur, np.float32)
+        rhs = np.zeros(self.shape, np.float32)
+        assert lib().cgfd_ref_onestage(self.h, it, ipair, istage, _f(w_cur), _f(rhs)) == 0
+        return rhs
+
+    def run(self, nsteps, w0=None, rec_iptr=None, outdir=None):
+        """Returns (w_final, record[it][icmp][ip], seconds inside drv_rk_curv_col_allstep)."""
+        w = np.zeros(self.shape, np.float32) if w0 is None else np.array(w0, np.float32, order="C", copy=True)
+        nrec = 0 if rec_iptr is None else len(rec_iptr)
+        idx = np.ascontiguousarray(rec_iptr if nrec else [0], np.int64)
+        rec = np.zeros((nsteps, self.ncmp, max(nrec, 1)), np.float32)
+        secs = C.c_double(0.0)
+        tmp = None
+        if outdir is None:
+            tmp = tempfile.TemporaryDirectory()
+            outdir = tmp.name
+        rc = lib().cgfd_ref_run(self.h, nsteps, _f(w), nrec, idx.ctypes.data_as(C.POINTER(C.c_int64)), _f(rec),
+                                outdir.encode(), C.byref(secs))
+        assert rc == 0
+        if tmp is not None:
+            tmp.cleanup()
+        return w, (rec if nrec else rec[:, :, :0]), secs.value
