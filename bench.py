@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py -- Gpoint-updates/s per RK4 step of the CGFD3D time-stepping hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size NIxNJxNK]
+
+N = 1 : BASELINE.json configs[1]: isotropic elastic, Gaussian-hill topography (curvilinear grid),
+        400x400x200, CFS-PML (10 layers, 5 faces) + traction-image free surface, one moment source.
+N > 1 : launched by torchrun, one rank per GPU; BASELINE.json configs[2]: weak scaling, 800x800x400 per
+        GPU (overridable with --size), x-y decomposition, NCCL halo exchange.
+
+One JSON line on stdout (rank 0). `value` = physical grid points advanced one RK4 step per second with
+everything resident in HBM, timed with CUDA events on the solver's stream (max over ranks);
+`e2e` = the same through the public API from HOST buffers: initial wavefield H2D, every step the
+receiver samples and a surface Vx/Vy/Vz snapshot D2H, final wavefield D2H.
+`--impl reference` times the unmodified reference CPU code (oracle/_ref, built from /root/reference
+by oracle/Makefile) on a bounded sample of the same workload with one replica per host core.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Gpoint-updates/s per RK4 step"
+BYTES_PER_POINT_STEP_ISO = 768.0  # 4*(16*C + 4*M), C = 9, M = 12
+
+
+def parse_size(s):
+    a = [int(v) for v in s.lower().split("x")]
+    assert len(a) == 3
+    return tuple(a)
+
+
+def proc_grid(n):
+    """process grid of the weak-scaling runs: 2x1, 2x2, 4x2."""
+    return {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2)}.get(n) or (n, 1)
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons of one GPU while the timed region runs (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.stop = False
+        self.t = None
+
+    def _loop(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([v.strip() for v in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.t = threading.Thread(target=self._loop, daemon=True)
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        pw = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "power_w_max": max(pw) if pw else None, "samples": len(self.rows)}
+
+
+def build_rank_problem(size, rank, nranks):
+    from cgfd3d_b200 import hostsetup as hs
+    ni, nj, nk = size
+    px, py = proc_grid(nranks)
+    ix, iy = rank // py, rank % py   # row-major, y fastest (MPI_Cart_create, forward/mympi_t.c:32-40)
+    def rk(a, b):
+        return a * py + b if (0 <= a < px and 0 <= b < py) else -1
+    neigh = (rk(ix - 1, iy), rk(ix + 1, iy), rk(ix, iy - 1), rk(ix, iy + 1))
+    gni, gnj = ni * px, nj * py
+    # hill spans the global domain (sigma ~ 1/10 of it, height ~ 10 cells)
+    dh = (100.0, 100.0, 100.0)
+    sigma = 0.1 * max(gni, gnj) * dh[0]
+    # dt below the CFL bound of the stretched grid (estimate_dt on the full array is slow; checked in tests)
+    prob = hs.build_problem(ni, nj, nk, dh=dh, topo="hill", hill=(1000.0, sigma), pml_layers=10, free_top=True,
+                            dt=0.012, sub=(ix * ni, iy * nj, gni, gnj, neigh))
+    # one explosive moment source under the hill top, on the rank that owns it
+    gsi, gsj = gni // 2, gnj // 2
+    if ix * ni <= gsi < (ix + 1) * ni and iy * nj <= gsj < (iy + 1) * nj:
+        hs.make_source(prob, gsi - ix * ni, gsj - iy * nj, nk - 1 - 20, nt_total=100000, kind="moment",
+                       mech=(1e16, 1e16, 1e16, 0, 0, 0), fc=2.0, t0=0.5, stf_len=1.0)
+    return prob
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from cgfd3d_b200 import solver
+
+    nranks = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if nranks != args.gpus:
+        if nranks == 1 and args.gpus > 1:
+            raise SystemExit("launch multi-GPU runs with torchrun (one rank per GPU)")
+    torch.cuda.set_device(local)
+    if nranks > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    size = args.size or ((400, 400, 200) if nranks == 1 else (800, 800, 400))
+    t0 = time.time()
+    prob = build_rank_problem(size, rank, nranks)
+    t_host = time.time() - t0
+    t0 = time.time()
+    S = solver.Solver(prob, device=local)
+    t_upload = time.time() - t0
+    if nranks > 1:
+        uid = [solver.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        S.comm_init(uid[0], rank, nranks)
+    if args.variant:
+        S.set_variant(args.variant)
+    ni, nj, nk = size
+    npts = ni * nj * nk
+    K, W = args.steps, args.warmup
+
+    def barrier():
+        torch.cuda.synchronize()
+        if nranks > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing -----------------------------------------------------------------
+    S.run(W, it0=0)
+    S.set_profiling(True)
+    barrier()
+    with ClockSampler(local) as clk:
+        tw0 = time.time()
+        S.run(K, it0=W)
+        barrier()
+        tw1 = time.time()
+    ms = S.last_run_ms()
+    main_ms, main_n, launches = S.get_profile()
+    S.set_profiling(False)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if nranks > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = npts * nranks * K / (ms_max * 1e-3) / 1e9
+
+    # ---- end to end from host buffers -------------------------------------------------------------
+    rec = [prob.iptr(ni // 2 + 5 * n, nj // 2 + 3 * n, nk - 1) for n in range(-4, 5)]
+    S.set_record_points(rec, K + 8)
+    w_host = torch.zeros(S.shape, dtype=torch.float32).pin_memory().numpy()
+    snap = torch.zeros((3, nj, ni), dtype=torch.float32).pin_memory().numpy()
+    h2d = w_host.nbytes / K
+    d2h = w_host.nbytes / K + len(rec) * 9 * 4 + snap.nbytes
+    barrier()
+    te0 = time.time()
+    S.set_wavefield(w_host)
+    for n in range(K):
+        S.run(1, it0=W + K + n)
+        S.get_record(n, 1)
+        for c in range(3):
+            S.get_box(c, 3, ni, 1, 3, nj, 1, prob.nz - 4, 1, 1, out=snap[c:c + 1])
+    S.get_wavefield(out=w_host)
+    barrier()
+    te = torch.tensor([time.time() - te0], dtype=torch.float64, device="cuda")
+    if nranks > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e = npts * nranks * K / float(te.item()) / 1e9
+    finite = bool(np.isfinite(w_host).all())
+
+    out = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        kb = (main_ms / max(main_n, 1)) * 1e-3
+        # algorithmic bytes of one interior-kernel launch = 768/4 B per point-stage x the points it covers
+        main_pts = ni * nj * (nk - 4)   # the free-surface kernel owns the top 4 rows
+        ach = (BYTES_PER_POINT_STEP_ISO / 4.0) * main_pts / kb / 1e9 if main_n else None
+        out = {
+            "metric": METRIC, "value": round(value, 4), "unit": "Gpoint-updates/s", "n_gpus": nranks, "steps": K, "warmup": W,
+            "ms_per_step": round(ms_max / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "isotropic elastic, Gaussian-hill topography (curvilinear), %dx%dx%d per GPU, CFS-PML 10 layers x 5 faces, "
+                                   "traction-image free surface, 1 moment source" % size,
+                       "proc_grid": "%dx%d" % proc_grid(nranks), "l2": "working set >> 126 MB L2 (no flush needed)",
+                       "variant": args.variant or "default"},
+            "e2e": {"value": round(e2e, 4), "unit": "Gpoint-updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "what": "set_wavefield + K x (run(1) + receivers + surface Vx/Vy/Vz snapshot to host) + get_wavefield"},
+            "gpu_launches": int(launches),
+            "clocks": clk.summary(),
+            "roofline": {"bound": "hbm", "kernel": "k_iso_main", "achieved": None if ach is None else round(ach, 1), "peak": peak,
+                         "unit": "GB/s", "frac": None if ach is None else round(ach / peak, 4), "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                         "launches_timed": int(main_n), "avg_launch_ms": round(main_ms / max(main_n, 1), 4),
+                         "algorithmic_bytes_per_launch": int((BYTES_PER_POINT_STEP_ISO / 4.0) * main_pts),
+                         "whole_step_frac": round(BYTES_PER_POINT_STEP_ISO * npts / (ms_max / K * 1e-3) / 1e9 / peak, 4)},
+            "setup_s": {"host_arrays": round(t_host, 2), "upload": round(t_upload, 2)},
+            "wall_s_timed": round(tw1 - tw0, 4), "finite": finite,
+        }
+        if nranks == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(1, steps=args.cpu_steps)
+    S.close()
+    if nranks > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+
+
+# ---- reference CPU arm --------------------------------------------------------------------------
+SAMPLE = (100, 100, 60)
+
+
+def _ref_worker(q, steps):
+    from cgfd3d_b200 import hostsetup as hs
+    from oracle import ref_flat
+    ni, nj, nk = SAMPLE
+    prob = hs.build_problem(ni, nj, nk, topo="hill", hill=(1000.0, 1000.0), pml_layers=10, free_top=True, dt=0.012)
+    hs.make_source(prob, ni // 2, nj // 2, nk - 1 - 20, nt_total=100000)
+    R = ref_flat.RefSolver(prob)
+    _, _, secs = R.run(steps)
+    q.put(secs)
+
+
+def cpu_baseline(cores, steps=4):
+    """reference CPU code (drv_rk_curv_col_allstep of oracle/_ref) on a bounded sample, `cores` replicas."""
+    import multiprocessing as mp
+    from oracle import ref_flat
+    if not ref_flat.available():
+        return {"value": None, "unit": "Gpoint-updates/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_ref_worker, args=(q, steps)) for _ in range(cores)]
+    for p in ps:
+        p.start()
+    secs = [q.get() for _ in ps]
+    for p in ps:
+        p.join()
+    npts = SAMPLE[0] * SAMPLE[1] * SAMPLE[2]
+    v = cores * npts * steps / max(secs) / 1e9
+    return {"value": round(v, 6), "unit": "Gpoint-updates/s", "cores": cores, "kind": "reference",
+            "sample": "%d steps of the same physics (hill, CFS-PML 10x5, free surface) on a %dx%dx%d block; %d independent single-rank "
+                      "replicas of the unmodified reference (no MPI in the image: upper bound, no halo cost)" % ((steps,) + SAMPLE + (cores,))}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    K, W = args.steps, args.warmup
+    # one "step" of this arm = one RK4 step of the sample on every core; W warm-up steps are folded into the same call
+    steps = max(1, min(K, 8))
+    cpu_baseline(min(cores, 2), steps=1)  # warm-up (page-in)
+    t0 = time.time()
+    cb = cpu_baseline(cores, steps=steps)
+    wall = time.time() - t0
+    out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "Gpoint-updates/s", "n_gpus": args.gpus, "steps": steps,
+           "warmup": 1, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic",
+           "config": {"workload": "isotropic elastic, Gaussian-hill topography, CFS-PML 10 layers x 5 faces, traction-image free surface; "
+                                  "CPU sample %dx%dx%d per core" % SAMPLE},
+           "cpu_baseline": cb,
+           "e2e": {"value": cb["value"], "unit": "Gpoint-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "wall_s": round(wall, 2)}
+    if cb["value"] is not None:
+        npts = SAMPLE[0] * SAMPLE[1] * SAMPLE[2]
+        out["ms_per_step"] = round(cores * npts / (cb["value"] * 1e9) * 1e3, 3)
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--size", type=parse_size, default=None)
+    ap.add_argument("--variant", default="")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=4)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl != "reference":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

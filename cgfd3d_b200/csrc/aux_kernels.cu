@@ -1,0 +1,134 @@
+// Small per-stage / per-step kernels around the fused RHS pass: source injection, surface-force
+// slices, output taps (record points, sub-box pack, peak ground motion), sponge, halo pack/unpack.
+#include "aux_kernels.cuh"
+
+namespace cgfd {
+
+// Point / Gaussian body sources added after the fused stage update: the reference adds
+// F*w*slw/J to hV and -M*w/J to hT before the RK axpy (forward/sv_curv_col_el.c:350-476);
+// here the same term is pushed through the axpy: tmp += a*s, end += b*s.
+__global__ void k_src_inject(SrcDev S, int it, int istage, float *tmp, float *end, float a, float b, size_t V, int kind)
+{
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= S.npts) return;
+  const int is = S.pt_src[n];
+  const int itb = S.it_begin[is], ite = S.it_end[is];
+  if (it < itb || it > ite) return;
+  const size_t tab = ((size_t)is * S.max_nt + (size_t)(it - itb)) * S.max_stage + istage;
+  const size_t p = S.pt_iptr[n];
+  float add[9];
+#pragma unroll
+  for (int c = 0; c < 9; c++) add[c] = 0.0f;
+  if (S.force_actived) {
+    const float w = S.pt_wV[n];
+    add[VX] = S.Fx[tab] * w; add[VY] = S.Fy[tab] * w; add[VZ] = S.Fz[tab] * w;
+  }
+  if (S.moment_actived) {
+    const float w = S.pt_wM[n];
+    add[TXX] = -(S.Mxx[tab] * w); add[TYY] = -(S.Myy[tab] * w); add[TZZ] = -(S.Mzz[tab] * w);
+    add[TXZ] = -(S.Mxz[tab] * w); add[TYZ] = -(S.Myz[tab] * w); add[TXY] = -(S.Mxy[tab] * w);
+  }
+#pragma unroll
+  for (int c = 0; c < 9; c++) {
+    if (add[c] != 0.0f) {
+      if (kind != KIND_LAST) atomicAdd(tmp + c * V + p, a * add[c]);
+      atomicAdd(end + c * V + p, b * add[c]);
+    }
+  }
+}
+
+// surface force slices TxSrc.. / VxSrc.. of one stage (forward/src_t.c:153-314); slices are
+// zeroed by a memset before this kernel.
+__global__ void k_src_surface(SrcDev S, int it, int istage, float *Tx, float *Ty, float *Tz, float *Vx, float *Vy, float *Vz)
+{
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= S.nsurf_pts) return;
+  const int ns = S.sf_rate_slot[n];          // index into the *_rate tables
+  const int is = S.sf_src[n];
+  const int itb = S.it_begin[is], ite = S.it_end[is];
+  if (it < itb || it > ite) return;
+  const size_t tab = ((size_t)is * S.max_nt + (size_t)(it - itb)) * S.max_stage + istage;
+  const size_t tabr = ((size_t)ns * S.max_nt + (size_t)(it - itb)) * S.max_stage + istage;
+  const int p2 = S.sf_iptr2d[n];
+  const float c = S.sf_coef[n], cj = S.sf_coef_over_jac[n];
+  atomicAdd(Tx + p2, S.Fx[tab] * c); atomicAdd(Ty + p2, S.Fy[tab] * c); atomicAdd(Tz + p2, S.Fz[tab] * c);
+  atomicAdd(Vx + p2, S.Fx_rate[tabr] * cj); atomicAdd(Vy + p2, S.Fy_rate[tabr] * cj); atomicAdd(Vz + p2, S.Fz_rate[tabr] * cj);
+}
+
+// io_line_keep / integer-point io_recv_keep (forward/io_funcs.c:1584-1645): one sample per
+// component per registered point per step.
+__global__ void k_record(const float *w, size_t V, int ncmp, int npts, const int64_t *iptr, float *rec_it)
+{
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= npts * ncmp) return;
+  int c = n / npts, ip = n % npts;
+  rec_it[(size_t)c * npts + ip] = w[c * V + iptr[ip]];
+}
+
+// strided sub-box of one component (io_snap_nc_put / io_slice_nc_put packing,
+// forward/io_funcs.c:1032-1104, 1161-1262)
+__global__ void k_pack_box(const float *w, int nx, int ny, int i1, int ni, int di, int j1, int nj, int dj, int k1, int nk,
+                           int dk, float *out)
+{
+  size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t tot = (size_t)ni * nj * nk;
+  if (n >= tot) return;
+  int ii = n % ni, jj = (n / ni) % nj, kk = n / ((size_t)ni * nj);
+  out[n] = w[((size_t)(k1 + kk * dk) * ny + (j1 + jj * dj)) * nx + (i1 + ii * di)];
+}
+
+// PGV / PGA / PGD maps on the free surface (PG_calcu, forward/wav_t.c:379-455)
+__global__ void k_pg(const float *w_new, const float *w_old, size_t V, int nx, int ny, int ni1, int ni2, int nj1, int nj2,
+                     int nk2, float dt, float *PG, float *Dis)
+{
+  int i = ni1 + blockIdx.x * blockDim.x + threadIdx.x;
+  int j = nj1 + blockIdx.y;
+  if (i > ni2 || j > nj2) return;
+  const size_t sl = (size_t)nx * ny;
+  const size_t p = (size_t)nk2 * sl + (size_t)j * nx + i, p1 = (size_t)j * nx + i;
+  const float vx1 = w_new[p], vy1 = w_new[V + p], vz1 = w_new[2 * V + p];
+  const float vx0 = w_old[p], vy0 = w_old[V + p], vz0 = w_old[2 * V + p];
+  const float Ax = fabsf((vx1 - vx0) / dt), Ay = fabsf((vy1 - vy0) / dt), Az = fabsf((vz1 - vz0) / dt);
+  float dx = Dis[p1] + 0.5f * (vx1 + vx0) * dt, dy = Dis[sl + p1] + 0.5f * (vy1 + vy0) * dt,
+        dz = Dis[2 * sl + p1] + 0.5f * (vz1 + vz0) * dt;
+  Dis[p1] = dx; Dis[sl + p1] = dy; Dis[2 * sl + p1] = dz;
+  const float Vv = sqrtf(vx1 * vx1 + vy1 * vy1 + vz1 * vz1), Vh = sqrtf(vx1 * vx1 + vy1 * vy1);
+  const float A = sqrtf(Ax * Ax + Ay * Ay + Az * Az), Ah = sqrtf(Ax * Ax + Ay * Ay);
+  const float D = sqrtf(dx * dx + dy * dy + dz * dz), Dh = sqrtf(dx * dx + dy * dy);
+  const float vals[15] = {Vv, Vh, fabsf(vx1), fabsf(vy1), fabsf(vz1), A, Ah, Ax, Ay, Az, D, Dh, fabsf(dx), fabsf(dy), fabsf(dz)};
+#pragma unroll
+  for (int n = 0; n < 15; n++) {
+    float *q = PG + n * sl + p1;
+    if (*q < vals[n]) *q = vals[n];
+  }
+}
+
+// exponential sponge: W *= min(Ex[i],Ey[j],Ez[k]) inside one shell block (forward/bdry_t.c:840-890)
+__global__ void k_ablexp(float *w, size_t V, int ncmp, int nx, int ny, int i1, int i2, int j1, int j2, int k1, int k2,
+                         const float *Ex, const float *Ey, const float *Ez)
+{
+  int i = i1 + blockIdx.x * blockDim.x + threadIdx.x;
+  int j = j1 + blockIdx.y, k = k1 + blockIdx.z;
+  if (i > i2 || j > j2 || k > k2) return;
+  float d = fminf(fminf(Ex[i], Ey[j]), Ez[k]);
+  size_t p = ((size_t)k * ny + j) * nx + i;
+  for (int c = 0; c < ncmp; c++) w[c * V + p] *= d;
+}
+
+// halo strips <-> contiguous message buffers, layout [ivar][k][j][i] per side as
+// blk_macdrp_pack_mesg / unpack_mesg (forward/blk_t.c:576-808): only j in [nj1,nj2], k in [nk1,nk2]
+// for x messages and i in [ni1,ni2] for y messages (no edges / corners).
+__global__ void k_halo_copy(float *w, float *buf, size_t V, int ncmp, int nx, int ny, int i1, int ni, int j1, int nj, int k1,
+                            int nk, int unpack)
+{
+  size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t per = (size_t)ni * nj * nk;
+  if (n >= per * ncmp) return;
+  int c = n / per;
+  size_t r = n % per;
+  int ii = r % ni, jj = (r / ni) % nj, kk = r / ((size_t)ni * nj);
+  size_t p = c * V + ((size_t)(k1 + kk) * ny + (j1 + jj)) * nx + (i1 + ii);
+  if (unpack) w[p] = buf[n]; else buf[n] = w[p];
+}
+
+}  // namespace cgfd

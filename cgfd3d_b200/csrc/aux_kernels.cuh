@@ -1,0 +1,36 @@
+#pragma once
+#include "cgfd_dev.cuh"
+
+namespace cgfd {
+
+// device copy of the source tables (forward/src_t.h:21-128) plus the flattened footprints
+struct SrcDev {
+  int nsrc, max_nt, max_stage;
+  int force_actived, moment_actived;
+  const int *it_begin, *it_end;
+  const float *Fx, *Fy, *Fz, *Mxx, *Myy, *Mzz, *Mxz, *Myz, *Mxy;
+  const float *Fx_rate, *Fy_rate, *Fz_rate;
+  // body-source footprint points: grid index, owning source, weights w*slw/J (force) and w/J (moment)
+  int npts;
+  const int64_t *pt_iptr;
+  const int *pt_src;
+  const float *pt_wV, *pt_wM;
+  // surface-force footprint points on the k = nk2 slice
+  int nsurf_pts;
+  const int *sf_src, *sf_rate_slot, *sf_iptr2d;
+  const float *sf_coef, *sf_coef_over_jac;
+};
+
+__global__ void k_src_inject(SrcDev S, int it, int istage, float *tmp, float *end, float a, float b, size_t V, int kind);
+__global__ void k_src_surface(SrcDev S, int it, int istage, float *Tx, float *Ty, float *Tz, float *Vx, float *Vy, float *Vz);
+__global__ void k_record(const float *w, size_t V, int ncmp, int npts, const int64_t *iptr, float *rec_it);
+__global__ void k_pack_box(const float *w, int nx, int ny, int i1, int ni, int di, int j1, int nj, int dj, int k1, int nk,
+                           int dk, float *out);
+__global__ void k_pg(const float *w_new, const float *w_old, size_t V, int nx, int ny, int ni1, int ni2, int nj1, int nj2,
+                     int nk2, float dt, float *PG, float *Dis);
+__global__ void k_ablexp(float *w, size_t V, int ncmp, int nx, int ny, int i1, int i2, int j1, int j2, int k1, int k2,
+                         const float *Ex, const float *Ey, const float *Ez);
+__global__ void k_halo_copy(float *w, float *buf, size_t V, int ncmp, int nx, int ny, int i1, int ni, int j1, int nj, int k1,
+                            int nk, int unpack);
+
+}  // namespace cgfd

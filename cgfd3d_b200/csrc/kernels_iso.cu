@@ -1,0 +1,323 @@
+// Isotropic elastic RHS + CFS-PML + free surface + RK stage update, one fused pass per stage.
+//
+//   k_iso_main : all rows below the free-surface rows. One thread per (i,j) column marching along
+//                z with a 5-deep register queue per component; the current x-y plane of the 9
+//                components sits in a double-buffered shared-memory tile (one barrier per plane).
+//                Restates sv_curv_col_el_iso_rhs_inner (forward/sv_curv_col_el_iso.c:208-441),
+//                sv_curv_col_el_iso_rhs_cfspml (:644-1146) and the RK axpy loops of
+//                forward/drv_rk_curv_col.c:292-446 without ever writing the RHS to memory.
+//   k_iso_top  : the top four rows when the top is a free surface: traction-image momentum RHS
+//                (sv_curv_col_el_rhs_timg_z2, forward/sv_curv_col_el.c:30-305), reduced-order /
+//                matrix Dz for the stress RHS (sv_curv_col_el_iso_rhs_vlow_z2, iso.c:451-634),
+//                PML with its free-surface terms, RK update.
+#include "physics.cuh"
+
+namespace cgfd {
+
+__constant__ FdConst c_fd;
+
+template <int D> struct Ofs {            // stencil offsets of direction index D
+  static constexpr int first = D ? -3 : -1;
+  static constexpr int left = D ? 3 : 1;   // points on the negative side
+  static constexpr int right = D ? 1 : 3;
+};
+
+constexpr int TX = 32, TY = 8;
+constexpr int SX = TX + 4, SY = TY + 4;
+constexpr int NHALO = 4 * TY + 4 * TX;          // halo cells per component per plane
+constexpr int NSLOT = (9 * NHALO + TX * TY - 1) / (TX * TY);
+
+template <int DX, int DY, int DZ, int KIND>
+__global__ void __launch_bounds__(TX *TY, 2) k_iso_main(const StageArgs P)
+{
+  __shared__ float s[2][9][SY][SX];
+  constexpr int XL = Ofs<DX>::left, YL = Ofs<DY>::left, ZB = Ofs<DZ>::left, ZA = Ofs<DZ>::right;
+
+  const int tx = threadIdx.x, ty = threadIdx.y, t = ty * TX + tx;
+  const int i0 = P.ni1 + blockIdx.x * TX, j0 = P.nj1 + blockIdx.y * TY;
+  const int i = i0 + tx, j = j0 + ty;
+  const int k0 = P.kbeg + blockIdx.z * P.zchunk;
+  const int k1 = min(k0 + P.zchunk - 1, P.kend);
+  const bool inarr = (i < P.nx) && (j < P.ny);
+  const bool active = (i <= P.ni2) && (j <= P.nj2);
+  const size_t pij = (size_t)j * P.siz_line + i;
+
+  // halo slots of this thread: offset inside one x-y plane (+ component) and inside the smem tile
+  int hg[NSLOT], hs[NSLOT];
+#pragma unroll
+  for (int q = 0; q < NSLOT; q++) {
+    int idx = t + q * (TX * TY);
+    hg[q] = -1; hs[q] = 0;
+    if (idx < 9 * NHALO) {
+      int c = idx / NHALO, r = idx % NHALO;
+      int sx, sy;
+      if (r < 4 * TY) { int row = r >> 2, c4 = r & 3; sy = row + YL; sx = (c4 < XL) ? c4 : TX + c4; }
+      else { r -= 4 * TY; int r4 = r / TX, col = r % TX; sx = col + XL; sy = (r4 < YL) ? r4 : TY + r4; }
+      int gi = i0 - XL + sx, gj = j0 - YL + sy;
+      if (gi < P.nx && gj < P.ny) {
+        hg[q] = gj * (int)P.siz_line + gi;   // plane offset < 2^31
+        hs[q] = (c * SY + sy) * SX + sx;
+      }
+      // component stride added at use
+      hg[q] = (hg[q] < 0) ? -1 : hg[q];
+      if (hg[q] >= 0) hs[q] |= (c << 24);
+    }
+  }
+
+  float q[9][5];
+  if (inarr) {
+#pragma unroll
+    for (int c = 0; c < 9; c++)
+#pragma unroll
+      for (int n = 0; n < 4; n++)
+        q[c][n] = __ldg(P.cur + c * P.siz_vol + (size_t)(k0 - ZB + n) * P.siz_slice + pij);
+  }
+
+  // per-thread PML membership along x and y is fixed for the whole column
+  const float *cx = c_fd.coef[DX], *cy = c_fd.coef[DY], *cz = c_fd.coef[DZ];
+
+  for (int k = k0; k <= k1; k++) {
+    const int buf = k & 1;
+    const size_t pk = (size_t)k * P.siz_slice;
+    if (inarr) {
+#pragma unroll
+      for (int c = 0; c < 9; c++) {
+        q[c][4] = __ldg(P.cur + c * P.siz_vol + (size_t)(k + ZA) * P.siz_slice + pij);
+        s[buf][c][ty + YL][tx + XL] = q[c][ZB];
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < NSLOT; n++) {
+      if (hg[n] >= 0) {
+        int c = hs[n] >> 24;
+        (&s[buf][0][0][0])[hs[n] & 0xffffff] = __ldg(P.cur + c * P.siz_vol + pk + hg[n]);
+      }
+    }
+    __syncthreads();
+
+    if (active) {
+      const size_t p = pk + pij;
+      Deriv d;
+#pragma unroll
+      for (int c = 0; c < 9; c++) {
+        const float *row = &s[buf][c][ty + YL][tx + XL];
+        d.x[c] = cx[0] * row[Ofs<DX>::first + 0] + cx[1] * row[Ofs<DX>::first + 1] + cx[2] * row[Ofs<DX>::first + 2]
+               + cx[3] * row[Ofs<DX>::first + 3] + cx[4] * row[Ofs<DX>::first + 4];
+        d.y[c] = cy[0] * row[(Ofs<DY>::first + 0) * SX] + cy[1] * row[(Ofs<DY>::first + 1) * SX]
+               + cy[2] * row[(Ofs<DY>::first + 2) * SX] + cy[3] * row[(Ofs<DY>::first + 3) * SX]
+               + cy[4] * row[(Ofs<DY>::first + 4) * SX];
+        d.z[c] = cz[0] * q[c][0] + cz[1] * q[c][1] + cz[2] * q[c][2] + cz[3] * q[c][3] + cz[4] * q[c][4];
+      }
+      const Met m = load_metric(P, p);
+      const float lam = __ldg(P.media[0] + p), mu = __ldg(P.media[1] + p), slw = __ldg(P.media[2] + p);
+      const float lam2mu = lam + 2.0f * mu;
+      float h[9];
+      momentum(d, m, slw, h);
+      hooke_iso(d, m, lam, mu, lam2mu, h);
+      pml_all_iso<KIND>(P, i, j, k, d, m, lam, mu, lam2mu, slw, h);
+#pragma unroll
+      for (int c = 0; c < 9; c++)
+        rk_update<KIND>(P.pre, P.tmp, P.end, c * P.siz_vol + p, q[c][ZB], h[c], P.a, P.b);
+    }
+#pragma unroll
+    for (int c = 0; c < 9; c++) {
+      q[c][0] = q[c][1]; q[c][1] = q[c][2]; q[c][2] = q[c][3]; q[c][3] = q[c][4];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// free-surface rows: k in [nk2-3, nk2], one thread per point, neighbours straight from L1/L2
+// ---------------------------------------------------------------------------------------------
+template <int DX, int DY, int DZ, int KIND>
+__global__ void __launch_bounds__(128) k_iso_top(const StageArgs P)
+{
+  const int i = P.ni1 + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = P.nj1 + blockIdx.y;
+  const int k = P.kbeg + blockIdx.z;
+  if (i > P.ni2 || j > P.nj2 || k > P.kend) return;
+  const size_t L = P.siz_line, S = P.siz_slice, V = P.siz_vol;
+  const size_t p = (size_t)k * S + (size_t)j * L + i;
+  const size_t p2 = (size_t)j * L + i;
+  const float *cx = c_fd.coef[DX], *cy = c_fd.coef[DY], *cz = c_fd.coef[DZ];
+  constexpr int FX = Ofs<DX>::first, FY = Ofs<DY>::first, FZ = Ofs<DZ>::first;
+  const int nsurf = P.nk2 - k;   // 0 at the surface
+
+  Deriv d;
+  float cur[9];
+#pragma unroll
+  for (int c = 0; c < 9; c++) {
+    const float *w = P.cur + c * V + p;
+    cur[c] = __ldg(w);
+    d.x[c] = cx[0] * __ldg(w + FX) + cx[1] * __ldg(w + FX + 1) + cx[2] * __ldg(w + FX + 2) + cx[3] * __ldg(w + FX + 3)
+           + cx[4] * __ldg(w + FX + 4);
+    d.y[c] = cy[0] * __ldg(w + (FY + 0) * (long)L) + cy[1] * __ldg(w + (FY + 1) * (long)L)
+           + cy[2] * __ldg(w + (FY + 2) * (long)L) + cy[3] * __ldg(w + (FY + 3) * (long)L)
+           + cy[4] * __ldg(w + (FY + 4) * (long)L);
+    // interior zeta operator; rows whose stencil leaves the grid get replaced below
+    d.z[c] = cz[0] * __ldg(w + (FZ + 0) * (long)S) + cz[1] * __ldg(w + (FZ + 1) * (long)S)
+           + cz[2] * __ldg(w + (FZ + 2) * (long)S) + cz[3] * __ldg(w + (FZ + 3) * (long)S)
+           + cz[4] * __ldg(w + (FZ + 4) * (long)S);
+  }
+  const Met m = load_metric(P, p);
+  const float lam = __ldg(P.media[0] + p), mu = __ldg(P.media[1] + p), slw = __ldg(P.media[2] + p);
+  const float lam2mu = lam + 2.0f * mu;
+
+  // --- velocity gradient along zeta in the top three rows (vlow, iso.c:503-593)
+  if (nsurf == 0) {
+    const float *A = P.matVx2Vz + p2 * 9, *B = P.matVy2Vz + p2 * 9, *F = P.matF2Vz + p2 * 9;
+    float sx = P.VxSrc ? __ldg(P.VxSrc + p2) : 0.0f, sy = P.VySrc ? __ldg(P.VySrc + p2) : 0.0f,
+          sz = P.VzSrc ? __ldg(P.VzSrc + p2) : 0.0f;
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      float v = __ldg(A + 3 * r + 0) * d.x[VX] + __ldg(A + 3 * r + 1) * d.x[VY] + __ldg(A + 3 * r + 2) * d.x[VZ]
+              + __ldg(B + 3 * r + 0) * d.y[VX] + __ldg(B + 3 * r + 1) * d.y[VY] + __ldg(B + 3 * r + 2) * d.y[VZ];
+      v += __ldg(F + 3 * r + 0) * sx + __ldg(F + 3 * r + 1) * sy + __ldg(F + 3 * r + 2) * sz;
+      d.z[r] = v;
+    }
+  } else if (nsurf == 1) {
+    const long o0 = DZ ? -(long)S : 0, o1 = DZ ? 0 : (long)S;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const float *w = P.cur + c * V + p;
+      d.z[c] = c_fd.lay2[DZ][0] * __ldg(w + o0) + c_fd.lay2[DZ][1] * __ldg(w + o1);
+    }
+  } else if (nsurf == 2) {
+    const long o0 = DZ ? -2 * (long)S : 0;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const float *w = P.cur + c * V + p + o0;
+      d.z[c] = c_fd.lay3[DZ][0] * __ldg(w) + c_fd.lay3[DZ][1] * __ldg(w + S) + c_fd.lay3[DZ][2] * __ldg(w + 2 * S);
+    }
+  }
+
+  float h[9];
+  momentum(d, m, slw, h);
+  hooke_iso(d, m, lam, mu, lam2mu, h);
+
+  // --- traction image: momentum RHS in conservative form (sv_curv_col_el.c:84-304)
+  const int kmin = P.nk2 - (FZ + 4);
+  if (k >= kmin) {
+    const int n_free = P.nk2 - k - FZ;
+    const float jac = __ldg(P.metric[M_JAC] + p);
+    const float slwjac = slw / jac;
+    // component triplets (T1,T2,T3) with flux_n = J*(e_x T1 + e_y T2 + e_z T3)
+    const int T1[3] = {TXX, TXY, TXZ}, T2[3] = {TXY, TYY, TYZ}, T3[3] = {TXZ, TYZ, TZZ};
+    const float *Ts[3] = {P.TxSrc, P.TySrc, P.TzSrc};
+    float fx[3][5], fy[3][5], fz[3][5];
+#pragma unroll
+    for (int n = 0; n < 5; n++) {
+      {
+        const size_t pp = p + (FX + n);
+        const float jn = __ldg(P.metric[M_JAC] + pp), ex = __ldg(P.metric[M_XIX] + pp), ey = __ldg(P.metric[M_XIY] + pp),
+                    ez = __ldg(P.metric[M_XIZ] + pp);
+#pragma unroll
+        for (int v = 0; v < 3; v++)
+          fx[v][n] = jn * (ex * __ldg(P.cur + T1[v] * V + pp) + ey * __ldg(P.cur + T2[v] * V + pp) + ez * __ldg(P.cur + T3[v] * V + pp));
+      }
+      {
+        const size_t pp = p + (long)(FY + n) * (long)L;
+        const float jn = __ldg(P.metric[M_JAC] + pp), ex = __ldg(P.metric[M_ETX] + pp), ey = __ldg(P.metric[M_ETY] + pp),
+                    ez = __ldg(P.metric[M_ETZ] + pp);
+#pragma unroll
+        for (int v = 0; v < 3; v++)
+          fy[v][n] = jn * (ex * __ldg(P.cur + T1[v] * V + pp) + ey * __ldg(P.cur + T2[v] * V + pp) + ez * __ldg(P.cur + T3[v] * V + pp));
+      }
+      if (n < n_free) {
+        const size_t pp = p + (long)(FZ + n) * (long)S;
+        const float jn = __ldg(P.metric[M_JAC] + pp), ex = __ldg(P.metric[M_ZTX] + pp), ey = __ldg(P.metric[M_ZTY] + pp),
+                    ez = __ldg(P.metric[M_ZTZ] + pp);
+#pragma unroll
+        for (int v = 0; v < 3; v++)
+          fz[v][n] = jn * (ex * __ldg(P.cur + T1[v] * V + pp) + ey * __ldg(P.cur + T2[v] * V + pp) + ez * __ldg(P.cur + T3[v] * V + pp));
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < 3; v++) {
+      const float ts = Ts[v] ? __ldg(Ts[v] + p2) : 0.0f;
+#pragma unroll
+      for (int n = 0; n < 5; n++) {
+        if (n == n_free) fz[v][n] = ts;
+        else if (n > n_free) {
+          const int im = 2 * n_free - n;    // mirror index inside the window
+          float below;
+          if (im >= 0) below = fz[v][im < 0 ? 0 : im];
+          else if (P.timg_mode == 0) below = 0.0f;
+          else {
+            // image row k + indx[n] - 2(n - n_free) (sv_curv_col_el.c:154-159)
+            const size_t pp = p + (long)(FZ + n - 2 * (n - n_free)) * (long)S;
+            const float jn = __ldg(P.metric[M_JAC] + pp), ex = __ldg(P.metric[M_ZTX] + pp), ey = __ldg(P.metric[M_ZTY] + pp),
+                        ez = __ldg(P.metric[M_ZTZ] + pp);
+            below = jn * (ex * __ldg(P.cur + T1[v] * V + pp) + ey * __ldg(P.cur + T2[v] * V + pp) + ez * __ldg(P.cur + T3[v] * V + pp));
+          }
+          fz[v][n] = 2.0f * ts - below;
+        }
+      }
+      float Dx = cx[0] * fx[v][0]; Dx += cx[1] * fx[v][1]; Dx += cx[2] * fx[v][2]; Dx += cx[3] * fx[v][3]; Dx += cx[4] * fx[v][4];
+      float Dy = cy[0] * fy[v][0]; Dy += cy[1] * fy[v][1]; Dy += cy[2] * fy[v][2]; Dy += cy[3] * fy[v][3]; Dy += cy[4] * fy[v][4];
+      float Dz = cz[0] * fz[v][0]; Dz += cz[1] * fz[v][1]; Dz += cz[2] * fz[v][2]; Dz += cz[3] * fz[v][3]; Dz += cz[4] * fz[v][4];
+      h[v] = (Dx + Dy + Dz) * slwjac;
+    }
+  }
+
+  pml_all_iso<KIND>(P, i, j, k, d, m, lam, mu, lam2mu, slw, h);
+#pragma unroll
+  for (int c = 0; c < 9; c++) rk_update<KIND>(P.pre, P.tmp, P.end, c * V + p, cur[c], h[c], P.a, P.b);
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int DX, int DY, int DZ, int KIND>
+static void launch_t(const StageArgs &P0, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1, int *nlaunch)
+{
+  StageArgs P = P0;
+  const int ni = P.ni2 - P.ni1 + 1, nj = P.nj2 - P.nj1 + 1;
+  const int ktop = P.free_top ? P.nk2 - 3 : P.nk2 + 1;   // first row of the free-surface kernel
+  // interior rows
+  P.kbeg = P.nk1; P.kend = (P.free_top ? ktop - 1 : P.nk2);
+  if (P.kend >= P.kbeg) {
+    const int nk = P.kend - P.kbeg + 1;
+    const int bx = (ni + TX - 1) / TX, by = (nj + TY - 1) / TY;
+    // z chunks: enough blocks to fill 148 SMs x 2 resident blocks a few times over
+    int nzc = 1;
+    while (nzc < nk && (long)bx * by * nzc < 148L * 2 * 4 && nk / (nzc + 1) >= 16) nzc++;
+    P.zchunk = (nk + nzc - 1) / nzc;
+    nzc = (nk + P.zchunk - 1) / P.zchunk;
+    dim3 grid(bx, by, nzc), block(TX, TY);
+    if (ev0) cudaEventRecord(ev0, st);
+    k_iso_main<DX, DY, DZ, KIND><<<grid, block, 0, st>>>(P);
+    if (ev1) cudaEventRecord(ev1, st);
+    (*nlaunch)++;
+  }
+  if (P.free_top) {
+    P.kbeg = (ktop < P.nk1) ? P.nk1 : ktop; P.kend = P.nk2;
+    dim3 block(128), grid((ni + 127) / 128, nj, P.kend - P.kbeg + 1);
+    k_iso_top<DX, DY, DZ, KIND><<<grid, block, 0, st>>>(P);
+    (*nlaunch)++;
+  }
+}
+
+template <int KIND>
+static void launch_k(const StageArgs &P, int dx, int dy, int dz, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, int *n)
+{
+  switch (dx * 4 + dy * 2 + dz) {
+    case 0: launch_t<0, 0, 0, KIND>(P, st, e0, e1, n); break;
+    case 1: launch_t<0, 0, 1, KIND>(P, st, e0, e1, n); break;
+    case 2: launch_t<0, 1, 0, KIND>(P, st, e0, e1, n); break;
+    case 3: launch_t<0, 1, 1, KIND>(P, st, e0, e1, n); break;
+    case 4: launch_t<1, 0, 0, KIND>(P, st, e0, e1, n); break;
+    case 5: launch_t<1, 0, 1, KIND>(P, st, e0, e1, n); break;
+    case 6: launch_t<1, 1, 0, KIND>(P, st, e0, e1, n); break;
+    default: launch_t<1, 1, 1, KIND>(P, st, e0, e1, n); break;
+  }
+}
+
+void launch_iso_stage(const StageArgs &P, int dx, int dy, int dz, int kind, int variant, cudaStream_t st,
+                      cudaEvent_t ev0, cudaEvent_t ev1, int *nlaunch)
+{
+  (void)variant;
+  if (kind == KIND_FIRST) launch_k<KIND_FIRST>(P, dx, dy, dz, st, ev0, ev1, nlaunch);
+  else if (kind == KIND_MID) launch_k<KIND_MID>(P, dx, dy, dz, st, ev0, ev1, nlaunch);
+  else launch_k<KIND_LAST>(P, dx, dy, dz, st, ev0, ev1, nlaunch);
+}
+
+}  // namespace cgfd

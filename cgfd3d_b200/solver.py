@@ -1,0 +1,198 @@
+"""Python binding of the C ABI (include/cgfd3d_b200.h) through ctypes.
+
+`Solver` mirrors what the reference's driver does with its structs
+(drv_rk_curv_col_allstep, forward/drv_rk_curv_col.c:27-556): upload once, run RK4 steps on the
+device, feed the output taps. There is no CPU path: a missing library or a missing GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcgfd3d_b200.so")
+
+SYMBOLS = [
+    "cgfd_b200_last_error", "cgfd_b200_abi_version", "cgfd_b200_sizeof_problem", "cgfd_b200_device_count", "cgfd_b200_create", "cgfd_b200_destroy",
+    "cgfd_b200_set_wavefield", "cgfd_b200_get_wavefield", "cgfd_b200_set_pml_aux", "cgfd_b200_get_pml_aux",
+    "cgfd_b200_pml_aux_size", "cgfd_b200_onestage", "cgfd_b200_get_pml_aux_rhs", "cgfd_b200_run",
+    "cgfd_b200_set_record_points", "cgfd_b200_get_record", "cgfd_b200_get_box", "cgfd_b200_get_pg",
+    "cgfd_b200_comm_unique_id", "cgfd_b200_comm_init", "cgfd_b200_set_profiling", "cgfd_b200_get_profile",
+    "cgfd_b200_last_run_ms", "cgfd_b200_set_variant",
+]
+
+_lib = None
+
+
+class CgfdError(RuntimeError):
+    pass
+
+
+def load_library():
+    """Load libcgfd3d_b200.so (built in-tree by __graft_entry__.build() / csrc/Makefile). Fails loudly."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise CgfdError("%s is missing: build it with `make -C cgfd3d_b200/csrc` (there is no CPU fallback)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, ci, fp = C.c_void_p, C.c_int, abi.fptr
+    L.cgfd_b200_last_error.restype = C.c_char_p
+    L.cgfd_b200_sizeof_problem.restype = C.c_size_t
+    L.cgfd_b200_create.argtypes = [C.POINTER(abi.Problem), ci, C.POINTER(vp)]
+    L.cgfd_b200_destroy.argtypes = [vp]
+    L.cgfd_b200_destroy.restype = None
+    L.cgfd_b200_set_wavefield.argtypes = [vp, fp]
+    L.cgfd_b200_get_wavefield.argtypes = [vp, fp]
+    L.cgfd_b200_set_pml_aux.argtypes = [vp, ci, ci, fp]
+    L.cgfd_b200_get_pml_aux.argtypes = [vp, ci, ci, fp]
+    L.cgfd_b200_get_pml_aux_rhs.argtypes = [vp, ci, ci, fp]
+    L.cgfd_b200_pml_aux_size.argtypes = [vp, ci, ci]
+    L.cgfd_b200_pml_aux_size.restype = C.c_size_t
+    L.cgfd_b200_onestage.argtypes = [vp, ci, ci, ci, fp, fp]
+    L.cgfd_b200_run.argtypes = [vp, ci, ci]
+    L.cgfd_b200_set_record_points.argtypes = [vp, ci, C.POINTER(C.c_int64), ci]
+    L.cgfd_b200_get_record.argtypes = [vp, ci, ci, fp]
+    L.cgfd_b200_get_box.argtypes = [vp] + [ci] * 10 + [fp]
+    L.cgfd_b200_get_pg.argtypes = [vp, fp]
+    L.cgfd_b200_comm_unique_id.argtypes = [C.c_char_p]
+    L.cgfd_b200_comm_init.argtypes = [vp, C.c_char_p, ci, ci]
+    L.cgfd_b200_set_profiling.argtypes = [vp, ci]
+    L.cgfd_b200_get_profile.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.cgfd_b200_last_run_ms.argtypes = [vp, C.POINTER(C.c_double)]
+    L.cgfd_b200_set_variant.argtypes = [vp, C.c_char_p]
+    _lib = L
+    return L
+
+
+def device_count() -> int:
+    return load_library().cgfd_b200_device_count()
+
+
+def _f(a):
+    assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(abi.fptr)
+
+
+class Solver:
+    """One subdomain resident on one GPU."""
+
+    def __init__(self, prob, device: int = 0):
+        self.L = load_library()
+        self.prob = prob
+        self._c = prob.to_c()
+        h = C.c_void_p()
+        self._chk(self.L.cgfd_b200_create(C.byref(self._c), device, C.byref(h)))
+        self.h = h
+        self.ncmp = prob.ncmp
+        self.shape = (self.ncmp, prob.nz, prob.ny, prob.nx)
+        self.nrec = 0
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise CgfdError(self.L.cgfd_b200_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.cgfd_b200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- state
+    def set_wavefield(self, w):
+        w = np.ascontiguousarray(w, np.float32)
+        assert w.shape == self.shape
+        self._chk(self.L.cgfd_b200_set_wavefield(self.h, _f(w)))
+
+    def get_wavefield(self, out=None):
+        w = np.empty(self.shape, np.float32) if out is None else out
+        self._chk(self.L.cgfd_b200_get_wavefield(self.h, _f(w)))
+        return w
+
+    def pml_aux_size(self, idim, iside):
+        return self.L.cgfd_b200_pml_aux_size(self.h, idim, iside)
+
+    def set_pml_aux(self, idim, iside, aux):
+        aux = np.ascontiguousarray(aux, np.float32)
+        assert aux.size == self.pml_aux_size(idim, iside)
+        self._chk(self.L.cgfd_b200_set_pml_aux(self.h, idim, iside, _f(aux)))
+
+    def get_pml_aux(self, idim, iside):
+        out = np.empty(self.pml_aux_size(idim, iside), np.float32)
+        self._chk(self.L.cgfd_b200_get_pml_aux(self.h, idim, iside, _f(out)))
+        return out
+
+    def get_pml_aux_rhs(self, idim, iside):
+        out = np.empty(self.pml_aux_size(idim, iside), np.float32)
+        self._chk(self.L.cgfd_b200_get_pml_aux_rhs(self.h, idim, iside, _f(out)))
+        return out
+
+    # -- compute
+    def onestage(self, it, ipair, istage, w_cur):
+        w_cur = np.ascontiguousarray(w_cur, np.float32)
+        assert w_cur.shape == self.shape
+        rhs = np.empty(self.shape, np.float32)
+        self._chk(self.L.cgfd_b200_onestage(self.h, it, ipair, istage, _f(w_cur), _f(rhs)))
+        return rhs
+
+    def run(self, nsteps, it0=0):
+        self._chk(self.L.cgfd_b200_run(self.h, it0, nsteps))
+
+    # -- taps
+    def set_record_points(self, iptr, max_nt):
+        idx = np.ascontiguousarray(iptr, np.int64)
+        self._chk(self.L.cgfd_b200_set_record_points(self.h, len(idx), idx.ctypes.data_as(C.POINTER(C.c_int64)), max_nt))
+        self.nrec = len(idx)
+
+    def get_record(self, it_first, nt):
+        out = np.empty((nt, self.ncmp, self.nrec), np.float32)
+        self._chk(self.L.cgfd_b200_get_record(self.h, it_first, nt, _f(out)))
+        return out
+
+    def get_box(self, icmp, i1, ni, di, j1, nj, dj, k1, nk, dk, out=None):
+        o = np.empty((nk, nj, ni), np.float32) if out is None else out
+        self._chk(self.L.cgfd_b200_get_box(self.h, icmp, i1, ni, di, j1, nj, dj, k1, nk, dk, _f(o)))
+        return o
+
+    def get_pg(self):
+        out = np.empty((15, self.prob.ny, self.prob.nx), np.float32)
+        self._chk(self.L.cgfd_b200_get_pg(self.h, _f(out)))
+        return out
+
+    # -- multi-GPU
+    def comm_init(self, unique_id: bytes, rank: int, nranks: int):
+        self._chk(self.L.cgfd_b200_comm_init(self.h, unique_id, rank, nranks))
+
+    # -- measurement
+    def set_profiling(self, on=True):
+        self._chk(self.L.cgfd_b200_set_profiling(self.h, 1 if on else 0))
+
+    def get_profile(self):
+        ms, n1, n2 = C.c_double(), C.c_int64(), C.c_int64()
+        self._chk(self.L.cgfd_b200_get_profile(self.h, C.byref(ms), C.byref(n1), C.byref(n2)))
+        return ms.value, n1.value, n2.value
+
+    def last_run_ms(self):
+        ms = C.c_double()
+        self._chk(self.L.cgfd_b200_last_run_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def set_variant(self, name: str):
+        self._chk(self.L.cgfd_b200_set_variant(self.h, name.encode()))
+
+
+def comm_unique_id() -> bytes:
+    L = load_library()
+    buf = C.create_string_buffer(128)
+    if L.cgfd_b200_comm_unique_id(buf) != 0:
+        raise CgfdError(L.cgfd_b200_last_error().decode())
+    return buf.raw

@@ -144,6 +144,8 @@ typedef struct cgfd_b200_ctx cgfd_b200_ctx;
 /* text of the last error on this thread */
 const char *cgfd_b200_last_error(void);
 int  cgfd_b200_abi_version(void);
+/* sizeof(cgfd_problem_t) as compiled into the library, for binding self-checks */
+size_t cgfd_b200_sizeof_problem(void);
 /* number of visible CUDA devices (0 when none; never an error) */
 int  cgfd_b200_device_count(void);
 

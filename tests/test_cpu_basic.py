@@ -1,0 +1,49 @@
+"""CPU-side checks: the C-ABI library loads and exports every declared symbol, the ctypes mirror
+matches the compiled struct, the compute path refuses to run without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from cgfd3d_b200 import abi, hostsetup as hs, solver
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = solver.load_library()
+    header = open(os.path.join(ROOT, "include", "cgfd3d_b200.h")).read()
+    declared = set(re.findall(r"\b(cgfd_b200_[a-z0-9_]+)\s*\(", header))
+    declared.discard("cgfd_b200_ctx")
+    assert declared, "no declarations found"
+    for name in sorted(declared):
+        assert hasattr(L, name), "library does not export " + name
+    assert set(solver.SYMBOLS) <= declared
+
+
+def test_struct_layout_matches_library():
+    L = solver.load_library()
+    assert L.cgfd_b200_abi_version() == abi.ABI_VERSION
+    assert L.cgfd_b200_sizeof_problem() == ctypes.sizeof(abi.Problem)
+
+
+def test_no_cpu_fallback():
+    if solver.device_count() > 0:
+        pytest.skip("a GPU is present")
+    prob = hs.build_problem(12, 12, 12, pml_layers=2)
+    with pytest.raises(solver.CgfdError, match="no CUDA device"):
+        solver.Solver(prob)
+
+
+def test_fd_tables():
+    fd = hs.fd_macdrp()
+    # every stage flips all three axes (forward/fd_t.c:233-236)
+    for p in range(8):
+        for s in range(3):
+            for a in range(3):
+                assert fd.dir[p][s][a] + fd.dir[p][s + 1][a] == 1
+    assert abs(sum(fd.coef[0])) < 1e-3 and abs(sum(fd.coef[1])) < 1e-3  # the reference rounds its coefficients
+    assert [fd.indx[0][n] for n in range(5)] == [-1, 0, 1, 2, 3]
+    assert [fd.indx[1][n] for n in range(5)] == [-3, -2, -1, 0, 1]

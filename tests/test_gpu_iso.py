@@ -1,0 +1,136 @@
+"""GPU parity of the isotropic hot path against the UNMODIFIED reference functions
+(oracle/_ref/libcgfd_ref_flat.so = reference sources + the zero-guarded traction image), through the C ABI.
+
+Tolerances (float32; differences come from FMA contraction and the order the source term enters the RK axpy):
+  one RHS evaluation : max|gpu-ref| <= 2e-5 * max|ref| per component
+  N-step runs        : relative L2 <= 1e-4 per component / per trace (BASELINE.json north_star)
+"""
+import numpy as np
+import pytest
+
+from cgfd3d_b200 import abi, solver
+from oracle import ref_flat
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+TOL_STAGE = 2e-5
+TOL_RUN = 1e-4
+
+
+def _need():
+    if not ref_flat.available():
+        pytest.fail("oracle/_ref/libcgfd_ref_flat.so is missing (build it with make -C oracle ref where /root/reference exists)")
+    if solver.device_count() < 1:
+        pytest.fail("no CUDA device: the hot path has no CPU fallback")
+
+
+def _check_stage(prob, it, ipair, istage, seed):
+    w, aux = util.random_state(prob, seed)
+    R = ref_flat.RefSolver(prob)
+    G = solver.Solver(prob)
+    for key, a in aux.items():
+        R.set_pml_aux(key[0], key[1], a.ravel())
+        G.set_pml_aux(key[0], key[1], a.ravel())
+    rr = R.onestage(it, ipair, istage, w)
+    rg = G.onestage(it, ipair, istage, w)
+    bad = []
+    for c in range(9):
+        e = util.rel_max(rg[c], rr[c])
+        if not e <= TOL_STAGE:
+            bad.append((util.CMP[c], e))
+    for key in aux:
+        ar = R.get_pml_aux_rhs(*key).reshape(9, -1)
+        ag = G.get_pml_aux_rhs(*key).reshape(9, -1)
+        for c in range(9):
+            e = util.rel_max(ag[c], ar[c])
+            if not e <= TOL_STAGE:
+                bad.append(("aux%s.%s" % (key, util.CMP[c]), e))
+    G.close()
+    assert not bad, "ipair=%d istage=%d: %s" % (ipair, istage, bad)
+
+
+@pytest.mark.parametrize("ipair", range(8))
+def test_onestage_all_direction_pairs(ipair):
+    """every (x,y,z) direction combination: 8 pairs x stages 0,1 cover all 8 kernels twice"""
+    _need()
+    prob = util.small_problem(seed=7)
+    for istage in (0, 1):
+        _check_stage(prob, it=3, ipair=ipair, istage=istage, seed=100 + ipair)
+
+
+@pytest.mark.parametrize("case", ["flat", "nopml", "pml6", "gauss", "force", "odd"])
+def test_onestage_variants(case):
+    _need()
+    kw = dict(seed=3)
+    if case == "flat":
+        kw.update(topo="flat")
+    elif case == "nopml":
+        kw.update(pml_faces=())
+    elif case == "pml6":
+        kw.update(free_top=False)
+    elif case == "gauss":
+        kw.update(spatial="gauss")
+    elif case == "force":
+        kw.update(src="force", spatial="gauss")
+    elif case == "odd":
+        kw.update(ni=37, nj=19, nk=23, pml_layers=5)
+    prob = util.small_problem(**kw)
+    _check_stage(prob, it=2, ipair=2, istage=1, seed=5)
+    _check_stage(prob, it=2, ipair=5, istage=2, seed=6)
+
+
+@pytest.mark.parametrize("case", ["hill_pml_free", "flat_pml6", "gauss_src"])
+def test_run_matches_reference_driver(case):
+    """N RK4 steps from rest with a point source: full wavefield, PML aux and recorded traces against
+    drv_rk_curv_col_allstep run on the same flat arrays."""
+    _need()
+    nt = 60
+    kw = dict(ni=40, nj=36, nk=30, pml_layers=8, nt_total=nt)
+    if case == "flat_pml6":
+        kw.update(topo="flat", free_top=False)
+    if case == "gauss_src":
+        kw.update(spatial="gauss")
+    prob = util.small_problem(**kw)
+    rec = [prob.iptr(10 + 5 * n, 12 + 3 * n, prob.nk - 1) for n in range(5)] + [prob.iptr(20, 17, prob.nk - 8)]
+    R = ref_flat.RefSolver(prob)
+    wr, recr, _ = R.run(nt, rec_iptr=rec)
+    G = solver.Solver(prob)
+    G.set_record_points(rec, nt)
+    G.run(nt)
+    wg = G.get_wavefield()
+    recg = G.get_record(0, nt)
+    bad = []
+    for c in range(9):
+        e = util.rel_l2(wg[c], wr[c])
+        if not e <= TOL_RUN:
+            bad.append(("w." + util.CMP[c], e))
+    for c in range(3):  # velocity traces (surface stresses vanish, their relative error is meaningless)
+        for ip in range(len(rec)):
+            e = util.rel_l2(recg[:, c, ip], recr[:, c, ip])
+            if not e <= TOL_RUN:
+                bad.append(("rec%d.%s" % (ip, util.CMP[c]), e))
+    for key in prob.pml:
+        e = util.rel_l2(G.get_pml_aux(*key), R.get_pml_aux(*key))
+        if not e <= TOL_RUN:
+            bad.append(("aux%s" % (key,), e))
+    assert np.isfinite(wg).all()
+    assert float(np.abs(wr[0]).max()) > 0
+    G.close()
+    assert not bad, bad
+
+
+def test_box_and_pg_taps():
+    _need()
+    nt = 20
+    prob = util.small_problem(ni=30, nj=28, nk=24, pml_layers=5, nt_total=nt)
+    G = solver.Solver(prob)
+    G.run(nt)
+    w = G.get_wavefield()
+    box = G.get_box(2, 4, 10, 2, 5, 8, 3, prob.nz - 4, 1, 1)
+    np.testing.assert_array_equal(box, w[2, prob.nz - 4:prob.nz - 3, 5:5 + 8 * 3:3, 4:4 + 10 * 2:2])
+    pg = G.get_pg()
+    assert pg.shape[0] == 15 and float(pg[0].max()) > 0
+    # PGVz is the running max of |Vz| on the surface: at least the final value
+    assert (pg[4, 3:-3, 3:-3] + 1e-30 >= np.abs(w[2, prob.nz - 4, 3:-3, 3:-3])).all()
+    G.close()
