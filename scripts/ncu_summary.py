@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""Summarise gpurun_out/<tag>/{launches.csv,prof_*.ncu-rep,bench.json} into profiles/<tag>_*.txt (read here, no GPU)."""
+import collections, csv, json, os, subprocess, sys
+
+tag = sys.argv[1]
+src = os.path.join("gpurun_out", tag)
+os.makedirs("profiles", exist_ok=True)
+out = []
+lf = os.path.join(src, "launches.csv")
+if os.path.isfile(lf):
+    rows = list(csv.reader(open(lf)))
+    hdr = None
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for r in rows:
+        if "Kernel Name" in r:
+            hdr = r
+            continue
+        if hdr and len(r) == len(hdr):
+            d = dict(zip(hdr, r))
+            if d.get("Metric Name") == "gpu__time_duration.sum":
+                v = float(d["Metric Value"].replace(",", ""))
+                v = v / 1e6 if d["Metric Unit"] == "ns" else v / 1e3 if d["Metric Unit"] == "us" else v
+                agg[d["Kernel Name"][:70]][0] += 1
+                agg[d["Kernel Name"][:70]][1] += v
+    tot = sum(v[1] for v in agg.values())
+    out.append("# ncu launch list (gpu__time_duration.sum, --clock-control none; cold-cache, serialised: compare SHARES)")
+    fam = collections.defaultdict(float)
+    for k, v in sorted(agg.items(), key=lambda x: -x[1][1]):
+        out.append("%-72s n=%4d total=%9.3f ms avg=%8.4f ms share=%5.1f%%" % (k, v[0], v[1], v[1] / v[0], 100 * v[1] / tot))
+        fam[k.split("<")[0].replace("void ", "").split("(")[0]] += v[1]
+    out.append("# by kernel family")
+    for k, v in sorted(fam.items(), key=lambda x: -x[1]):
+        out.append("%-40s total=%9.3f ms share=%5.1f%%" % (k, v, 100 * v / tot))
+want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread", "launch__grid_size",
+        "launch__block_size", "launch__waves_per_multiprocessor", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+        "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio"]
+for f in sorted(os.listdir(src)):
+    if f.endswith(".ncu-rep"):
+        p = subprocess.run(["ncu", "-i", os.path.join(src, f), "--page", "raw", "--csv"], capture_output=True, text=True)
+        rows = list(csv.reader(p.stdout.splitlines()))
+        if len(rows) < 3:
+            continue
+        hdr, units = rows[0], rows[1]
+        out.append("\n# ncu --set full: %s" % f)
+        for r in rows[2:]:
+            d = dict(zip(hdr, r))
+            out.append(d["Kernel Name"][:80])
+            for w in want:
+                if w in d:
+                    out.append("    %-90s %s %s" % (w, d[w], units[hdr.index(w)]))
+bj = os.path.join(src, "bench.json")
+if os.path.isfile(bj):
+    out.append("\n# bench.py line of the same session")
+    out.append(open(bj).read().strip())
+open(os.path.join("profiles", tag + "_summary.txt"), "w").write("\n".join(out) + "\n")
+print("\n".join(out[-60:]))
