@@ -41,11 +41,17 @@ struct cgfd_b200_ctx {
   float dt = 0;
   int medium = 0, nmaxwell = 0, ncmp = 9, nmedia = 0;
   float wl[CGFD_MAX_MAXWELL];
-  size_t V = 0, slice = 0;
-  float *lev[4] = {nullptr, nullptr, nullptr, nullptr};
+  // padded device layout (see cgfd_dev.cuh): pitch PX, index 0 of a row sits `shift` floats in
+  int PX = 0, shift = 0;
+  size_t V = 0, slice = 0;          // padded volume / slice (floats)
+  size_t hV = 0, hslice = 0;        // host (unpadded) volume / slice
+  float *lev[4] = {nullptr, nullptr, nullptr, nullptr};   // bases (unshifted)
+  float *metric_blk = nullptr, *media_blk = nullptr;
+  CUtensorMap map_halo[4], map_cen[4], map_met, map_med;
+  bool have_maps = false;
+  int zchunk = 0;
   int ipre = 0, ia = 1, ib = 2, iend = 3;   // roles of the four level buffers
-  float *zero_lev = nullptr;
-  float *metric[NMETRIC];
+  float *metric[NMETRIC];           // shifted pointers into metric_blk
   float *media[MAX_MEDIA];
   int free_top = 0, timg_mode = 0;
   PmlFaceHost pml[3][2];
@@ -89,6 +95,56 @@ template <typename T> static int upload(cgfd_b200_ctx *c, T **dst, const T *src,
   c->owned.push_back(*dst);
   if (src) CK(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
   else CK(cudaMemset(*dst, 0, n * sizeof(T)));
+  return 0;
+}
+
+// host [rows][nx] <-> device padded rows (pitch PX, shifted)
+static int copy_in3d(cgfd_b200_ctx *c, float *dev_base, const float *host, size_t ncomp, cudaStream_t st)
+{
+  CK(cudaMemcpy2DAsync(dev_base + c->shift, (size_t)c->PX * sizeof(float), host, (size_t)c->g.nx * sizeof(float),
+                       (size_t)c->g.nx * sizeof(float), (size_t)c->g.ny * c->g.nz * ncomp, cudaMemcpyDefault, st));
+  return 0;
+}
+static int copy_out3d(cgfd_b200_ctx *c, float *host, const float *dev_base, size_t ncomp, cudaStream_t st)
+{
+  CK(cudaMemcpy2DAsync(host, (size_t)c->g.nx * sizeof(float), dev_base + c->shift, (size_t)c->PX * sizeof(float),
+                       (size_t)c->g.nx * sizeof(float), (size_t)c->g.ny * c->g.nz * ncomp, cudaMemcpyDefault, st));
+  return 0;
+}
+// host flat index (i + j*nx + k*nx*ny) -> index relative to a shifted device pointer
+static inline int64_t dev_index(const cgfd_b200_ctx *c, int64_t hp)
+{
+  const int64_t nx = c->g.nx, ny = c->g.ny;
+  const int64_t i = hp % nx, j = (hp / nx) % ny, k = hp / (nx * ny);
+  return i + j * (int64_t)c->PX + k * (int64_t)c->slice;
+}
+
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_tiled_fn get_encode()
+{
+  static encode_tiled_fn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (encode_tiled_fn)p;
+  }
+  return fn;
+}
+// 4-D map over [ncomp][nz][ny][PX] float32 with box (bx, by, 1, bc)
+static int make_map(cgfd_b200_ctx *c, CUtensorMap *m, float *base, int ncomp, int bx, int by, int bc)
+{
+  encode_tiled_fn enc = get_encode();
+  if (!enc) return fail("cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dim[4] = {(cuuint64_t)c->PX, (cuuint64_t)c->g.ny, (cuuint64_t)c->g.nz, (cuuint64_t)ncomp};
+  cuuint64_t str[3] = {(cuuint64_t)c->PX * 4, (cuuint64_t)c->slice * 4, (cuuint64_t)c->V * 4};
+  cuuint32_t box[4] = {(cuuint32_t)bx, (cuuint32_t)by, 1, (cuuint32_t)bc};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dim, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
   return 0;
 }
 
@@ -139,7 +195,7 @@ static int setup_sources(cgfd_b200_ctx *c, const cgfd_problem_t *p)
       float wV = 0.0f, wM = 0.0f;
       if (s.force_actived && (s.is_surface_force_strict == 0 || sk < g.nk2)) wV = slw[ip] / jac[ip];
       if (s.moment_actived) wM = (float)(1.0 / jac[ip]);
-      pt_iptr.push_back((int64_t)ip); pt_src.push_back(is); pt_wV.push_back(wV); pt_wM.push_back(wM);
+      pt_iptr.push_back(dev_index(c, (int64_t)ip)); pt_src.push_back(is); pt_wV.push_back(wV); pt_wM.push_back(wM);
     } else {
       int k2 = (sk + H < g.nk2) ? H : g.nk2 - sk;
       norm_delt3d_z2fre(ext, s.si_inc[is], s.sj_inc[is], s.sk_inc[is], s.ext_func_coef, H, k2);
@@ -153,7 +209,7 @@ static int setup_sources(cgfd_b200_ctx *c, const cgfd_problem_t *p)
             float coef = ext[ie], wV = 0.0f, wM = 0.0f;
             if (s.force_actived && (s.is_surface_force_strict == 0 || k < g.nk2)) wV = coef * slw[ip] / jac[ip];
             if (s.moment_actived) wM = coef / jac[ip];
-            pt_iptr.push_back((int64_t)ip); pt_src.push_back(is); pt_wV.push_back(wV); pt_wM.push_back(wM);
+            pt_iptr.push_back(dev_index(c, (int64_t)ip)); pt_src.push_back(is); pt_wV.push_back(wV); pt_wM.push_back(wM);
           }
     }
   }
@@ -260,8 +316,14 @@ extern "C" int cgfd_b200_create(const cgfd_problem_t *p, int device, cgfd_b200_c
   if (g.ni1 != 3 || g.nj1 != 3 || g.nk1 != 3 || g.ni2 != g.nx - 4 || g.nj2 != g.ny - 4 || g.nk2 != g.nz - 4) {
     delete c; return fail("cgfd_b200_create: expected 3 ghost layers on every side");
   }
-  c->slice = (size_t)g.nx * g.ny; c->V = c->slice * g.nz;
+  c->shift = (32 - g.ni1 % 32) % 32;
+  c->PX = ((g.nx + c->shift + 31) / 32) * 32;
+  c->hslice = (size_t)g.nx * g.ny; c->hV = c->hslice * g.nz;
+  c->slice = (size_t)c->PX * g.ny; c->V = c->slice * g.nz;
+  if (const char *e = getenv("CGFD_ZCHUNK")) c->zchunk = atoi(e);
+  if (const char *e = getenv("CGFD_VARIANT")) c->variant = atoi(e);
   CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+  if (iso_kernels_init()) { delete c; return fail("cgfd_b200_create: cudaFuncSetAttribute failed (needs sm_100 shared memory sizes)"); }
   CK(cudaEventCreate(&c->run0)); CK(cudaEventCreate(&c->run1));
 
   FdConst fc;
@@ -274,9 +336,31 @@ extern "C" int cgfd_b200_create(const cgfd_problem_t *p, int device, cgfd_b200_c
 
   int rc = 0;
   for (int l = 0; l < 4; l++) rc |= upload(c, &c->lev[l], (const float *)nullptr, c->V * c->ncmp);
-  for (int m = 0; m < NMETRIC; m++) rc |= upload(c, &c->metric[m], p->metric[m], c->V);
-  for (int m = 0; m < p->nmedia; m++) rc |= upload(c, &c->media[m], p->media[m], c->V);
+  rc |= upload(c, &c->metric_blk, (const float *)nullptr, c->V * NMETRIC);
+  rc |= upload(c, &c->media_blk, (const float *)nullptr, c->V * p->nmedia);
   if (rc) { cgfd_b200_destroy(c); return 1; }
+  for (int m = 0; m < NMETRIC; m++) {
+    c->metric[m] = c->metric_blk + (size_t)m * c->V + c->shift;
+    rc |= copy_in3d(c, c->metric_blk + (size_t)m * c->V, p->metric[m], 1, c->st);
+  }
+  for (int m = 0; m < p->nmedia; m++) {
+    c->media[m] = c->media_blk + (size_t)m * c->V + c->shift;
+    rc |= copy_in3d(c, c->media_blk + (size_t)m * c->V, p->media[m], 1, c->st);
+  }
+  CK(cudaStreamSynchronize(c->st));
+  if (rc) { cgfd_b200_destroy(c); return 1; }
+  // tensor maps of the TMA kernel
+  {
+    int mrc = 0;
+    for (int l = 0; l < 4 && !mrc; l++) {
+      mrc |= make_map(c, &c->map_halo[l], c->lev[l], 9, TILE_X + 4, TILE_Y + 4, 9);
+      mrc |= make_map(c, &c->map_cen[l], c->lev[l], 9, TILE_X, TILE_Y, 9);
+    }
+    if (!mrc) mrc |= make_map(c, &c->map_met, c->metric_blk + c->V /* skip jac */, 9, TILE_X, TILE_Y, 9);
+    if (!mrc) mrc |= make_map(c, &c->map_med, c->media_blk, p->nmedia, TILE_X, TILE_Y, 3);
+    c->have_maps = (mrc == 0);
+    if (mrc && c->variant != 1) { cgfd_b200_destroy(c); return 1; }
+  }
 
   for (int idim = 0; idim < 3; idim++) for (int is = 0; is < 2; is++) {
     const cgfd_pml_face_t &f = p->pml[idim][is];
@@ -294,19 +378,19 @@ extern "C" int cgfd_b200_create(const cgfd_problem_t *p, int device, cgfd_b200_c
   }
   if (c->free_top) {
     if (!p->matVx2Vz || !p->matVy2Vz || !p->matF2Vz) { cgfd_b200_destroy(c); return fail("cgfd_b200_create: free surface needs matVx2Vz/matVy2Vz/matF2Vz"); }
-    rc |= upload(c, &c->mats[0], p->matVx2Vz, c->slice * 9);
-    rc |= upload(c, &c->mats[1], p->matVy2Vz, c->slice * 9);
-    rc |= upload(c, &c->mats[2], p->matF2Vz, c->slice * 9);
-    if (p->matD) rc |= upload(c, &c->mats[3], p->matD, c->slice * 9);
-    rc |= upload(c, &c->PG, (const float *)nullptr, c->slice * 15);
-    rc |= upload(c, &c->Dis, (const float *)nullptr, c->slice * 3);
+    rc |= upload(c, &c->mats[0], p->matVx2Vz, c->hslice * 9);
+    rc |= upload(c, &c->mats[1], p->matVy2Vz, c->hslice * 9);
+    rc |= upload(c, &c->mats[2], p->matF2Vz, c->hslice * 9);
+    if (p->matD) rc |= upload(c, &c->mats[3], p->matD, c->hslice * 9);
+    rc |= upload(c, &c->PG, (const float *)nullptr, c->hslice * 15);
+    rc |= upload(c, &c->Dis, (const float *)nullptr, c->hslice * 3);
   }
   if (p->ablexp_enabled) {
     c->ablexp = 1; memcpy(c->ablexp_blk, p->ablexp_blk, sizeof(c->ablexp_blk));
     rc |= upload(c, &c->Ex, p->ablexp_Ex, g.nx); rc |= upload(c, &c->Ey, p->ablexp_Ey, g.ny); rc |= upload(c, &c->Ez, p->ablexp_Ez, g.nz);
   }
   rc |= setup_sources(c, p);
-  if (c->has_surf) rc |= upload(c, &c->srcslice, (const float *)nullptr, c->slice * 6);
+  if (c->has_surf) rc |= upload(c, &c->srcslice, (const float *)nullptr, c->hslice * 6);
   if (rc) { cgfd_b200_destroy(c); return 1; }
   CK(cudaDeviceSynchronize());
   *out = c;
@@ -331,14 +415,14 @@ extern "C" void cgfd_b200_destroy(cgfd_b200_ctx *c)
 extern "C" int cgfd_b200_set_wavefield(cgfd_b200_ctx *c, const float *w)
 {
   CK(cudaSetDevice(c->device));
-  CK(cudaMemcpyAsync(c->lev[c->ipre], w, c->V * c->ncmp * sizeof(float), cudaMemcpyHostToDevice, c->st));
+  if (copy_in3d(c, c->lev[c->ipre], w, c->ncmp, c->st)) return 1;
   CK(cudaStreamSynchronize(c->st));
   return 0;
 }
 extern "C" int cgfd_b200_get_wavefield(cgfd_b200_ctx *c, float *w)
 {
   CK(cudaSetDevice(c->device));
-  CK(cudaMemcpyAsync(w, c->lev[c->ipre], c->V * c->ncmp * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+  if (copy_out3d(c, w, c->lev[c->ipre], c->ncmp, c->st)) return 1;
   CK(cudaStreamSynchronize(c->st));
   return 0;
 }
@@ -375,9 +459,9 @@ static void fill_args(cgfd_b200_ctx *c, StageArgs &P)
 {
   memset(&P, 0, sizeof(P));
   const cgfd_grid_t &g = c->g;
-  P.nx = g.nx; P.ny = g.ny; P.nz = g.nz;
+  P.nx = g.nx; P.ny = g.ny; P.nz = g.nz; P.shift = c->shift;
   P.ni1 = g.ni1; P.ni2 = g.ni2; P.nj1 = g.nj1; P.nj2 = g.nj2; P.nk1 = g.nk1; P.nk2 = g.nk2;
-  P.siz_line = g.nx; P.siz_slice = c->slice; P.siz_vol = c->V;
+  P.siz_line = c->PX; P.siz_slice = c->slice; P.siz_vol = c->V;
   for (int m = 0; m < NMETRIC; m++) P.metric[m] = c->metric[m];
   for (int m = 0; m < c->nmedia; m++) P.media[m] = c->media[m];
   P.nmaxwell = c->nmaxwell;
@@ -385,8 +469,8 @@ static void fill_args(cgfd_b200_ctx *c, StageArgs &P)
   P.free_top = c->free_top; P.timg_mode = c->timg_mode;
   P.matVx2Vz = c->mats[0]; P.matVy2Vz = c->mats[1]; P.matF2Vz = c->mats[2]; P.matD = c->mats[3];
   if (c->has_surf) {
-    P.TxSrc = c->srcslice; P.TySrc = c->srcslice + c->slice; P.TzSrc = c->srcslice + 2 * c->slice;
-    P.VxSrc = c->srcslice + 3 * c->slice; P.VySrc = c->srcslice + 4 * c->slice; P.VzSrc = c->srcslice + 5 * c->slice;
+    P.TxSrc = c->srcslice; P.TySrc = c->srcslice + c->hslice; P.TzSrc = c->srcslice + 2 * c->hslice;
+    P.VxSrc = c->srcslice + 3 * c->hslice; P.VySrc = c->srcslice + 4 * c->hslice; P.VzSrc = c->srcslice + 5 * c->hslice;
   }
   for (int idim = 0; idim < 3; idim++) for (int is = 0; is < 2; is++) {
     PmlFaceHost &h = c->pml[idim][is];
@@ -403,8 +487,14 @@ static void fill_args(cgfd_b200_ctx *c, StageArgs &P)
 static int run_stage(cgfd_b200_ctx *c, StageArgs &P, int it, int ipair, int istage, int kind, int icur, int ipre, int itmp,
                      int iend, float a, float b)
 {
-  P.cur = c->lev[icur]; P.pre = c->lev[ipre]; P.tmp = c->lev[itmp]; P.end = c->lev[iend];
+  const int sh = c->shift;
+  P.cur = c->lev[icur] + sh; P.pre = c->lev[ipre] + sh; P.tmp = c->lev[itmp] + sh; P.end = c->lev[iend] + sh;
   P.a = a; P.b = b;
+  TmaMaps maps;
+  if (c->have_maps) {
+    maps.cur = c->map_halo[icur]; maps.pre = c->map_cen[ipre]; maps.end = c->map_cen[iend];
+    maps.met = c->map_met; maps.med = c->map_med;
+  }
   for (int idim = 0; idim < 3; idim++) for (int is = 0; is < 2; is++) {
     PmlFaceHost &h = c->pml[idim][is];
     if (!h.on) continue;
@@ -413,9 +503,9 @@ static int run_stage(cgfd_b200_ctx *c, StageArgs &P, int it, int ipair, int ista
   }
   int nl = 0;
   if (c->has_surf) {
-    CK(cudaMemsetAsync(c->srcslice, 0, c->slice * 6 * sizeof(float), c->st));
-    k_src_surface<<<(c->src.nsurf_pts + 127) / 128, 128, 0, c->st>>>(c->src, it, istage, c->srcslice, c->srcslice + c->slice,
-        c->srcslice + 2 * c->slice, c->srcslice + 3 * c->slice, c->srcslice + 4 * c->slice, c->srcslice + 5 * c->slice);
+    CK(cudaMemsetAsync(c->srcslice, 0, c->hslice * 6 * sizeof(float), c->st));
+    k_src_surface<<<(c->src.nsurf_pts + 127) / 128, 128, 0, c->st>>>(c->src, it, istage, c->srcslice, c->srcslice + c->hslice,
+        c->srcslice + 2 * c->hslice, c->srcslice + 3 * c->hslice, c->srcslice + 4 * c->hslice, c->srcslice + 5 * c->hslice);
     nl++;
   }
   const int *dir = c->fd.dir[ipair][istage];
@@ -426,9 +516,9 @@ static int run_stage(cgfd_b200_ctx *c, StageArgs &P, int it, int ipair, int ista
     }
     e0 = c->ev[c->ev_used]; e1 = c->ev[c->ev_used + 1]; c->ev_used += 2;
   }
-  launch_iso_stage(P, dir[0], dir[1], dir[2], kind, c->variant, c->st, e0, e1, &nl);
+  launch_iso_stage(P, c->have_maps ? &maps : nullptr, dir[0], dir[1], dir[2], kind, c->variant, c->zchunk, c->st, e0, e1, &nl);
   if (c->has_src) {
-    k_src_inject<<<(c->src.npts + 127) / 128, 128, 0, c->st>>>(c->src, it, istage, c->lev[itmp], c->lev[iend], a, b, c->V, kind);
+    k_src_inject<<<(c->src.npts + 127) / 128, 128, 0, c->st>>>(c->src, it, istage, c->lev[itmp] + sh, c->lev[iend] + sh, a, b, c->V, kind);
     nl++;
   }
   c->total_launches += nl;
@@ -469,25 +559,25 @@ extern "C" int cgfd_b200_run(cgfd_b200_ctx *c, int it0, int nsteps)
         // (forward/drv_rk_curv_col.c:193-199, 308-312, 448-469)
         const int np = (s != CGFD_NUM_STAGES - 1) ? ipair : (it + 1) % CGFD_NUM_PAIRS;
         const int ns = (s != CGFD_NUM_STAGES - 1) ? s + 1 : 0;
-        float *w = (s != CGFD_NUM_STAGES - 1) ? c->lev[itmp] : c->lev[c->iend];
+        float *w = ((s != CGFD_NUM_STAGES - 1) ? c->lev[itmp] : c->lev[c->iend]) + c->shift;
         if (halo_exchange(c->halo, w, c->fd.dir[np][ns][0], c->fd.dir[np][ns][1], c->st)) return fail(halo_error());
         c->total_launches += halo_launches_per_exchange(c->halo);
       }
     }
-    float *wnew = c->lev[c->iend], *wold = c->lev[c->ipre];
+    float *wnew = c->lev[c->iend] + c->shift, *wold = c->lev[c->ipre] + c->shift;
     const cgfd_grid_t &g = c->g;
     if (c->ablexp) {
       for (int n = 0; n < 6; n++) {
         const int *B = c->ablexp_blk[n];
         if (!B[0]) continue;
         dim3 blk(64), grd((B[2] - B[1] + 64) / 64, B[4] - B[3] + 1, B[6] - B[5] + 1);
-        k_ablexp<<<grd, blk, 0, c->st>>>(wnew, c->V, c->ncmp, g.nx, g.ny, B[1], B[2], B[3], B[4], B[5], B[6], c->Ex, c->Ey, c->Ez);
+        k_ablexp<<<grd, blk, 0, c->st>>>(wnew, c->V, c->ncmp, c->PX, g.ny, B[1], B[2], B[3], B[4], B[5], B[6], c->Ex, c->Ey, c->Ez);
         c->total_launches++;
       }
     }
     if (c->free_top) {
       dim3 blk(128), grd((g.ni2 - g.ni1 + 128) / 128, g.nj2 - g.nj1 + 1);
-      k_pg<<<grd, blk, 0, c->st>>>(wnew, wold, c->V, g.nx, g.ny, g.ni1, g.ni2, g.nj1, g.nj2, g.nk2, dt, c->PG, c->Dis);
+      k_pg<<<grd, blk, 0, c->st>>>(wnew, wold, c->V, c->PX, g.nx, g.ny, g.ni1, g.ni2, g.nj1, g.nj2, g.nk2, dt, c->PG, c->Dis);
       c->total_launches++;
     }
     if (c->nrec > 0 && c->rec_count < c->rec_max_nt) {
@@ -514,10 +604,11 @@ extern "C" int cgfd_b200_onestage(cgfd_b200_ctx *c, int it, int ipair, int istag
 {
   CK(cudaSetDevice(c->device));
   const size_t nb = c->V * c->ncmp * sizeof(float);
+  const int sh = c->shift;
   // rhs = 0 + 1*L(w_cur): the stage update with w_pre := 0, a := 1, b := 0. Uses the level buffers as
   // scratch (the context's wavefield is overwritten; PML aux level n is preserved).
   const int icur = c->ia, iout = c->ib, izero = c->iend, iz2 = c->ipre;
-  CK(cudaMemcpyAsync(c->lev[icur], w_cur, nb, cudaMemcpyHostToDevice, c->st));
+  if (copy_in3d(c, c->lev[icur], w_cur, c->ncmp, c->st)) return 1;
   CK(cudaMemsetAsync(c->lev[iout], 0, nb, c->st));
   CK(cudaMemsetAsync(c->lev[izero], 0, nb, c->st));
   CK(cudaMemsetAsync(c->lev[iz2], 0, nb, c->st));
@@ -532,7 +623,12 @@ extern "C" int cgfd_b200_onestage(cgfd_b200_ctx *c, int it, int ipair, int istag
   }
   StageArgs P;
   fill_args(c, P);
-  P.cur = c->lev[icur]; P.pre = c->lev[iz2]; P.tmp = c->lev[iout]; P.end = c->lev[izero];
+  P.cur = c->lev[icur] + sh; P.pre = c->lev[iz2] + sh; P.tmp = c->lev[iout] + sh; P.end = c->lev[izero] + sh;
+  TmaMaps maps;
+  if (c->have_maps) {
+    maps.cur = c->map_halo[icur]; maps.pre = c->map_cen[iz2]; maps.end = c->map_cen[izero];
+    maps.met = c->map_met; maps.med = c->map_med;
+  }
   // aux: cur = copy of level n, pre = zeros, tmp = out, end = scratch
   // run_stage sets aux pointers from level indices; patch aux_pre to the zero buffer afterwards is not
   // possible through indices, so do it by hand here.
@@ -545,16 +641,16 @@ extern "C" int cgfd_b200_onestage(cgfd_b200_ctx *c, int it, int ipair, int istag
   }
   int nl = 0;
   if (c->has_surf) {
-    CK(cudaMemsetAsync(c->srcslice, 0, c->slice * 6 * sizeof(float), c->st));
-    k_src_surface<<<(c->src.nsurf_pts + 127) / 128, 128, 0, c->st>>>(c->src, it, istage, c->srcslice, c->srcslice + c->slice,
-        c->srcslice + 2 * c->slice, c->srcslice + 3 * c->slice, c->srcslice + 4 * c->slice, c->srcslice + 5 * c->slice);
+    CK(cudaMemsetAsync(c->srcslice, 0, c->hslice * 6 * sizeof(float), c->st));
+    k_src_surface<<<(c->src.nsurf_pts + 127) / 128, 128, 0, c->st>>>(c->src, it, istage, c->srcslice, c->srcslice + c->hslice,
+        c->srcslice + 2 * c->hslice, c->srcslice + 3 * c->hslice, c->srcslice + 4 * c->hslice, c->srcslice + 5 * c->hslice);
   }
   const int *dir = c->fd.dir[ipair][istage];
-  launch_iso_stage(P, dir[0], dir[1], dir[2], KIND_MID, c->variant, c->st, nullptr, nullptr, &nl);
+  launch_iso_stage(P, c->have_maps ? &maps : nullptr, dir[0], dir[1], dir[2], KIND_MID, c->variant, c->zchunk, c->st, nullptr, nullptr, &nl);
   if (c->has_src)
-    k_src_inject<<<(c->src.npts + 127) / 128, 128, 0, c->st>>>(c->src, it, istage, c->lev[iout], c->lev[izero], 1.0f, 0.0f, c->V, KIND_MID);
+    k_src_inject<<<(c->src.npts + 127) / 128, 128, 0, c->st>>>(c->src, it, istage, c->lev[iout] + sh, c->lev[izero] + sh, 1.0f, 0.0f, c->V, KIND_MID);
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(rhs, c->lev[iout], nb, cudaMemcpyDeviceToHost, c->st));
+  if (copy_out3d(c, rhs, c->lev[iout], c->ncmp, c->st)) return 1;
   CK(cudaStreamSynchronize(c->st));
   // leave a clean state: wavefield levels zero
   CK(cudaMemsetAsync(c->lev[icur], 0, nb, c->st));
@@ -569,8 +665,10 @@ extern "C" int cgfd_b200_set_record_points(cgfd_b200_ctx *c, int n, const int64_
   CK(cudaSetDevice(c->device));
   c->nrec = 0; c->rec_count = 0;
   if (n <= 0) return 0;
-  for (int i = 0; i < n; i++) if (iptr[i] < 0 || (size_t)iptr[i] >= c->V) return fail("set_record_points: index out of range");
-  if (upload(c, &c->rec_iptr, iptr, n)) return 1;
+  for (int i = 0; i < n; i++) if (iptr[i] < 0 || (size_t)iptr[i] >= c->hV) return fail("set_record_points: index out of range");
+  std::vector<int64_t> dv(n);
+  for (int i = 0; i < n; i++) dv[i] = dev_index(c, iptr[i]);
+  if (upload(c, &c->rec_iptr, dv.data(), n)) return 1;
   if (upload(c, &c->rec, (const float *)nullptr, (size_t)n * c->ncmp * max_nt)) return 1;
   c->nrec = n; c->rec_max_nt = max_nt;
   return 0;
@@ -597,7 +695,7 @@ extern "C" int cgfd_b200_get_box(cgfd_b200_ctx *c, int icmp, int i1, int ni, int
     CK(cudaMalloc((void **)&c->boxbuf, tot * sizeof(float)));
     c->boxcap = tot;
   }
-  k_pack_box<<<(unsigned)((tot + 255) / 256), 256, 0, c->st>>>(c->lev[c->ipre] + (size_t)icmp * c->V, g.nx, g.ny, i1, ni, di, j1, nj,
+  k_pack_box<<<(unsigned)((tot + 255) / 256), 256, 0, c->st>>>(c->lev[c->ipre] + c->shift + (size_t)icmp * c->V, c->PX, g.ny, i1, ni, di, j1, nj,
                                                               dj, k1, nk, dk, c->boxbuf);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, c->boxbuf, tot * sizeof(float), cudaMemcpyDeviceToHost, c->st));
@@ -609,7 +707,7 @@ extern "C" int cgfd_b200_get_pg(cgfd_b200_ctx *c, float *pg)
   if (!c->PG) return fail("get_pg: no free surface");
   CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->st));
-  CK(cudaMemcpy(pg, c->PG, c->slice * 15 * sizeof(float), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(pg, c->PG, c->hslice * 15 * sizeof(float), cudaMemcpyDeviceToHost));
   return 0;
 }
 
@@ -623,7 +721,7 @@ extern "C" int cgfd_b200_comm_init(cgfd_b200_ctx *c, const char id[128], int ran
 {
   CK(cudaSetDevice(c->device));
   if (c->halo) return fail("comm_init: already initialised");
-  c->halo = halo_create(id, rank, nranks, c->neigh, c->g, c->ncmp, c->V, c->st);
+  c->halo = halo_create(id, rank, nranks, c->neigh, c->g, c->ncmp, c->V, c->PX, c->st);
   if (!c->halo) return fail(halo_error());
   return 0;
 }

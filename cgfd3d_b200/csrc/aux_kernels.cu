@@ -78,14 +78,14 @@ __global__ void k_pack_box(const float *w, int nx, int ny, int i1, int ni, int d
 }
 
 // PGV / PGA / PGD maps on the free surface (PG_calcu, forward/wav_t.c:379-455)
-__global__ void k_pg(const float *w_new, const float *w_old, size_t V, int nx, int ny, int ni1, int ni2, int nj1, int nj2,
-                     int nk2, float dt, float *PG, float *Dis)
+__global__ void k_pg(const float *w_new, const float *w_old, size_t V, int pitch, int nx, int ny, int ni1, int ni2, int nj1,
+                     int nj2, int nk2, float dt, float *PG, float *Dis)
 {
   int i = ni1 + blockIdx.x * blockDim.x + threadIdx.x;
   int j = nj1 + blockIdx.y;
   if (i > ni2 || j > nj2) return;
-  const size_t sl = (size_t)nx * ny;
-  const size_t p = (size_t)nk2 * sl + (size_t)j * nx + i, p1 = (size_t)j * nx + i;
+  const size_t sl = (size_t)nx * ny;   // unpadded 2-D maps
+  const size_t p = ((size_t)nk2 * ny + j) * pitch + i, p1 = (size_t)j * nx + i;
   const float vx1 = w_new[p], vy1 = w_new[V + p], vz1 = w_new[2 * V + p];
   const float vx0 = w_old[p], vy0 = w_old[V + p], vz0 = w_old[2 * V + p];
   const float Ax = fabsf((vx1 - vx0) / dt), Ay = fabsf((vy1 - vy0) / dt), Az = fabsf((vz1 - vz0) / dt);

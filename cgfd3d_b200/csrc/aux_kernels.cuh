@@ -26,8 +26,8 @@ __global__ void k_src_surface(SrcDev S, int it, int istage, float *Tx, float *Ty
 __global__ void k_record(const float *w, size_t V, int ncmp, int npts, const int64_t *iptr, float *rec_it);
 __global__ void k_pack_box(const float *w, int nx, int ny, int i1, int ni, int di, int j1, int nj, int dj, int k1, int nk,
                            int dk, float *out);
-__global__ void k_pg(const float *w_new, const float *w_old, size_t V, int nx, int ny, int ni1, int ni2, int nj1, int nj2,
-                     int nk2, float dt, float *PG, float *Dis);
+__global__ void k_pg(const float *w_new, const float *w_old, size_t V, int pitch, int nx, int ny, int ni1, int ni2, int nj1,
+                     int nj2, int nk2, float dt, float *PG, float *Dis);
 __global__ void k_ablexp(float *w, size_t V, int ncmp, int nx, int ny, int i1, int i2, int j1, int j2, int k1, int k2,
                          const float *Ex, const float *Ey, const float *Ez);
 __global__ void k_halo_copy(float *w, float *buf, size_t V, int ncmp, int nx, int ny, int i1, int ni, int j1, int nj, int k1,

@@ -2,6 +2,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 namespace cgfd {
@@ -38,12 +39,18 @@ struct PmlFaceDev {
   float *aux_end;               // accumulating level n+1
 };
 
+// Device arrays keep the reference's [nz][ny][nx] order but with a padded x pitch: every row starts
+// `shift` floats into a pitch that is a multiple of 32 floats, so that the first physical point
+// (i = ni1) of every row sits on a 128-byte boundary. All 3-D base pointers handed to the kernels
+// are already advanced by `shift`, i.e. they are indexed with the reference's own (i,j,k).
+// 2-D per-surface-point arrays (matrices, source slices, PG maps) are unpadded [ny][nx].
 struct StageArgs {
-  int nx, ny, nz;
+  int nx, ny, nz;               // logical extents incl. ghosts
+  int shift;                    // x offset of index 0 inside a padded row
   int ni1, ni2, nj1, nj2, nk1, nk2;
   int kbeg, kend;               // rows handled by this launch, inclusive
   int zchunk;                   // rows per block along z (main kernel)
-  size_t siz_line, siz_slice, siz_vol;
+  size_t siz_line, siz_slice, siz_vol;   // padded pitch, pitch*ny, pitch*ny*nz
   const float *cur;             // w_cur  [ncmp][nz][ny][nx]
   const float *pre;             // w_pre
   float *tmp;                   // w_tmp written for the next stage
@@ -60,8 +67,19 @@ struct StageArgs {
   const float *TxSrc, *TySrc, *TzSrc, *VxSrc, *VySrc, *VzSrc;  // [ny][nx] or nullptr (== 0)
 };
 
+// tensor maps of one stage launch (TMA variant of the interior kernel)
+struct TmaMaps {
+  CUtensorMap cur;   // w_cur, box (TX+4, TY+4, 1, 9)
+  CUtensorMap met;   // xi_x..zeta_z, box (TX, TY, 1, 9)
+  CUtensorMap med;   // media, box (TX, TY, 1, nmedia)
+  CUtensorMap pre;   // w_pre, box (TX, TY, 1, 9)
+  CUtensorMap end;   // w_end, box (TX, TY, 1, 9)
+};
+
 // launchers (kernels_*.cu); dir = direction index per axis of this stage's operator
-void launch_iso_stage(const StageArgs &P, int dx, int dy, int dz, int kind, int variant, cudaStream_t st,
-                      cudaEvent_t ev0, cudaEvent_t ev1, int *nlaunch);
+void launch_iso_stage(const StageArgs &P, const TmaMaps *maps, int dx, int dy, int dz, int kind, int variant, int zchunk,
+                      cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1, int *nlaunch);
+int iso_kernels_init();   // one-time function attributes (dynamic shared memory)
+constexpr int TILE_X = 32, TILE_Y = 8;
 
 }  // namespace cgfd

@@ -54,6 +54,7 @@ struct HaloComm {
   cgfd_grid_t g;
   int ncmp = 9;
   size_t V = 0;
+  int pitch = 0;   // padded x pitch of the device arrays
   float *sbuf[4] = {nullptr, nullptr, nullptr, nullptr};
   float *rbuf[4] = {nullptr, nullptr, nullptr, nullptr};
   size_t plane[4];    // floats per exchanged plane per side
@@ -69,12 +70,12 @@ int halo_unique_id(char id[128])
 }
 
 HaloComm *halo_create(const char id[128], int rank, int nranks, const int neigh[4], const cgfd_grid_t &g, int ncmp, size_t V,
-                      cudaStream_t st)
+                      int pitch, cudaStream_t st)
 {
   (void)st;
   if (load_nccl()) return nullptr;
   HaloComm *h = new HaloComm();
-  h->rank = rank; h->nranks = nranks; h->g = g; h->ncmp = ncmp; h->V = V;
+  h->rank = rank; h->nranks = nranks; h->g = g; h->ncmp = ncmp; h->V = V; h->pitch = pitch;
   for (int n = 0; n < 4; n++) h->neigh[n] = neigh[n];
   ncclUniqueId u;
   memcpy(u.internal, id, 128);
@@ -127,7 +128,7 @@ int halo_exchange(HaloComm *h, float *w, int dirx, int diry, cudaStream_t st)
     const int wni = (s < 2) ? send_w[s] : ni, wnj = (s < 2) ? nj : send_w[s];
     cnt_s[s] = (size_t)wni * wnj * nk * h->ncmp;
     cnt_r[s] = (size_t)((s < 2) ? recv_w[s] : ni) * ((s < 2) ? nj : recv_w[s]) * nk * h->ncmp;
-    k_halo_copy<<<(unsigned)((cnt_s[s] + 255) / 256), 256, 0, st>>>(w, h->sbuf[s], h->V, h->ncmp, g.nx, g.ny, send_i1[s], wni,
+    k_halo_copy<<<(unsigned)((cnt_s[s] + 255) / 256), 256, 0, st>>>(w, h->sbuf[s], h->V, h->ncmp, h->pitch, g.ny, send_i1[s], wni,
                                                                    send_j1[s], wnj, g.nk1, nk, 0);
   }
   NC(g_nccl.GroupStart());
@@ -140,7 +141,7 @@ int halo_exchange(HaloComm *h, float *w, int dirx, int diry, cudaStream_t st)
   for (int s = 0; s < 4; s++) {
     if (h->neigh[s] < 0) continue;
     const int wni = (s < 2) ? recv_w[s] : ni, wnj = (s < 2) ? nj : recv_w[s];
-    k_halo_copy<<<(unsigned)((cnt_r[s] + 255) / 256), 256, 0, st>>>(w, h->rbuf[s], h->V, h->ncmp, g.nx, g.ny, recv_i1[s], wni,
+    k_halo_copy<<<(unsigned)((cnt_r[s] + 255) / 256), 256, 0, st>>>(w, h->rbuf[s], h->V, h->ncmp, h->pitch, g.ny, recv_i1[s], wni,
                                                                    recv_j1[s], wnj, g.nk1, nk, 1);
   }
   if (cudaGetLastError() != cudaSuccess) { g_herr = "halo kernels failed to launch"; return 1; }

@@ -9,7 +9,7 @@ struct HaloComm;
 const char *halo_error();
 int halo_unique_id(char id[128]);
 HaloComm *halo_create(const char id[128], int rank, int nranks, const int neigh[4], const cgfd_grid_t &g, int ncmp, size_t V,
-                      cudaStream_t st);
+                      int pitch, cudaStream_t st);
 void halo_destroy(HaloComm *h);
 // refresh the ghosts of level w for an operator with direction indices (dirx, diry)
 int halo_exchange(HaloComm *h, float *w, int dirx, int diry, cudaStream_t st);

@@ -1,16 +1,21 @@
 // Isotropic elastic RHS + CFS-PML + free surface + RK stage update, one fused pass per stage.
 //
-//   k_iso_main : all rows below the free-surface rows. One thread per (i,j) column marching along
-//                z with a 5-deep register queue per component; the current x-y plane of the 9
-//                components sits in a double-buffered shared-memory tile (one barrier per plane).
+//   k_iso_main_tma : all rows below the free-surface rows (default). One thread per (i,j) column of a
+//                32x8 tile marching along z. Every operand of a plane -- the 9 wavefield components with
+//                their x-y halo, 9 metric and 3 media arrays, w_pre and w_end -- is brought into a
+//                2-stage shared-memory ring by TMA (cp.async.bulk.tensor, one elected thread, mbarrier
+//                completion), two planes ahead of the arithmetic; the zeta stencil lives in a 5-deep
+//                register queue per component that is rotated by unrolling, not by moves.
 //                Restates sv_curv_col_el_iso_rhs_inner (forward/sv_curv_col_el_iso.c:208-441),
 //                sv_curv_col_el_iso_rhs_cfspml (:644-1146) and the RK axpy loops of
 //                forward/drv_rk_curv_col.c:292-446 without ever writing the RHS to memory.
+//   k_iso_main : the same pass with plain loads (LDG -> shared tile), kept as variant 1 for A/B runs.
 //   k_iso_top  : the top four rows when the top is a free surface: traction-image momentum RHS
 //                (sv_curv_col_el_rhs_timg_z2, forward/sv_curv_col_el.c:30-305), reduced-order /
 //                matrix Dz for the stress RHS (sv_curv_col_el_iso_rhs_vlow_z2, iso.c:451-634),
 //                PML with its free-surface terms, RK update.
 #include "physics.cuh"
+#include "tma.cuh"
 
 namespace cgfd {
 
@@ -22,11 +27,14 @@ template <int D> struct Ofs {            // stencil offsets of direction index D
   static constexpr int right = D ? 1 : 3;
 };
 
-constexpr int TX = 32, TY = 8;
+constexpr int TX = TILE_X, TY = TILE_Y;
 constexpr int SX = TX + 4, SY = TY + 4;
 constexpr int NHALO = 4 * TY + 4 * TX;          // halo cells per component per plane
 constexpr int NSLOT = (9 * NHALO + TX * TY - 1) / (TX * TY);
 
+// =============================================================================================
+// variant 1: plain loads
+// =============================================================================================
 template <int DX, int DY, int DZ, int KIND>
 __global__ void __launch_bounds__(TX *TY, 2) k_iso_main(const StageArgs P)
 {
@@ -42,7 +50,7 @@ __global__ void __launch_bounds__(TX *TY, 2) k_iso_main(const StageArgs P)
   const bool active = (i <= P.ni2) && (j <= P.nj2);
   const size_t pij = (size_t)j * P.siz_line + i;
 
-  // halo slots of this thread: offset inside one x-y plane (+ component) and inside the smem tile
+  // halo slots of this thread: offset inside one x-y plane and inside the smem tile (+ component)
   int hg[NSLOT], hs[NSLOT];
 #pragma unroll
   for (int q = 0; q < NSLOT; q++) {
@@ -56,11 +64,8 @@ __global__ void __launch_bounds__(TX *TY, 2) k_iso_main(const StageArgs P)
       int gi = i0 - XL + sx, gj = j0 - YL + sy;
       if (gi < P.nx && gj < P.ny) {
         hg[q] = gj * (int)P.siz_line + gi;   // plane offset < 2^31
-        hs[q] = (c * SY + sy) * SX + sx;
+        hs[q] = ((c * SY + sy) * SX + sx) | (c << 24);
       }
-      // component stride added at use
-      hg[q] = (hg[q] < 0) ? -1 : hg[q];
-      if (hg[q] >= 0) hs[q] |= (c << 24);
     }
   }
 
@@ -72,13 +77,12 @@ __global__ void __launch_bounds__(TX *TY, 2) k_iso_main(const StageArgs P)
       for (int n = 0; n < 4; n++)
         q[c][n] = __ldg(P.cur + c * P.siz_vol + (size_t)(k0 - ZB + n) * P.siz_slice + pij);
   }
-
-  // per-thread PML membership along x and y is fixed for the whole column
   const float *cx = c_fd.coef[DX], *cy = c_fd.coef[DY], *cz = c_fd.coef[DZ];
 
   for (int k = k0; k <= k1; k++) {
     const int buf = k & 1;
     const size_t pk = (size_t)k * P.siz_slice;
+    const size_t p = pk + pij;
     if (inarr) {
 #pragma unroll
       for (int c = 0; c < 9; c++) {
@@ -93,10 +97,18 @@ __global__ void __launch_bounds__(TX *TY, 2) k_iso_main(const StageArgs P)
         (&s[buf][0][0][0])[hs[n] & 0xffffff] = __ldg(P.cur + c * P.siz_vol + pk + hg[n]);
       }
     }
+    // operands of the epilogue, requested before the barrier so that they are in flight during the arithmetic
+    float pv[9], ev[9];
+    if (active) {
+#pragma unroll
+      for (int c = 0; c < 9; c++) {
+        if (KIND == KIND_MID) pv[c] = __ldg(P.pre + c * P.siz_vol + p);
+        if (KIND != KIND_FIRST) ev[c] = P.end[c * P.siz_vol + p];
+      }
+    }
     __syncthreads();
 
     if (active) {
-      const size_t p = pk + pij;
       Deriv d;
 #pragma unroll
       for (int c = 0; c < 9; c++) {
@@ -112,12 +124,13 @@ __global__ void __launch_bounds__(TX *TY, 2) k_iso_main(const StageArgs P)
       const float lam = __ldg(P.media[0] + p), mu = __ldg(P.media[1] + p), slw = __ldg(P.media[2] + p);
       const float lam2mu = lam + 2.0f * mu;
       float h[9];
-      momentum(d, m, slw, h);
       hooke_iso(d, m, lam, mu, lam2mu, h);
-      pml_all_iso<KIND>(P, i, j, k, d, m, lam, mu, lam2mu, slw, h);
+      pml_all_iso<KIND, 0>(P, i, j, k, d, m, lam, mu, lam2mu, slw, h);
+      momentum(d, m, slw, h);
+      pml_all_iso<KIND, 1>(P, i, j, k, d, m, lam, mu, lam2mu, slw, h);
 #pragma unroll
       for (int c = 0; c < 9; c++)
-        rk_update<KIND>(P.pre, P.tmp, P.end, c * P.siz_vol + p, q[c][ZB], h[c], P.a, P.b);
+        rk_store<KIND>(P.tmp, P.end, c * P.siz_vol + p, q[c][ZB], pv[c], ev[c], h[c], P.a, P.b);
     }
 #pragma unroll
     for (int c = 0; c < 9; c++) {
@@ -126,9 +139,168 @@ __global__ void __launch_bounds__(TX *TY, 2) k_iso_main(const StageArgs P)
   }
 }
 
-// ---------------------------------------------------------------------------------------------
+// =============================================================================================
+// default: TMA-fed shared-memory ring
+// =============================================================================================
+constexpr int NST = 2;                               // ring depth (planes in flight per block)
+constexpr int CEN_BYTES = TX * TY * 4;               // one centre tile of one array
+constexpr int CUR_BYTES = 9 * SY * SX * 4;           // 9 components with halo
+constexpr int OFF_CUR = 0;
+constexpr int OFF_MET = ((CUR_BYTES + 127) / 128) * 128;
+constexpr int OFF_MED = OFF_MET + 9 * CEN_BYTES;
+constexpr int OFF_PRE = OFF_MED + 3 * CEN_BYTES;
+constexpr int OFF_END = OFF_PRE + 9 * CEN_BYTES;
+constexpr int STAGE_BYTES = OFF_END + 9 * CEN_BYTES;
+constexpr int TMA_SMEM_BYTES = NST * STAGE_BYTES + 128 /*alignment slack*/ + 64 /*barriers*/;
+
+template <int KIND> __device__ __forceinline__ constexpr uint32_t stage_tx_bytes()
+{
+  return CUR_BYTES + 12 * CEN_BYTES + (KIND == KIND_MID ? 9 * CEN_BYTES : 0) + (KIND != KIND_FIRST ? 9 * CEN_BYTES : 0);
+}
+
+struct TmaCtx {
+  unsigned char *ring;
+  uint64_t *full;
+  int tx, ty, t, i, j, i0, j0, k1;
+  bool active, inarr;
+  size_t pij;
+};
+
+template <int DX, int DY, int KIND>
+__device__ __forceinline__ void tma_issue(const StageArgs &P, const TmaMaps &M, const TmaCtx &C, int kk, int s)
+{
+  constexpr int XL = Ofs<DX>::left, YL = Ofs<DY>::left;
+  unsigned char *b = C.ring + s * STAGE_BYTES;
+  uint64_t *bar = C.full + s;
+  mbar_expect_tx(bar, stage_tx_bytes<KIND>());
+  tma_load_4d(b + OFF_CUR, &M.cur, bar, C.i0 - XL + P.shift, C.j0 - YL, kk, 0);
+  tma_load_4d(b + OFF_MET, &M.met, bar, C.i0 + P.shift, C.j0, kk, 0);
+  tma_load_4d(b + OFF_MED, &M.med, bar, C.i0 + P.shift, C.j0, kk, 0);
+  if (KIND == KIND_MID) tma_load_4d(b + OFF_PRE, &M.pre, bar, C.i0 + P.shift, C.j0, kk, 0);
+  if (KIND != KIND_FIRST) tma_load_4d(b + OFF_END, &M.end, bar, C.i0 + P.shift, C.j0, kk, 0);
+}
+
+// one plane: qa..qd hold the zeta neighbours k-ZB .. k-ZB+3, qe receives k+ZA (already fetched into qn)
+template <int DX, int DY, int DZ, int KIND>
+__device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, const TmaCtx &C, int k, int it,
+                                          const float (&qa)[9], const float (&qb)[9], const float (&qc)[9],
+                                          const float (&qd)[9], float (&qe)[9], float (&qn)[9])
+{
+  constexpr int XL = Ofs<DX>::left, YL = Ofs<DY>::left, ZA = Ofs<DZ>::right;
+  constexpr int FX = Ofs<DX>::first, FY = Ofs<DY>::first;
+  const int s = it % NST;
+  const uint32_t parity = (it / NST) & 1;
+  const float *cx = c_fd.coef[DX], *cy = c_fd.coef[DY], *cz = c_fd.coef[DZ];
+#pragma unroll
+  for (int c = 0; c < 9; c++) qe[c] = qn[c];
+  if (C.inarr && k + 1 <= C.k1) {
+#pragma unroll
+    for (int c = 0; c < 9; c++) qn[c] = __ldg(P.cur + c * P.siz_vol + (size_t)(k + 1 + ZA) * P.siz_slice + C.pij);
+  }
+  mbar_wait(C.full + s, parity);
+  if (C.active) {
+    const unsigned char *b = C.ring + s * STAGE_BYTES;
+    const float *sc = (const float *)(b + OFF_CUR) + (C.ty + YL) * SX + C.tx + XL;
+    const float *sm = (const float *)(b + OFF_MET) + C.t;
+    const float *sd = (const float *)(b + OFF_MED) + C.t;
+    const float *sp = (const float *)(b + OFF_PRE) + C.t;
+    const float *se = (const float *)(b + OFF_END) + C.t;
+    const float(&qz)[9] = DZ ? qd : qb;   // centre plane of the queue
+    const size_t p = (size_t)k * P.siz_slice + C.pij;
+    Met m;
+    m.xix = sm[0 * TX * TY]; m.xiy = sm[1 * TX * TY]; m.xiz = sm[2 * TX * TY];
+    m.etx = sm[3 * TX * TY]; m.ety = sm[4 * TX * TY]; m.etz = sm[5 * TX * TY];
+    m.ztx = sm[6 * TX * TY]; m.zty = sm[7 * TX * TY]; m.ztz = sm[8 * TX * TY];
+    const float lam = sd[0], mu = sd[TX * TY], slw = sd[2 * TX * TY];
+    const float lam2mu = lam + 2.0f * mu;
+    Deriv d;
+    float h[9];
+    // ---- stress half: needs the velocity derivatives only
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const float *r = sc + c * SY * SX;
+      d.x[c] = cx[0] * r[FX] + cx[1] * r[FX + 1] + cx[2] * r[FX + 2] + cx[3] * r[FX + 3] + cx[4] * r[FX + 4];
+      d.y[c] = cy[0] * r[FY * SX] + cy[1] * r[(FY + 1) * SX] + cy[2] * r[(FY + 2) * SX] + cy[3] * r[(FY + 3) * SX] + cy[4] * r[(FY + 4) * SX];
+      d.z[c] = cz[0] * qa[c] + cz[1] * qb[c] + cz[2] * qc[c] + cz[3] * qd[c] + cz[4] * qe[c];
+    }
+    hooke_iso(d, m, lam, mu, lam2mu, h);
+    pml_all_iso<KIND, 0>(P, C.i, C.j, k, d, m, lam, mu, lam2mu, slw, h);
+#pragma unroll
+    for (int c = 3; c < 9; c++)
+      rk_store<KIND>(P.tmp, P.end, c * P.siz_vol + p, qz[c], (KIND == KIND_MID) ? sp[c * TX * TY] : 0.0f,
+                     (KIND != KIND_FIRST) ? se[c * TX * TY] : 0.0f, h[c], P.a, P.b);
+    // ---- velocity half: needs the stress derivatives only
+#pragma unroll
+    for (int c = 3; c < 9; c++) {
+      const float *r = sc + c * SY * SX;
+      d.x[c] = cx[0] * r[FX] + cx[1] * r[FX + 1] + cx[2] * r[FX + 2] + cx[3] * r[FX + 3] + cx[4] * r[FX + 4];
+      d.y[c] = cy[0] * r[FY * SX] + cy[1] * r[(FY + 1) * SX] + cy[2] * r[(FY + 2) * SX] + cy[3] * r[(FY + 3) * SX] + cy[4] * r[(FY + 4) * SX];
+      d.z[c] = cz[0] * qa[c] + cz[1] * qb[c] + cz[2] * qc[c] + cz[3] * qd[c] + cz[4] * qe[c];
+    }
+    momentum(d, m, slw, h);
+    pml_all_iso<KIND, 1>(P, C.i, C.j, k, d, m, lam, mu, lam2mu, slw, h);
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+      rk_store<KIND>(P.tmp, P.end, c * P.siz_vol + p, qz[c], (KIND == KIND_MID) ? sp[c * TX * TY] : 0.0f,
+                     (KIND != KIND_FIRST) ? se[c * TX * TY] : 0.0f, h[c], P.a, P.b);
+  }
+  __syncthreads();   // every thread is done with ring slot s
+  if (C.t == 0 && k + NST <= C.k1) tma_issue<DX, DY, KIND>(P, M, C, k + NST, s);
+}
+
+template <int DX, int DY, int DZ, int KIND>
+__global__ void __launch_bounds__(TX *TY, 2) k_iso_main_tma(const StageArgs P, const __grid_constant__ TmaMaps M)
+{
+  extern __shared__ unsigned char smem_raw[];
+  constexpr int ZB = Ofs<DZ>::left, ZA = Ofs<DZ>::right;
+  TmaCtx C;
+  C.ring = (unsigned char *)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+  C.full = (uint64_t *)(C.ring + NST * STAGE_BYTES);
+  C.tx = threadIdx.x; C.ty = threadIdx.y; C.t = C.ty * TX + C.tx;
+  C.i0 = P.ni1 + blockIdx.x * TX; C.j0 = P.nj1 + blockIdx.y * TY;
+  C.i = C.i0 + C.tx; C.j = C.j0 + C.ty;
+  const int k0 = P.kbeg + blockIdx.z * P.zchunk;
+  C.k1 = min(k0 + P.zchunk - 1, P.kend);
+  C.inarr = (C.i < P.nx) && (C.j < P.ny);
+  C.active = (C.i <= P.ni2) && (C.j <= P.nj2);
+  C.pij = (size_t)C.j * P.siz_line + C.i;
+
+  if (C.t == 0) {
+#pragma unroll
+    for (int s = 0; s < NST; s++) mbar_init(C.full + s, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (C.t == 0) {
+#pragma unroll
+    for (int s = 0; s < NST; s++)
+      if (k0 + s <= C.k1) tma_issue<DX, DY, KIND>(P, M, C, k0 + s, s);
+  }
+
+  float q0[9], q1[9], q2[9], q3[9], q4[9], qn[9];
+#pragma unroll
+  for (int c = 0; c < 9; c++) { q0[c] = q1[c] = q2[c] = q3[c] = q4[c] = qn[c] = 0.0f; }
+  if (C.inarr) {
+#pragma unroll
+    for (int c = 0; c < 9; c++) {
+      const float *w = P.cur + c * P.siz_vol + (size_t)(k0 - ZB) * P.siz_slice + C.pij;
+      q0[c] = __ldg(w); q1[c] = __ldg(w + P.siz_slice); q2[c] = __ldg(w + 2 * P.siz_slice); q3[c] = __ldg(w + 3 * P.siz_slice);
+      qn[c] = __ldg(w + 4 * P.siz_slice);   // plane k0 + ZA
+    }
+  }
+  int k = k0, it = 0;
+  while (true) {
+    tma_plane<DX, DY, DZ, KIND>(P, M, C, k, it, q0, q1, q2, q3, q4, qn); if (++k > C.k1) break; ++it;
+    tma_plane<DX, DY, DZ, KIND>(P, M, C, k, it, q1, q2, q3, q4, q0, qn); if (++k > C.k1) break; ++it;
+    tma_plane<DX, DY, DZ, KIND>(P, M, C, k, it, q2, q3, q4, q0, q1, qn); if (++k > C.k1) break; ++it;
+    tma_plane<DX, DY, DZ, KIND>(P, M, C, k, it, q3, q4, q0, q1, q2, qn); if (++k > C.k1) break; ++it;
+    tma_plane<DX, DY, DZ, KIND>(P, M, C, k, it, q4, q0, q1, q2, q3, qn); if (++k > C.k1) break; ++it;
+  }
+}
+
+// =============================================================================================
 // free-surface rows: k in [nk2-3, nk2], one thread per point, neighbours straight from L1/L2
-// ---------------------------------------------------------------------------------------------
+// =============================================================================================
 template <int DX, int DY, int DZ, int KIND>
 __global__ void __launch_bounds__(128) k_iso_top(const StageArgs P)
 {
@@ -138,13 +310,18 @@ __global__ void __launch_bounds__(128) k_iso_top(const StageArgs P)
   if (i > P.ni2 || j > P.nj2 || k > P.kend) return;
   const size_t L = P.siz_line, S = P.siz_slice, V = P.siz_vol;
   const size_t p = (size_t)k * S + (size_t)j * L + i;
-  const size_t p2 = (size_t)j * L + i;
+  const size_t p2 = (size_t)j * P.nx + i;
   const float *cx = c_fd.coef[DX], *cy = c_fd.coef[DY], *cz = c_fd.coef[DZ];
   constexpr int FX = Ofs<DX>::first, FY = Ofs<DY>::first, FZ = Ofs<DZ>::first;
   const int nsurf = P.nk2 - k;   // 0 at the surface
 
   Deriv d;
-  float cur[9];
+  float cur[9], pv[9], ev[9];
+#pragma unroll
+  for (int c = 0; c < 9; c++) {
+    if (KIND == KIND_MID) pv[c] = __ldg(P.pre + c * V + p);
+    if (KIND != KIND_FIRST) ev[c] = P.end[c * V + p];
+  }
 #pragma unroll
   for (int c = 0; c < 9; c++) {
     const float *w = P.cur + c * V + p;
@@ -260,14 +437,16 @@ __global__ void __launch_bounds__(128) k_iso_top(const StageArgs P)
     }
   }
 
-  pml_all_iso<KIND>(P, i, j, k, d, m, lam, mu, lam2mu, slw, h);
+  pml_all_iso<KIND, 0>(P, i, j, k, d, m, lam, mu, lam2mu, slw, h);
+  pml_all_iso<KIND, 1>(P, i, j, k, d, m, lam, mu, lam2mu, slw, h);
 #pragma unroll
-  for (int c = 0; c < 9; c++) rk_update<KIND>(P.pre, P.tmp, P.end, c * V + p, cur[c], h[c], P.a, P.b);
+  for (int c = 0; c < 9; c++) rk_store<KIND>(P.tmp, P.end, c * V + p, cur[c], pv[c], ev[c], h[c], P.a, P.b);
 }
 
-// ---------------------------------------------------------------------------------------------
+// =============================================================================================
 template <int DX, int DY, int DZ, int KIND>
-static void launch_t(const StageArgs &P0, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1, int *nlaunch)
+static void launch_t(const StageArgs &P0, const TmaMaps *maps, int variant, int zchunk, cudaStream_t st, cudaEvent_t ev0,
+                     cudaEvent_t ev1, int *nlaunch)
 {
   StageArgs P = P0;
   const int ni = P.ni2 - P.ni1 + 1, nj = P.nj2 - P.nj1 + 1;
@@ -277,14 +456,19 @@ static void launch_t(const StageArgs &P0, cudaStream_t st, cudaEvent_t ev0, cuda
   if (P.kend >= P.kbeg) {
     const int nk = P.kend - P.kbeg + 1;
     const int bx = (ni + TX - 1) / TX, by = (nj + TY - 1) / TY;
-    // z chunks: enough blocks to fill 148 SMs x 2 resident blocks a few times over
-    int nzc = 1;
-    while (nzc < nk && (long)bx * by * nzc < 148L * 2 * 4 && nk / (nzc + 1) >= 16) nzc++;
+    int nzc;
+    if (zchunk > 0) nzc = (nk + zchunk - 1) / zchunk;
+    else {
+      // z chunks: at least ~8 waves of 148 SMs x 2 resident blocks, chunks no shorter than 24 rows
+      nzc = 1;
+      while (nzc < nk && (long)bx * by * nzc < 148L * 2 * 8 && nk / (nzc + 1) >= 24) nzc++;
+    }
     P.zchunk = (nk + nzc - 1) / nzc;
     nzc = (nk + P.zchunk - 1) / P.zchunk;
     dim3 grid(bx, by, nzc), block(TX, TY);
     if (ev0) cudaEventRecord(ev0, st);
-    k_iso_main<DX, DY, DZ, KIND><<<grid, block, 0, st>>>(P);
+    if (variant == 1 || !maps) k_iso_main<DX, DY, DZ, KIND><<<grid, block, 0, st>>>(P);
+    else k_iso_main_tma<DX, DY, DZ, KIND><<<grid, block, TMA_SMEM_BYTES, st>>>(P, *maps);
     if (ev1) cudaEventRecord(ev1, st);
     (*nlaunch)++;
   }
@@ -296,28 +480,42 @@ static void launch_t(const StageArgs &P0, cudaStream_t st, cudaEvent_t ev0, cuda
   }
 }
 
+template <int DX, int DY, int DZ, int KIND> static int set_attr_t()
+{
+  cudaError_t e = cudaFuncSetAttribute(k_iso_main_tma<DX, DY, DZ, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES);
+  if (e != cudaSuccess) return 1;
+  e = cudaFuncSetAttribute(k_iso_main_tma<DX, DY, DZ, KIND>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  return e != cudaSuccess;
+}
+template <int KIND> static int set_attr_k()
+{
+  return set_attr_t<0, 0, 0, KIND>() | set_attr_t<0, 0, 1, KIND>() | set_attr_t<0, 1, 0, KIND>() | set_attr_t<0, 1, 1, KIND>() |
+         set_attr_t<1, 0, 0, KIND>() | set_attr_t<1, 0, 1, KIND>() | set_attr_t<1, 1, 0, KIND>() | set_attr_t<1, 1, 1, KIND>();
+}
+int iso_kernels_init() { return set_attr_k<KIND_FIRST>() | set_attr_k<KIND_MID>() | set_attr_k<KIND_LAST>(); }
+
 template <int KIND>
-static void launch_k(const StageArgs &P, int dx, int dy, int dz, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, int *n)
+static void launch_k(const StageArgs &P, const TmaMaps *maps, int dx, int dy, int dz, int variant, int zchunk, cudaStream_t st,
+                     cudaEvent_t e0, cudaEvent_t e1, int *n)
 {
   switch (dx * 4 + dy * 2 + dz) {
-    case 0: launch_t<0, 0, 0, KIND>(P, st, e0, e1, n); break;
-    case 1: launch_t<0, 0, 1, KIND>(P, st, e0, e1, n); break;
-    case 2: launch_t<0, 1, 0, KIND>(P, st, e0, e1, n); break;
-    case 3: launch_t<0, 1, 1, KIND>(P, st, e0, e1, n); break;
-    case 4: launch_t<1, 0, 0, KIND>(P, st, e0, e1, n); break;
-    case 5: launch_t<1, 0, 1, KIND>(P, st, e0, e1, n); break;
-    case 6: launch_t<1, 1, 0, KIND>(P, st, e0, e1, n); break;
-    default: launch_t<1, 1, 1, KIND>(P, st, e0, e1, n); break;
+    case 0: launch_t<0, 0, 0, KIND>(P, maps, variant, zchunk, st, e0, e1, n); break;
+    case 1: launch_t<0, 0, 1, KIND>(P, maps, variant, zchunk, st, e0, e1, n); break;
+    case 2: launch_t<0, 1, 0, KIND>(P, maps, variant, zchunk, st, e0, e1, n); break;
+    case 3: launch_t<0, 1, 1, KIND>(P, maps, variant, zchunk, st, e0, e1, n); break;
+    case 4: launch_t<1, 0, 0, KIND>(P, maps, variant, zchunk, st, e0, e1, n); break;
+    case 5: launch_t<1, 0, 1, KIND>(P, maps, variant, zchunk, st, e0, e1, n); break;
+    case 6: launch_t<1, 1, 0, KIND>(P, maps, variant, zchunk, st, e0, e1, n); break;
+    default: launch_t<1, 1, 1, KIND>(P, maps, variant, zchunk, st, e0, e1, n); break;
   }
 }
 
-void launch_iso_stage(const StageArgs &P, int dx, int dy, int dz, int kind, int variant, cudaStream_t st,
-                      cudaEvent_t ev0, cudaEvent_t ev1, int *nlaunch)
+void launch_iso_stage(const StageArgs &P, const TmaMaps *maps, int dx, int dy, int dz, int kind, int variant, int zchunk,
+                      cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1, int *nlaunch)
 {
-  (void)variant;
-  if (kind == KIND_FIRST) launch_k<KIND_FIRST>(P, dx, dy, dz, st, ev0, ev1, nlaunch);
-  else if (kind == KIND_MID) launch_k<KIND_MID>(P, dx, dy, dz, st, ev0, ev1, nlaunch);
-  else launch_k<KIND_LAST>(P, dx, dy, dz, st, ev0, ev1, nlaunch);
+  if (kind == KIND_FIRST) launch_k<KIND_FIRST>(P, maps, dx, dy, dz, variant, zchunk, st, ev0, ev1, nlaunch);
+  else if (kind == KIND_MID) launch_k<KIND_MID>(P, maps, dx, dy, dz, variant, zchunk, st, ev0, ev1, nlaunch);
+  else launch_k<KIND_LAST>(P, maps, dx, dy, dz, variant, zchunk, st, ev0, ev1, nlaunch);
 }
 
 }  // namespace cgfd

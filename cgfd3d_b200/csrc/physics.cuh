@@ -23,7 +23,8 @@ __device__ __forceinline__ Met load_metric(const StageArgs &P, size_t p)
   return m;
 }
 
-// momentum equation, forward/sv_curv_col_el_iso.c:398-406 (same for every medium)
+// momentum equation, forward/sv_curv_col_el_iso.c:398-406 (same for every medium); uses the
+// stress entries of d only
 __device__ __forceinline__ void momentum(const Deriv &d, const Met &m, float slw, float *h)
 {
   h[VX] = slw * (m.xix * d.x[TXX] + m.xiy * d.x[TXY] + m.xiz * d.x[TXZ]
@@ -37,7 +38,7 @@ __device__ __forceinline__ void momentum(const Deriv &d, const Met &m, float slw
                + m.ztx * d.z[TXZ] + m.zty * d.z[TYZ] + m.ztz * d.z[TZZ]);
 }
 
-// Hooke's law, isotropic, forward/sv_curv_col_el_iso.c:409-435
+// Hooke's law, isotropic, forward/sv_curv_col_el_iso.c:409-435; uses the velocity entries of d only
 __device__ __forceinline__ void hooke_iso(const Deriv &d, const Met &m, float lam, float mu, float lam2mu, float *h)
 {
   h[TXX] = lam2mu * (m.xix * d.x[VX] + m.etx * d.y[VX] + m.ztx * d.z[VX])
@@ -58,19 +59,20 @@ __device__ __forceinline__ void hooke_iso(const Deriv &d, const Met &m, float la
 //   first : tmp = pre + a*rhs ; end  = pre + b*rhs      (w_cur == w_pre, its value is `cur_c`)
 //   mid   : tmp = pre + a*rhs ; end += b*rhs
 //   last  :                     end += b*rhs
+// pre_v / end_v are the values of w_pre / w_end at this point, fetched by the caller ahead of time
+// (first: both unused; last: pre_v unused).
 template <int KIND>
-__device__ __forceinline__ void rk_update(const float *__restrict__ pre, float *__restrict__ tmp, float *__restrict__ end,
-                                          size_t off, float cur_c, float rhs, float a, float b)
+__device__ __forceinline__ void rk_store(float *__restrict__ tmp, float *__restrict__ end, size_t off, float cur_c,
+                                         float pre_v, float end_v, float rhs, float a, float b)
 {
   if (KIND == KIND_FIRST) {
     tmp[off] = cur_c + a * rhs;
     end[off] = cur_c + b * rhs;
   } else if (KIND == KIND_MID) {
-    float pv = __ldg(pre + off);
-    tmp[off] = pv + a * rhs;
-    end[off] = end[off] + b * rhs;
+    tmp[off] = pre_v + a * rhs;
+    end[off] = end_v + b * rhs;
   } else {
-    end[off] = end[off] + b * rhs;
+    end[off] = end_v + b * rhs;
   }
 }
 
@@ -80,11 +82,15 @@ __device__ __forceinline__ void rk_update(const float *__restrict__ pre, float *
 //   h     += (B-1)*rhs_n - B*aux ;  aux_rhs = D*rhs_n - A*aux
 // with the free-surface terms at k == nk2 for x/y faces (:841-901, :989-1048), followed by the RK
 // update of the auxiliary variables (forward/drv_rk_curv_col.c:315-346, 371-402, 426-438).
-template <int AXIS, int KIND>
+// PART 0 handles the 6 stress components (needs the velocity derivatives along the normal),
+// PART 1 the 3 velocity components (needs the stress derivatives), so that a caller can finish one
+// half of the RHS before it forms the other.
+template <int AXIS, int KIND, int PART>
 __device__ __forceinline__ void pml_face_iso(const StageArgs &P, const PmlFaceDev &F, int i, int j, int k,
                                              const Deriv &d, const Met &m, float lam, float mu, float lam2mu, float slw,
                                              float *h)
 {
+  constexpr int C0 = PART ? 0 : 3, C1 = PART ? 3 : 9;
   const int ia = (AXIS == 0) ? (i - F.i1) : (AXIS == 1) ? (j - F.j1) : (k - F.k1);
   const float cA = __ldg(F.A + ia), cB = __ldg(F.B + ia), cD = __ldg(F.D + ia);
   const float cB1 = cB - 1.0f;
@@ -92,27 +98,36 @@ __device__ __forceinline__ void pml_face_iso(const StageArgs &P, const PmlFaceDe
   const float e1 = (AXIS == 0) ? m.xix : (AXIS == 1) ? m.etx : m.ztx;
   const float e2 = (AXIS == 0) ? m.xiy : (AXIS == 1) ? m.ety : m.zty;
   const float e3 = (AXIS == 0) ? m.xiz : (AXIS == 1) ? m.etz : m.ztz;
-  float r[9];
-  r[VX] = slw * (e1 * D_[TXX] + e2 * D_[TXY] + e3 * D_[TXZ]);
-  r[VY] = slw * (e1 * D_[TXY] + e2 * D_[TYY] + e3 * D_[TYZ]);
-  r[VZ] = slw * (e1 * D_[TXZ] + e2 * D_[TYZ] + e3 * D_[TZZ]);
-  r[TXX] = lam2mu * e1 * D_[VX] + lam * e2 * D_[VY] + lam * e3 * D_[VZ];
-  r[TYY] = lam * e1 * D_[VX] + lam2mu * e2 * D_[VY] + lam * e3 * D_[VZ];
-  r[TZZ] = lam * e1 * D_[VX] + lam * e2 * D_[VY] + lam2mu * e3 * D_[VZ];
-  r[TXY] = mu * (e2 * D_[VX] + e1 * D_[VY]);
-  r[TXZ] = mu * (e3 * D_[VX] + e1 * D_[VZ]);
-  r[TYZ] = mu * (e3 * D_[VY] + e2 * D_[VZ]);
-
   const size_t pa = ((size_t)(k - F.k1) * F.snj + (size_t)(j - F.j1)) * F.sni + (size_t)(i - F.i1);
+  float au[9], pv[9], ev[9];
+#pragma unroll
+  for (int c = C0; c < C1; c++) {
+    const size_t o = c * F.siz + pa;
+    au[c] = __ldg(F.aux_cur + o);
+    if (KIND == KIND_MID) pv[c] = __ldg(F.aux_pre + o);
+    if (KIND != KIND_FIRST) ev[c] = F.aux_end[o];
+  }
+  float r[9];
+  if (PART) {
+    r[VX] = slw * (e1 * D_[TXX] + e2 * D_[TXY] + e3 * D_[TXZ]);
+    r[VY] = slw * (e1 * D_[TXY] + e2 * D_[TYY] + e3 * D_[TYZ]);
+    r[VZ] = slw * (e1 * D_[TXZ] + e2 * D_[TYZ] + e3 * D_[TZZ]);
+  } else {
+    r[TXX] = lam2mu * e1 * D_[VX] + lam * e2 * D_[VY] + lam * e3 * D_[VZ];
+    r[TYY] = lam * e1 * D_[VX] + lam2mu * e2 * D_[VY] + lam * e3 * D_[VZ];
+    r[TZZ] = lam * e1 * D_[VX] + lam * e2 * D_[VY] + lam2mu * e3 * D_[VZ];
+    r[TXY] = mu * (e2 * D_[VX] + e1 * D_[VY]);
+    r[TXZ] = mu * (e3 * D_[VX] + e1 * D_[VZ]);
+    r[TYZ] = mu * (e3 * D_[VY] + e2 * D_[VZ]);
+  }
   float ar[9];
 #pragma unroll
-  for (int c = 0; c < 9; c++) {
-    float a = __ldg(F.aux_cur + c * F.siz + pa);
-    h[c] += cB1 * r[c] - cB * a;
-    ar[c] = cD * r[c] - cA * a;
+  for (int c = C0; c < C1; c++) {
+    h[c] += cB1 * r[c] - cB * au[c];
+    ar[c] = cD * r[c] - cA * au[c];
   }
-  if (AXIS < 2 && P.free_top && k == P.nk2) {
-    const float *M = ((AXIS == 0) ? P.matVx2Vz : P.matVy2Vz) + ((size_t)j * P.siz_line + i) * 9;
+  if (PART == 0 && AXIS < 2 && P.free_top && k == P.nk2) {
+    const float *M = ((AXIS == 0) ? P.matVx2Vz : P.matVy2Vz) + ((size_t)j * P.nx + i) * 9;
     float z0 = __ldg(M + 0) * D_[VX] + __ldg(M + 1) * D_[VY] + __ldg(M + 2) * D_[VZ];
     float z1 = __ldg(M + 3) * D_[VX] + __ldg(M + 4) * D_[VY] + __ldg(M + 5) * D_[VZ];
     float z2 = __ldg(M + 6) * D_[VX] + __ldg(M + 7) * D_[VY] + __ldg(M + 8) * D_[VZ];
@@ -130,40 +145,39 @@ __device__ __forceinline__ void pml_face_iso(const StageArgs &P, const PmlFaceDe
     }
   }
 #pragma unroll
-  for (int c = 0; c < 9; c++) {
-    size_t o = c * F.siz + pa;
+  for (int c = C0; c < C1; c++) {
+    const size_t o = c * F.siz + pa;
     if (KIND == KIND_FIRST) {
-      float pv = __ldg(F.aux_cur + o);
-      F.aux_tmp[o] = pv + P.a * ar[c];
-      F.aux_end[o] = pv + P.b * ar[c];
+      F.aux_tmp[o] = au[c] + P.a * ar[c];
+      F.aux_end[o] = au[c] + P.b * ar[c];
     } else if (KIND == KIND_MID) {
-      F.aux_tmp[o] = __ldg(F.aux_pre + o) + P.a * ar[c];
-      F.aux_end[o] = F.aux_end[o] + P.b * ar[c];
+      F.aux_tmp[o] = pv[c] + P.a * ar[c];
+      F.aux_end[o] = ev[c] + P.b * ar[c];
     } else {
-      F.aux_end[o] = F.aux_end[o] + P.b * ar[c];
+      F.aux_end[o] = ev[c] + P.b * ar[c];
     }
   }
 }
 
 // all PML faces a point belongs to, in the reference's face order x1,x2,y1,y2,z1,z2
-template <int KIND>
+template <int KIND, int PART>
 __device__ __forceinline__ void pml_all_iso(const StageArgs &P, int i, int j, int k, const Deriv &d, const Met &m,
                                             float lam, float mu, float lam2mu, float slw, float *h)
 {
 #pragma unroll
   for (int s = 0; s < 2; s++) {
     const PmlFaceDev &F = P.pml[0][s];
-    if (F.on && i >= F.i1 && i <= F.i2) pml_face_iso<0, KIND>(P, F, i, j, k, d, m, lam, mu, lam2mu, slw, h);
+    if (F.on && i >= F.i1 && i <= F.i2) pml_face_iso<0, KIND, PART>(P, F, i, j, k, d, m, lam, mu, lam2mu, slw, h);
   }
 #pragma unroll
   for (int s = 0; s < 2; s++) {
     const PmlFaceDev &F = P.pml[1][s];
-    if (F.on && j >= F.j1 && j <= F.j2) pml_face_iso<1, KIND>(P, F, i, j, k, d, m, lam, mu, lam2mu, slw, h);
+    if (F.on && j >= F.j1 && j <= F.j2) pml_face_iso<1, KIND, PART>(P, F, i, j, k, d, m, lam, mu, lam2mu, slw, h);
   }
 #pragma unroll
   for (int s = 0; s < 2; s++) {
     const PmlFaceDev &F = P.pml[2][s];
-    if (F.on && k >= F.k1 && k <= F.k2) pml_face_iso<2, KIND>(P, F, i, j, k, d, m, lam, mu, lam2mu, slw, h);
+    if (F.on && k >= F.k1 && k <= F.k2) pml_face_iso<2, KIND, PART>(P, F, i, j, k, d, m, lam, mu, lam2mu, slw, h);
   }
 }
 
