@@ -353,7 +353,7 @@ extern "C" int cgfd_b200_create(const cgfd_problem_t *p, int device, cgfd_b200_c
   {
     int mrc = 0;
     for (int l = 0; l < 4 && !mrc; l++) {
-      mrc |= make_map(c, &c->map_halo[l], c->lev[l], 9, TILE_X + 4, TILE_Y + 4, 9);
+      mrc |= make_map(c, &c->map_halo[l], c->lev[l], 9, TILE_X + 2 * HALO_X, TILE_Y + 4, 9);
       mrc |= make_map(c, &c->map_cen[l], c->lev[l], 9, TILE_X, TILE_Y, 9);
     }
     if (!mrc) mrc |= make_map(c, &c->map_met, c->metric_blk + c->V /* skip jac */, 9, TILE_X, TILE_Y, 9);

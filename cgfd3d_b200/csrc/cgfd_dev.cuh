@@ -69,7 +69,7 @@ struct StageArgs {
 
 // tensor maps of one stage launch (TMA variant of the interior kernel)
 struct TmaMaps {
-  CUtensorMap cur;   // w_cur, box (TX+4, TY+4, 1, 9)
+  CUtensorMap cur;   // w_cur, box (TX+2*HALO_X, TY+4, 1, 9)
   CUtensorMap met;   // xi_x..zeta_z, box (TX, TY, 1, 9)
   CUtensorMap med;   // media, box (TX, TY, 1, nmedia)
   CUtensorMap pre;   // w_pre, box (TX, TY, 1, 9)
@@ -80,6 +80,6 @@ struct TmaMaps {
 void launch_iso_stage(const StageArgs &P, const TmaMaps *maps, int dx, int dy, int dz, int kind, int variant, int zchunk,
                       cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1, int *nlaunch);
 int iso_kernels_init();   // one-time function attributes (dynamic shared memory)
-constexpr int TILE_X = 32, TILE_Y = 8;
+constexpr int TILE_X = 32, TILE_Y = 8, HALO_X = 4;
 
 }  // namespace cgfd

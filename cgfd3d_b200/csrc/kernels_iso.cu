@@ -143,8 +143,12 @@ __global__ void __launch_bounds__(TX *TY, 2) k_iso_main(const StageArgs P)
 // default: TMA-fed shared-memory ring
 // =============================================================================================
 constexpr int NST = 2;                               // ring depth (planes in flight per block)
+// TMA needs a 16-byte aligned start along x, so the halo tile carries 4 columns on either side of
+// the 32 centre columns (the operators reach at most 3): pitch 40 floats, centre at column 4.
+constexpr int HX = HALO_X;
+constexpr int SXT = TX + 2 * HX;
 constexpr int CEN_BYTES = TX * TY * 4;               // one centre tile of one array
-constexpr int CUR_BYTES = 9 * SY * SX * 4;           // 9 components with halo
+constexpr int CUR_BYTES = 9 * SY * SXT * 4;          // 9 components with halo
 constexpr int OFF_CUR = 0;
 constexpr int OFF_MET = ((CUR_BYTES + 127) / 128) * 128;
 constexpr int OFF_MED = OFF_MET + 9 * CEN_BYTES;
@@ -169,11 +173,11 @@ struct TmaCtx {
 template <int DX, int DY, int KIND>
 __device__ __forceinline__ void tma_issue(const StageArgs &P, const TmaMaps &M, const TmaCtx &C, int kk, int s)
 {
-  constexpr int XL = Ofs<DX>::left, YL = Ofs<DY>::left;
+  constexpr int YL = Ofs<DY>::left;
   unsigned char *b = C.ring + s * STAGE_BYTES;
   uint64_t *bar = C.full + s;
   mbar_expect_tx(bar, stage_tx_bytes<KIND>());
-  tma_load_4d(b + OFF_CUR, &M.cur, bar, C.i0 - XL + P.shift, C.j0 - YL, kk, 0);
+  tma_load_4d(b + OFF_CUR, &M.cur, bar, C.i0 - HX + P.shift, C.j0 - YL, kk, 0);
   tma_load_4d(b + OFF_MET, &M.met, bar, C.i0 + P.shift, C.j0, kk, 0);
   tma_load_4d(b + OFF_MED, &M.med, bar, C.i0 + P.shift, C.j0, kk, 0);
   if (KIND == KIND_MID) tma_load_4d(b + OFF_PRE, &M.pre, bar, C.i0 + P.shift, C.j0, kk, 0);
@@ -186,7 +190,7 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
                                           const float (&qa)[9], const float (&qb)[9], const float (&qc)[9],
                                           const float (&qd)[9], float (&qe)[9], float (&qn)[9])
 {
-  constexpr int XL = Ofs<DX>::left, YL = Ofs<DY>::left, ZA = Ofs<DZ>::right;
+  constexpr int YL = Ofs<DY>::left, ZA = Ofs<DZ>::right;
   constexpr int FX = Ofs<DX>::first, FY = Ofs<DY>::first;
   const int s = it % NST;
   const uint32_t parity = (it / NST) & 1;
@@ -200,7 +204,7 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
   mbar_wait(C.full + s, parity);
   if (C.active) {
     const unsigned char *b = C.ring + s * STAGE_BYTES;
-    const float *sc = (const float *)(b + OFF_CUR) + (C.ty + YL) * SX + C.tx + XL;
+    const float *sc = (const float *)(b + OFF_CUR) + (C.ty + YL) * SXT + C.tx + HX;
     const float *sm = (const float *)(b + OFF_MET) + C.t;
     const float *sd = (const float *)(b + OFF_MED) + C.t;
     const float *sp = (const float *)(b + OFF_PRE) + C.t;
@@ -218,9 +222,9 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
     // ---- stress half: needs the velocity derivatives only
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-      const float *r = sc + c * SY * SX;
+      const float *r = sc + c * SY * SXT;
       d.x[c] = cx[0] * r[FX] + cx[1] * r[FX + 1] + cx[2] * r[FX + 2] + cx[3] * r[FX + 3] + cx[4] * r[FX + 4];
-      d.y[c] = cy[0] * r[FY * SX] + cy[1] * r[(FY + 1) * SX] + cy[2] * r[(FY + 2) * SX] + cy[3] * r[(FY + 3) * SX] + cy[4] * r[(FY + 4) * SX];
+      d.y[c] = cy[0] * r[FY * SXT] + cy[1] * r[(FY + 1) * SXT] + cy[2] * r[(FY + 2) * SXT] + cy[3] * r[(FY + 3) * SXT] + cy[4] * r[(FY + 4) * SXT];
       d.z[c] = cz[0] * qa[c] + cz[1] * qb[c] + cz[2] * qc[c] + cz[3] * qd[c] + cz[4] * qe[c];
     }
     hooke_iso(d, m, lam, mu, lam2mu, h);
@@ -232,9 +236,9 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
     // ---- velocity half: needs the stress derivatives only
 #pragma unroll
     for (int c = 3; c < 9; c++) {
-      const float *r = sc + c * SY * SX;
+      const float *r = sc + c * SY * SXT;
       d.x[c] = cx[0] * r[FX] + cx[1] * r[FX + 1] + cx[2] * r[FX + 2] + cx[3] * r[FX + 3] + cx[4] * r[FX + 4];
-      d.y[c] = cy[0] * r[FY * SX] + cy[1] * r[(FY + 1) * SX] + cy[2] * r[(FY + 2) * SX] + cy[3] * r[(FY + 3) * SX] + cy[4] * r[(FY + 4) * SX];
+      d.y[c] = cy[0] * r[FY * SXT] + cy[1] * r[(FY + 1) * SXT] + cy[2] * r[(FY + 2) * SXT] + cy[3] * r[(FY + 3) * SXT] + cy[4] * r[(FY + 4) * SXT];
       d.z[c] = cz[0] * qa[c] + cz[1] * qb[c] + cz[2] * qc[c] + cz[3] * qd[c] + cz[4] * qe[c];
     }
     momentum(d, m, slw, h);
@@ -251,10 +255,10 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
 template <int DX, int DY, int DZ, int KIND>
 __global__ void __launch_bounds__(TX *TY, 2) k_iso_main_tma(const StageArgs P, const __grid_constant__ TmaMaps M)
 {
-  extern __shared__ unsigned char smem_raw[];
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
   constexpr int ZB = Ofs<DZ>::left, ZA = Ofs<DZ>::right;
   TmaCtx C;
-  C.ring = (unsigned char *)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+  C.ring = smem_raw;
   C.full = (uint64_t *)(C.ring + NST * STAGE_BYTES);
   C.tx = threadIdx.x; C.ty = threadIdx.y; C.t = C.ty * TX + C.tx;
   C.i0 = P.ni1 + blockIdx.x * TX; C.j0 = P.nj1 + blockIdx.y * TY;
@@ -288,13 +292,13 @@ __global__ void __launch_bounds__(TX *TY, 2) k_iso_main_tma(const StageArgs P, c
       qn[c] = __ldg(w + 4 * P.siz_slice);   // plane k0 + ZA
     }
   }
-  int k = k0, it = 0;
-  while (true) {
-    tma_plane<DX, DY, DZ, KIND>(P, M, C, k, it, q0, q1, q2, q3, q4, qn); if (++k > C.k1) break; ++it;
-    tma_plane<DX, DY, DZ, KIND>(P, M, C, k, it, q1, q2, q3, q4, q0, qn); if (++k > C.k1) break; ++it;
-    tma_plane<DX, DY, DZ, KIND>(P, M, C, k, it, q2, q3, q4, q0, q1, qn); if (++k > C.k1) break; ++it;
-    tma_plane<DX, DY, DZ, KIND>(P, M, C, k, it, q3, q4, q0, q1, q2, qn); if (++k > C.k1) break; ++it;
-    tma_plane<DX, DY, DZ, KIND>(P, M, C, k, it, q4, q0, q1, q2, q3, qn); if (++k > C.k1) break; ++it;
+  int it = 0;
+  for (int k = k0; k <= C.k1; k++, it++) {
+    tma_plane<DX, DY, DZ, KIND>(P, M, C, k, it, q0, q1, q2, q3, q4, qn);
+    // rotate the zeta queue (register moves; unrolling by 5 instead makes the loop body outgrow the
+    // 32 KB instruction cache and the kernel instruction-fetch bound -- profiles/r1d)
+#pragma unroll
+    for (int c = 0; c < 9; c++) { q0[c] = q1[c]; q1[c] = q2[c]; q2[c] = q3[c]; q3[c] = q4[c]; }
   }
 }
 

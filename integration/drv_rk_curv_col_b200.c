@@ -1,0 +1,293 @@
+/*
+ * drv_rk_curv_col_b200.c -- drop-in replacement of forward/drv_rk_curv_col.c for the CGFD3D host
+ * program: same entry point, same arguments (forward/drv_rk_curv_col.h:17-37), called from
+ * forward/main_curv_col_el_3d.c:849-858. Link this file and libcgfd3d_b200.so instead of
+ * drv_rk_curv_col.o and sv_curv_col_*.o; the par file, every *_t struct and the SAC / nc output layout
+ * stay the reference's own.
+ *
+ * What runs where:
+ *   host (reference code, unchanged): nc file creation, free-surface matrix set-up (*_dvh2dvz),
+ *        io_recv_keep / io_line_keep / io_slice_nc_put / io_snap_nc_put / PG_slice_output;
+ *   GPU (libcgfd3d_b200.so through the C ABI of include/cgfd3d_b200.h): the whole RK4 stage loop --
+ *        RHS, CFS-PML, free surface, sources, RK update, halo exchange, PGV/PGA/PGD maps.
+ * After every step only the samples the output taps need are copied back: the receiver / line points
+ * (recorded on the device) and, on the steps a slice or snapshot is due, its strided sub-boxes. They are
+ * written into the host wavefield level the reference functions read (w_end), so those run unmodified.
+ *
+ * This file includes the reference's headers and therefore compiles only where the reference tree is.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <mpi.h>
+
+#include "fdlib_mem.h"
+#include "fdlib_math.h"
+#include "blk_t.h"
+#include "drv_rk_curv_col.h"
+#include "sv_curv_col_el.h"
+#include "sv_curv_col_el_iso.h"
+#include "sv_curv_col_el_vti.h"
+#include "sv_curv_col_el_aniso.h"
+#include "sv_curv_col_vis_iso.h"
+
+#include "cgfd3d_b200.h"
+
+#define DIE(...) do { fprintf(stderr, "cgfd3d_b200 driver: " __VA_ARGS__); fprintf(stderr, "\n"); fflush(stderr); \
+                      MPI_Abort(MPI_COMM_WORLD, 1); exit(1); } while (0)
+#define GPU(call) do { if ((call) != 0) DIE("%s failed: %s", #call, cgfd_b200_last_error()); } while (0)
+
+static void flatten_fd(const fd_t *fd, cgfd_fd_t *o)
+{
+  memset(o, 0, sizeof(*o));
+  for (int s = 0; s < CGFD_NUM_STAGES; s++) { o->rk_b[s] = fd->rk_b[s]; if (s < CGFD_NUM_STAGES - 1) o->rk_a[s] = fd->rk_a[s]; }
+  if (fd->num_of_pairs != CGFD_NUM_PAIRS || fd->num_rk_stages != CGFD_NUM_STAGES) DIE("expected 8 operator pairs and 4 RK stages");
+  for (int p = 0; p < CGFD_NUM_PAIRS; p++) for (int s = 0; s < CGFD_NUM_STAGES; s++) {
+    fd_op_t *ox = &fd->pair_fdx_op[p][s][fd->num_of_fdx_op - 1];
+    fd_op_t *oy = &fd->pair_fdy_op[p][s][fd->num_of_fdy_op - 1];
+    fd_op_t *oz = &fd->pair_fdz_op[p][s][fd->num_of_fdz_op - 1];
+    fd_op_t *ops[3] = { ox, oy, oz };
+    for (int a = 0; a < 3; a++) {
+      if (ops[a]->total_len != 5) DIE("interior operator must have 5 points");
+      int d = (ops[a]->indx[0] == -1) ? 0 : 1;   /* {-1..3} -> 0, {-3..1} -> 1 */
+      o->dir[p][s][a] = d;
+      for (int n = 0; n < 5; n++) { o->indx[d][n] = ops[a]->indx[n]; o->coef[d][n] = ops[a]->coef[n]; }
+    }
+    if (fd->num_of_fdz_op != 4) DIE("expected 4 zeta operators per stage (forward/fd_t.c:197-199)");
+    int dz = o->dir[p][s][2];
+    for (int lay = 1; lay <= 2; lay++) {
+      fd_op_t *l = &fd->pair_fdz_op[p][s][lay];
+      o->lay_len[lay][dz] = l->total_len;
+      for (int n = 0; n < l->total_len; n++) { o->lay_indx[lay][dz][n] = l->indx[n]; o->lay_coef[lay][dz][n] = l->coef[n]; }
+    }
+  }
+}
+
+/* copy a strided box of component icmp from the device into the host level `w` at the same indices */
+static void fetch_box(cgfd_b200_ctx *ctx, float *w, size_t siz_icmp, size_t siz_line, size_t siz_slice, int icmp,
+                      int i1, int ni, int di, int j1, int nj, int dj, int k1, int nk, int dk, float **buf, size_t *cap)
+{
+  size_t tot = (size_t)ni * nj * nk;
+  if (tot == 0) return;
+  if (tot > *cap) { *buf = (float *)realloc(*buf, tot * sizeof(float)); *cap = tot; }
+  GPU(cgfd_b200_get_box(ctx, icmp, i1, ni, di, j1, nj, dj, k1, nk, dk, *buf));
+  float *var = w + (size_t)icmp * siz_icmp;
+  size_t n = 0;
+  for (int kk = 0; kk < nk; kk++) for (int jj = 0; jj < nj; jj++) for (int ii = 0; ii < ni; ii++)
+    var[(size_t)(i1 + ii * di) + (size_t)(j1 + jj * dj) * siz_line + (size_t)(k1 + kk * dk) * siz_slice] = (*buf)[n++];
+}
+
+void
+drv_rk_curv_col_allstep(
+  fd_t            *fd,
+  gd_t        *gd,
+  gdcurv_metric_t *metric,
+  md_t      *md,
+  src_t     *src,
+  bdry_t    *bdry,
+  wav_t     *wav,
+  mympi_t    *mympi,
+  iorecv_t   *iorecv,
+  ioline_t   *ioline,
+  ioslice_t  *ioslice,
+  iosnap_t   *iosnap,
+  float dt, int nt_total, float t0,
+  char *output_fname_part,
+  char *output_dir,
+  int qc_check_nan_num_of_step,
+  const int output_all,
+  const int verbose)
+{
+  int myid = mympi->myid;
+  int *topoid = mympi->topoid;
+  const int ncmp = wav->ncmp;
+  const size_t siz_icmp = wav->siz_icmp;
+
+  /* host levels the reference's output functions work on (forward/drv_rk_curv_col.c:101-104) */
+  float *w_pre = wav->v5d + wav->siz_ilevel * 0;
+  float *w_rhs = wav->v5d + wav->siz_ilevel * 2;
+  float *w_end = wav->v5d + wav->siz_ilevel * 3;
+
+  if (myid == 0 && verbose > 0) fprintf(stdout, "prepare slice nc output ...\n");
+  ioslice_nc_t ioslice_nc;
+  io_slice_nc_create(ioslice, wav->ncmp, wav->visco_type, wav->cmp_name, gd->ni, gd->nj, gd->nk, topoid, &ioslice_nc);
+  if (myid == 0 && verbose > 0) fprintf(stdout, "prepare snap nc output ...\n");
+  iosnap_nc_t iosnap_nc;
+  io_snap_nc_create(iosnap, &iosnap_nc, topoid);
+
+  /* free-surface conversion matrices: one-shot host set-up, reference code (drv_rk_curv_col.c:132-159) */
+  if (bdry->is_sides_free[CONST_NDIM - 1][1] == 1) {
+    if (md->medium_type == CONST_MEDIUM_ELASTIC_ISO) sv_curv_col_el_iso_dvh2dvz(gd, metric, md, bdry, verbose);
+    else if (md->medium_type == CONST_MEDIUM_ELASTIC_VTI) sv_curv_col_el_vti_dvh2dvz(gd, metric, md, bdry, verbose);
+    else if (md->medium_type == CONST_MEDIUM_ELASTIC_ANISO) sv_curv_col_el_aniso_dvh2dvz(gd, metric, md, bdry, verbose);
+    else if (md->medium_type == CONST_MEDIUM_VISCOELASTIC_ISO && md->visco_type == CONST_VISCO_GMB)
+      sv_curv_col_vis_iso_dvh2dvz(gd, metric, md, bdry, fd->fdc_len, fd->fdc_indx, fd->fdc_coef, verbose);
+    else DIE("conversion matrix for medium_type=%d is not implemented", md->medium_type);
+  }
+
+  /* ---- flatten the reference structs into the C ABI problem description ---------------------------- */
+  cgfd_problem_t P;
+  memset(&P, 0, sizeof(P));
+  P.abi_version = CGFD_ABI_VERSION;
+  P.grid.nx = gd->nx; P.grid.ny = gd->ny; P.grid.nz = gd->nz;
+  P.grid.ni1 = gd->ni1; P.grid.ni2 = gd->ni2; P.grid.nj1 = gd->nj1; P.grid.nj2 = gd->nj2; P.grid.nk1 = gd->nk1; P.grid.nk2 = gd->nk2;
+  flatten_fd(fd, &P.fd);
+  P.dt = dt;
+  P.medium_type = md->medium_type;
+  P.nmaxwell = (md->medium_type == CONST_MEDIUM_VISCOELASTIC_ISO) ? md->nmaxwell : 0;
+  P.ncmp = ncmp;
+  const float *mt[10] = { metric->jac, metric->xi_x, metric->xi_y, metric->xi_z, metric->eta_x, metric->eta_y, metric->eta_z,
+                          metric->zeta_x, metric->zeta_y, metric->zeta_z };
+  for (int m = 0; m < 10; m++) P.metric[m] = mt[m];
+  if (md->medium_type == CONST_MEDIUM_ELASTIC_ISO) {
+    P.nmedia = 3; P.media[0] = md->lambda; P.media[1] = md->mu; P.media[2] = md->rho;
+  } else if (md->medium_type == CONST_MEDIUM_ELASTIC_VTI) {
+    const float *a[6] = { md->c11, md->c13, md->c33, md->c55, md->c66, md->rho };
+    P.nmedia = 6; for (int m = 0; m < 6; m++) P.media[m] = a[m];
+  } else if (md->medium_type == CONST_MEDIUM_ELASTIC_ANISO) {
+    const float *a[22] = { md->c11, md->c12, md->c13, md->c14, md->c15, md->c16, md->c22, md->c23, md->c24, md->c25, md->c26,
+                           md->c33, md->c34, md->c35, md->c36, md->c44, md->c45, md->c46, md->c55, md->c56, md->c66, md->rho };
+    P.nmedia = 22; for (int m = 0; m < 22; m++) P.media[m] = a[m];
+  } else if (md->medium_type == CONST_MEDIUM_VISCOELASTIC_ISO) {
+    P.nmedia = 3 + 2 * md->nmaxwell; P.media[0] = md->lambda; P.media[1] = md->mu; P.media[2] = md->rho;
+    if (md->nmaxwell > CGFD_MAX_MAXWELL) DIE("too many Maxwell bodies");
+    for (int n = 0; n < md->nmaxwell; n++) { P.media[3 + n] = md->Ylam[n]; P.media[3 + md->nmaxwell + n] = md->Ymu[n]; P.visco_wl[n] = md->wl[n]; }
+  } else DIE("medium_type=%d is not supported", md->medium_type);
+  if (md->visco_type == CONST_VISCO_GRAVES_QS) DIE("Graves Qs attenuation is not available on the GPU path yet");
+  P.free_top = bdry->is_sides_free[CONST_NDIM - 1][1];
+  P.timg_mode = getenv("CGFD_TIMG_MIRROR") ? CGFD_TIMG_MIRROR : CGFD_TIMG_ZERO;
+  for (int d = 0; d < 3; d++) for (int s = 0; s < 2; s++) {
+    if (bdry->is_enable_pml != 1 || bdry->is_sides_pml[d][s] != 1) continue;
+    P.pml[d][s].enabled = 1; P.pml[d][s].nlay = bdry->num_of_layers[d][s];
+    P.pml[d][s].A = bdry->A[d][s]; P.pml[d][s].B = bdry->B[d][s]; P.pml[d][s].D = bdry->D[d][s];
+  }
+  if (P.free_top) { P.matVx2Vz = bdry->matVx2Vz2; P.matVy2Vz = bdry->matVy2Vz2; P.matF2Vz = bdry->matF2Vz2; P.matD = bdry->matD; }
+  if (bdry->is_enable_ablexp == 1) {
+    P.ablexp_enabled = 1;
+    for (int n = 0; n < CONST_NDIM_2; n++) {
+      bdry_block_t *D = bdry->bdry_blk + n;
+      int v[7] = { D->enable, D->ni1, D->ni2, D->nj1, D->nj2, D->nk1, D->nk2 };
+      memcpy(P.ablexp_blk[n], v, sizeof(v));
+    }
+    P.ablexp_Ex = bdry->ablexp_Ex; P.ablexp_Ey = bdry->ablexp_Ey; P.ablexp_Ez = bdry->ablexp_Ez;
+  }
+  if (src->dd_is_valid == 1) DIE("distributed (dd) sources are not available on the GPU path yet");
+  cgfd_src_t *S = &P.src;
+  S->total_number = src->total_number; S->max_nt = src->max_nt; S->max_stage = src->max_stage;
+  S->si = src->si; S->sj = src->sj; S->sk = src->sk;
+  S->si_inc = src->si_inc; S->sj_inc = src->sj_inc; S->sk_inc = src->sk_inc;
+  S->it_begin = src->it_begin; S->it_end = src->it_end;
+  S->is_surface_force_strict = src->is_surface_force_strict;
+  S->total_number_surface_force = src->total_number_surface_force;
+  S->force_rate_indx = src->force_rate_indx;
+  S->itype_spatial_ext = src->itype_spatial_ext; S->ext_half_npoint = src->ext_half_npoint; S->ext_func_coef = src->ext_func_coef;
+  S->force_actived = src->force_actived; S->moment_actived = src->moment_actived;
+  S->Fx = src->Fx; S->Fy = src->Fy; S->Fz = src->Fz;
+  S->Mxx = src->Mxx; S->Myy = src->Myy; S->Mzz = src->Mzz; S->Mxz = src->Mxz; S->Myz = src->Myz; S->Mxy = src->Mxy;
+  S->Fx_rate = src->Fx_rate; S->Fy_rate = src->Fy_rate; S->Fz_rate = src->Fz_rate;
+  for (int n = 0; n < 4; n++) P.neigh[n] = (mympi->neighid[n] == MPI_PROC_NULL) ? -1 : mympi->neighid[n];
+
+  /* one rank drives one GPU: local device = rank modulo the devices of this node */
+  int ndev = cgfd_b200_device_count();
+  if (ndev <= 0) DIE("no CUDA device visible (this driver has no CPU fallback)");
+  cgfd_b200_ctx *ctx = NULL;
+  GPU(cgfd_b200_create(&P, myid % ndev, &ctx));
+  GPU(cgfd_b200_set_wavefield(ctx, w_pre));
+  for (int d = 0; d < 3; d++) for (int s = 0; s < 2; s++)
+    if (P.pml[d][s].enabled) {
+      /* aux vars hold ncmp components per level in the reference; the first 9 are the ones in use */
+      GPU(cgfd_b200_set_pml_aux(ctx, d, s, bdry->auxvar[d][s].var));
+    }
+  int nproc = mympi->nprocx * mympi->nprocy;
+  if (nproc > 1) {
+    char id[128];
+    if (myid == 0) GPU(cgfd_b200_comm_unique_id(id));
+    MPI_Bcast(id, 128, MPI_CHAR, 0, MPI_COMM_WORLD);
+    GPU(cgfd_b200_comm_init(ctx, id, myid, nproc));
+  }
+
+  /* ---- output taps: every grid point io_recv_keep / io_line_keep will read ------------------------- */
+  int nrec = iorecv->total_number * CONST_2_NDIM;
+  for (int n = 0; n < ioline->num_of_lines; n++) nrec += ioline->line_nr[n];
+  int64_t *rec_iptr = (int64_t *)malloc(sizeof(int64_t) * (nrec > 0 ? nrec : 1));
+  int ir = 0;
+  for (int n = 0; n < iorecv->total_number; n++) for (int q = 0; q < CONST_2_NDIM; q++) rec_iptr[ir++] = iorecv->recvone[n].indx1d[q];
+  for (int n = 0; n < ioline->num_of_lines; n++) for (int q = 0; q < ioline->line_nr[n]; q++) rec_iptr[ir++] = ioline->recv_iptr[n][q];
+  if (nrec > 0) GPU(cgfd_b200_set_record_points(ctx, nrec, rec_iptr, nt_total));
+  float *rec_step = (float *)malloc(sizeof(float) * (size_t)(nrec > 0 ? nrec : 1) * ncmp);
+  float *boxbuf = NULL; size_t boxcap = 0;
+  const int any_slice = ioslice_nc.num_of_slice_x + ioslice_nc.num_of_slice_y + ioslice_nc.num_of_slice_z;
+
+  if (myid == 0 && verbose > 0) fprintf(stdout, "start time loop (GPU) ...\n");
+  struct timespec ts0, ts1;
+  clock_gettime(CLOCK_MONOTONIC, &ts0);
+  for (int it = 0; it < nt_total; it++)
+  {
+    float t_cur = it * dt + t0;
+    float t_end = t_cur + dt;
+    if (myid == 0 && verbose > 10) fprintf(stdout, "-> it=%d, t=%f\n", it, t_cur);
+
+    GPU(cgfd_b200_run(ctx, it, 1));
+
+    /* receivers and lines: device record -> host w_end at the sampled indices -> reference functions */
+    if (nrec > 0) {
+      GPU(cgfd_b200_get_record(ctx, it, 1, rec_step));
+      for (int c = 0; c < ncmp; c++) for (int q = 0; q < nrec; q++) w_end[(size_t)c * siz_icmp + rec_iptr[q]] = rec_step[(size_t)c * nrec + q];
+      io_recv_keep(iorecv, w_end, it, ncmp, siz_icmp);
+      io_line_keep(ioline, w_end, it, ncmp, siz_icmp);
+    }
+    /* slices: planes through the physical range */
+    if (any_slice > 0) {
+      int c2 = (wav->visco_type == CONST_VISCO_GMB) ? 8 : ncmp - 1;
+      for (int c = 0; c <= c2; c++) {
+        for (int n = 0; n < ioslice_nc.num_of_slice_x; n++)
+          fetch_box(ctx, w_end, siz_icmp, gd->siz_iy, gd->siz_iz, c, ioslice->slice_x_indx[n], 1, 1, gd->nj1, gd->nj, 1, gd->nk1, gd->nk, 1, &boxbuf, &boxcap);
+        for (int n = 0; n < ioslice_nc.num_of_slice_y; n++)
+          fetch_box(ctx, w_end, siz_icmp, gd->siz_iy, gd->siz_iz, c, gd->ni1, gd->ni, 1, ioslice->slice_y_indx[n], 1, 1, gd->nk1, gd->nk, 1, &boxbuf, &boxcap);
+        for (int n = 0; n < ioslice_nc.num_of_slice_z; n++)
+          fetch_box(ctx, w_end, siz_icmp, gd->siz_iy, gd->siz_iz, c, gd->ni1, gd->ni, 1, gd->nj1, gd->nj, 1, ioslice->slice_z_indx[n], 1, 1, &boxbuf, &boxcap);
+      }
+      io_slice_nc_put(ioslice, &ioslice_nc, gd, w_end, w_rhs, it, t_end, 0, ncmp - 1, wav->visco_type);
+    }
+    /* snapshots due at this step (condition of io_snap_nc_put, forward/io_funcs.c:1152-1158) */
+    for (int n = 0; n < iosnap->num_of_snap; n++) {
+      int it1 = iosnap->it1[n], dit = iosnap->dit[n];
+      if (!(it >= it1 && (it - it1) / dit <= (nt_total - it1) / dit && (it - it1) % dit == 0)) continue;
+      int c1 = (iosnap->out_vel[n] == 1) ? 0 : 3;
+      int c2 = (iosnap->out_stress[n] == 1 || iosnap->out_strain[n] == 1) ? 8 : 2;
+      for (int c = c1; c <= c2; c++)
+        fetch_box(ctx, w_end, siz_icmp, gd->siz_iy, gd->siz_iz, c, iosnap->i1[n], iosnap->ni[n], iosnap->di[n], iosnap->j1[n], iosnap->nj[n],
+                  iosnap->dj[n], iosnap->k1[n], iosnap->nk[n], iosnap->dk[n], &boxbuf, &boxcap);
+    }
+    io_snap_nc_put(iosnap, &iosnap_nc, gd, md, wav, w_end, w_rhs, nt_total, it, t_end, 1, 1, 1);
+
+    if (output_all == 1) {
+      char ou_file[CONST_MAX_STRLEN];
+      GPU(cgfd_b200_get_wavefield(ctx, w_end));
+      io_build_fname_time(output_dir, "w3d", ".nc", topoid, it, ou_file);
+      io_var3d_export_nc(ou_file, w_end, wav->cmp_pos, wav->cmp_name, wav->ncmp, gd->index_name, gd->nx, gd->ny, gd->nz);
+    }
+  }
+  clock_gettime(CLOCK_MONOTONIC, &ts1);
+  if (myid == 0 && verbose > 0) {
+    double sec = (ts1.tv_sec - ts0.tv_sec) + 1e-9 * (ts1.tv_nsec - ts0.tv_nsec);
+    fprintf(stdout, "GPU time loop: %d steps in %.3f s = %.4f Gpoint-updates/s on this rank\n", nt_total, sec,
+            (double)gd->ni * gd->nj * gd->nk * nt_total / sec / 1e9);
+  }
+
+  if (bdry->is_sides_free[CONST_NDIM - 1][1] == 1) {
+    float *PG = (float *)fdlib_mem_calloc_1d_float(CONST_NDIM_5 * gd->ny * gd->nx, 0.0, "PG malloc");
+    GPU(cgfd_b200_get_pg(ctx, PG));
+    PG_slice_output(PG, gd, output_dir, output_fname_part, topoid);
+    free(PG);
+  }
+  /* leave the final state where the reference leaves it: level n of the host wavefield */
+  GPU(cgfd_b200_get_wavefield(ctx, w_pre));
+  io_slice_nc_close(&ioslice_nc);
+  io_snap_nc_close(&iosnap_nc);
+  cgfd_b200_destroy(ctx);
+  free(rec_iptr); free(rec_step); free(boxbuf);
+  (void)qc_check_nan_num_of_step;
+  return;
+}

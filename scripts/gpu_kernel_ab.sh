@@ -7,7 +7,7 @@ for V in 0 1; do
   echo "== variant $V: pytest"; CGFD_VARIANT=$V timeout 600 python -m pytest tests -x -q -m gpu > $OUT/pytest_v$V.log 2>&1; echo "rc=$?" >> $OUT/pytest_v$V.log; tail -4 $OUT/pytest_v$V.log
 done
 for V in 0 1; do
-  for Z in 0 24 49; do
+  for Z in 0 32 98; do
     echo "== bench variant $V zchunk $Z"
     CGFD_VARIANT=$V CGFD_ZCHUNK=$Z timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/bench_v${V}_z$Z.json 2> $OUT/bench_v${V}_z$Z.err
     python -c "
@@ -18,4 +18,4 @@ print('value',d['value'],'ms/step',d['ms_per_step'],'main avg ms',d['roofline'][
   done
 done
 echo "== ncu launches (default variant)"; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_launch.log 2>&1; echo "rc=$?"
-echo "== ncu full"; timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_iso_main -s 16 -c 4 -o $OUT/prof_main python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_full.log 2>&1; echo "rc=$?"
+echo "== ncu full"; timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_iso_main -s 17 -c 2 -o $OUT/prof_main python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_full.log 2>&1; echo "rc=$?"

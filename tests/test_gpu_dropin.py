@@ -1,0 +1,123 @@
+"""The drop-in path end to end: the reference's own main program and set-up code with its time-stepping
+driver replaced by integration/drv_rk_curv_col_b200.c + libcgfd3d_b200.so (oracle/_ref/cgfd_main_b200, linked
+where /root/reference exists), run on the reference's own input files, compared with
+
+  * tests/golden/ref_*.npz : seismograms (SAC) and surface snapshots (nc) the reference program produced for
+    the same files (tests/golden/make_golden.py), incl. BASELINE.json configs[0] at 1000 steps;
+  * a live run of the reference program (oracle/_ref/ref_main_zero) on a small case.
+
+Tolerance: relative L2 <= 1e-4 (BASELINE.json north_star); the exact statistic is stated in _compare().
+"""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from cgfd3d_b200 import solver
+from oracle import harness as H
+from tests import util
+from tests.golden import make_golden
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+BIN = H.ref_binary("cgfd_main_b200")
+
+
+def _need():
+    if not os.path.isfile(BIN):
+        pytest.fail("oracle/_ref/cgfd_main_b200 is missing (make -C oracle ref where /root/reference exists)")
+    if solver.device_count() < 1:
+        pytest.fail("no CUDA device")
+
+
+def _run_case(binary, par, src, stations):
+    wd = tempfile.mkdtemp(prefix="cgfd_dropin_")
+    H.write_case(wd, par, src, stations)
+    wall, out = H.run(binary, wd, timeout=3000)
+    sac = H.read_sac_dir(os.path.join(wd, "OUT"))
+    snap = H.read_cgnc(os.path.join(wd, "OUT", "surf_px0_py0.nc"))
+    pg = H.read_cgnc(os.path.join(wd, "OUT", "PG_V_A_D_px0_py0.nc"))
+    return sac, snap, pg, out
+
+
+def _joint(got, ref):
+    """sqrt(sum_c |got_c - ref_c|^2), sqrt(sum_c |ref_c|^2) over a list of component arrays"""
+    num = sum(float(np.sum((g.astype(np.float64) - r.astype(np.float64)) ** 2)) for g, r in zip(got, ref))
+    den = sum(float(np.sum(r.astype(np.float64) ** 2)) for r in ref)
+    return np.sqrt(num), np.sqrt(den)
+
+
+def _compare(sac, snap, gold):
+    """Statistic (stated here, the reference has no tests of its own):
+      * per receiver, the 3-component velocity seismogram and the 6-component stress seismogram:
+        ||gpu - ref||_2 / ||ref||_2 <= 1e-4 over the whole time series (components that vanish by symmetry, e.g. the
+        horizontal motion right above an explosion, are judged together with the component that carries the signal);
+      * the snapshot sequence as a whole (3 components, all frames): relative L2 <= 1e-4;
+      * every snapshot frame: ||gpu - ref||_2 <= 1e-4 * max(||ref frame||_2, 1e-2 * largest ||ref frame||_2), i.e. frames
+        whose energy is below 1 % of the strongest frame (the field has left the box, what remains is the PML residue,
+        which is ill-conditioned: the C port of the same algorithm drifts by 8e-5 there) are judged against that floor.
+    """
+    bad = []
+    nrec = len([k for k in gold if k.startswith("evt1_L1_") and k.endswith("_Vx")])
+    assert nrec >= 3
+    n = 0
+    for ir in range(nrec):
+        for names in (("Vx", "Vy", "Vz"), ("Txx", "Tyy", "Tzz", "Tyz", "Txz", "Txy")):
+            ref = [gold["evt1_L1_no%d_%s" % (ir, c)] for c in names]
+            got = [sac["evt1.L1.no%d.%s" % (ir, c)] for c in names]
+            num, den = _joint(got, ref)
+            assert den > 0
+            n += 1
+            if not num <= TOL * den:
+                bad.append(("rec%d.%s" % (ir, names[0][0]), num / den))
+    ref = [gold["snap_" + v] for v in ("Vx", "Vy", "Vz")]
+    got = [snap["vars"][v] for v in ("Vx", "Vy", "Vz")]
+    for g, r in zip(got, ref):
+        assert g.shape == r.shape, (g.shape, r.shape)
+    num, den = _joint(got, ref)
+    if not num <= TOL * den:
+        bad.append(("snapshots", num / den))
+    norms = [_joint([g[f] for g in got], [r[f] for r in ref]) for f in range(ref[0].shape[0])]
+    peak = max(d for _, d in norms)
+    for f, (e, d) in enumerate(norms):
+        n += 1
+        if not e <= TOL * max(d, 1e-2 * peak):
+            bad.append(("frame%d" % f, e / max(d, 1e-2 * peak)))
+    assert n > 10
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("name", ["small", "config1"])
+def test_dropin_matches_golden(name):
+    _need()
+    path = os.path.join(os.path.dirname(__file__), "golden", "ref_%s.npz" % name)
+    if not os.path.isfile(path):
+        pytest.fail("golden fixture %s missing (tests/golden/make_golden.py %s)" % (path, name))
+    gold = dict(np.load(path))
+    par, src, stations = make_golden.case_files(name, None)
+    sac, snap, pg, out = _run_case(BIN, par, src, stations)
+    assert "GPU time loop" in out
+    _compare(sac, snap, gold)
+
+
+def test_dropin_matches_live_reference_gauss_source():
+    """same files through both programs: Gaussian-smoothed source, different PML width, x/y/z slices"""
+    _need()
+    ni, nj, nk, nt = 40, 36, 30, 120
+    par = H.make_par(None, ni, nj, nk, nt, 0.02, pml_layers=6, src_spatial="gauss",
+                     lines=[{"name": "L1", "grid_index_start": [6, 8, nk - 1], "grid_index_incre": [6, 5, 0], "grid_index_count": 5}],
+                     snapshots=[{"name": "surf", "grid_index_start": [0, 0, nk - 1], "grid_index_count": [ni // 2, nj // 2, 1],
+                                 "grid_index_incre": [2, 2, 1], "time_index_start": 0, "time_index_incre": 10,
+                                 "save_velocity": 1, "save_stress": 0, "save_strain": 0}])
+    src = H.moment_src(20, 18, 9, m=(1e16, 0.5e16, 2e16, 0.2e16, -0.1e16, 0.3e16))
+    stations = [("r1", 0, 1, 25, 20, 0)]
+    sac_r, snap_r, pg_r, _ = _run_case(H.ref_binary("ref_main_zero"), par, src, stations)
+    sac_g, snap_g, pg_g, _ = _run_case(BIN, par, src, stations)
+    gold = {k.replace(".", "_"): v for k, v in sac_r.items() if ".L1." in k}
+    for v in ("Vx", "Vy", "Vz"):
+        gold["snap_" + v] = snap_r["vars"][v]
+    _compare(sac_g, snap_g, gold)
+    # peak-ground-motion maps (PG_calcu + PG_slice_output)
+    for v in ("PGV", "PGVz", "PGA", "PGD"):
+        assert util.rel_l2(pg_g["vars"][v], pg_r["vars"][v]) <= 1e-4, v
