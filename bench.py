@@ -29,6 +29,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# load every kernel image when the context is created, not at first launch inside the timed region
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 
 METRIC = "Gpoint-updates/s per RK4 step"
 BYTES_PER_POINT_STEP_ISO = 768.0  # 4*(16*C + 4*M), C = 9, M = 12
@@ -150,7 +152,9 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timing -----------------------------------------------------------------
-    S.run(W, it0=0)
+    # the 8 operator pairs (it % 8) use 8 different kernel instantiations: touch all of them before timing
+    S.run(max(W, 8), it0=0)
+    W = max(W, 8)
     S.set_profiling(True)
     barrier()
     with ClockSampler(local) as clk:

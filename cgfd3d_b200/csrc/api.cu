@@ -726,6 +726,13 @@ extern "C" int cgfd_b200_comm_init(cgfd_b200_ctx *c, const char id[128], int ran
   return 0;
 }
 
+extern "C" int cgfd_b200_halo_plan(const cgfd_grid_t *g, int dirx, int diry, int side, int send_box[6], int recv_box[6])
+{
+  if (!g || side < 0 || side > 3 || (dirx | diry) & ~1) return fail("halo_plan: bad arguments");
+  halo_plan(*g, dirx, diry, side, send_box, recv_box);
+  return 0;
+}
+
 // ---- measurement --------------------------------------------------------------------------------
 extern "C" int cgfd_b200_set_profiling(cgfd_b200_ctx *c, int on)
 {

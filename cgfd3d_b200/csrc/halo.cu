@@ -108,28 +108,43 @@ int halo_launches_per_exchange(HaloComm *h)
   return n;
 }
 
-int halo_exchange(HaloComm *h, float *w, int dirx, int diry, cudaStream_t st)
+// Which strips travel for an operator with direction indices (dirx, diry): operator widths are
+// dir 0 -> left 1 / right 3, dir 1 -> left 3 / right 1 (forward/fd_t.c:133-147); the message to x1 carries my
+// first `right` physical planes, the message to x2 my last `left` ones, and the ghosts filled from x1 / x2 are
+// `left` / `right` wide (forward/blk_t.c:497-510, 594-679, 700-808); y likewise. No edges or corners.
+// box = {i1, ni, j1, nj, k1, nk} in local indices including ghosts.
+void halo_plan(const cgfd_grid_t &g, int dirx, int diry, int side, int send_box[6], int recv_box[6])
 {
-  using cgfd::k_halo_copy;
-  const cgfd_grid_t &g = h->g;
   const int ni = g.ni2 - g.ni1 + 1, nj = g.nj2 - g.nj1 + 1, nk = g.nk2 - g.nk1 + 1;
-  // operator widths (forward/fd_t.c:133-147): dir 0 -> left 1 / right 3, dir 1 -> left 3 / right 1
   const int lx = dirx ? 3 : 1, rx = dirx ? 1 : 3, ly = diry ? 3 : 1, ry = diry ? 1 : 3;
-  // what goes to each side / what comes from it (forward/blk_t.c:497-510, 594-679)
   const int send_w[4] = {rx, lx, ry, ly};
   const int recv_w[4] = {lx, rx, ly, ry};
   const int send_i1[4] = {g.ni1, g.ni2 - lx + 1, g.ni1, g.ni1};
   const int send_j1[4] = {g.nj1, g.nj1, g.nj1, g.nj2 - ly + 1};
   const int recv_i1[4] = {g.ni1 - lx, g.ni2 + 1, g.ni1, g.ni1};
   const int recv_j1[4] = {g.nj1, g.nj1, g.nj1 - ly, g.nj2 + 1};
+  const int s = side;
+  send_box[0] = send_i1[s]; send_box[1] = (s < 2) ? send_w[s] : ni;
+  send_box[2] = send_j1[s]; send_box[3] = (s < 2) ? nj : send_w[s];
+  send_box[4] = g.nk1; send_box[5] = nk;
+  recv_box[0] = recv_i1[s]; recv_box[1] = (s < 2) ? recv_w[s] : ni;
+  recv_box[2] = recv_j1[s]; recv_box[3] = (s < 2) ? nj : recv_w[s];
+  recv_box[4] = g.nk1; recv_box[5] = nk;
+}
+
+int halo_exchange(HaloComm *h, float *w, int dirx, int diry, cudaStream_t st)
+{
+  using cgfd::k_halo_copy;
+  const cgfd_grid_t &g = h->g;
+  int sb[4][6], rb[4][6];
   size_t cnt_s[4], cnt_r[4];
   for (int s = 0; s < 4; s++) {
     if (h->neigh[s] < 0) continue;
-    const int wni = (s < 2) ? send_w[s] : ni, wnj = (s < 2) ? nj : send_w[s];
-    cnt_s[s] = (size_t)wni * wnj * nk * h->ncmp;
-    cnt_r[s] = (size_t)((s < 2) ? recv_w[s] : ni) * ((s < 2) ? nj : recv_w[s]) * nk * h->ncmp;
-    k_halo_copy<<<(unsigned)((cnt_s[s] + 255) / 256), 256, 0, st>>>(w, h->sbuf[s], h->V, h->ncmp, h->pitch, g.ny, send_i1[s], wni,
-                                                                   send_j1[s], wnj, g.nk1, nk, 0);
+    halo_plan(g, dirx, diry, s, sb[s], rb[s]);
+    cnt_s[s] = (size_t)sb[s][1] * sb[s][3] * sb[s][5] * h->ncmp;
+    cnt_r[s] = (size_t)rb[s][1] * rb[s][3] * rb[s][5] * h->ncmp;
+    k_halo_copy<<<(unsigned)((cnt_s[s] + 255) / 256), 256, 0, st>>>(w, h->sbuf[s], h->V, h->ncmp, h->pitch, g.ny, sb[s][0], sb[s][1],
+                                                                   sb[s][2], sb[s][3], sb[s][4], sb[s][5], 0);
   }
   NC(g_nccl.GroupStart());
   for (int s = 0; s < 4; s++) {
@@ -140,9 +155,8 @@ int halo_exchange(HaloComm *h, float *w, int dirx, int diry, cudaStream_t st)
   NC(g_nccl.GroupEnd());
   for (int s = 0; s < 4; s++) {
     if (h->neigh[s] < 0) continue;
-    const int wni = (s < 2) ? recv_w[s] : ni, wnj = (s < 2) ? nj : recv_w[s];
-    k_halo_copy<<<(unsigned)((cnt_r[s] + 255) / 256), 256, 0, st>>>(w, h->rbuf[s], h->V, h->ncmp, h->pitch, g.ny, recv_i1[s], wni,
-                                                                   recv_j1[s], wnj, g.nk1, nk, 1);
+    k_halo_copy<<<(unsigned)((cnt_r[s] + 255) / 256), 256, 0, st>>>(w, h->rbuf[s], h->V, h->ncmp, h->pitch, g.ny, rb[s][0], rb[s][1],
+                                                                   rb[s][2], rb[s][3], rb[s][4], rb[s][5], 1);
   }
   if (cudaGetLastError() != cudaSuccess) { g_herr = "halo kernels failed to launch"; return 1; }
   return 0;

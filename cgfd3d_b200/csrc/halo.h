@@ -14,3 +14,5 @@ void halo_destroy(HaloComm *h);
 // refresh the ghosts of level w for an operator with direction indices (dirx, diry)
 int halo_exchange(HaloComm *h, float *w, int dirx, int diry, cudaStream_t st);
 int halo_launches_per_exchange(HaloComm *h);
+// strips of one side (0..3 = x1,x2,y1,y2) as {i1, ni, j1, nj, k1, nk}; pure host logic
+void halo_plan(const cgfd_grid_t &g, int dirx, int diry, int side, int send_box[6], int recv_box[6]);

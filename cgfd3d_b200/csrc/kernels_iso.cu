@@ -184,22 +184,26 @@ __device__ __forceinline__ void tma_issue(const StageArgs &P, const TmaMaps &M, 
   if (KIND != KIND_FIRST) tma_load_4d(b + OFF_END, &M.end, bar, C.i0 + P.shift, C.j0, kk, 0);
 }
 
-// one plane: qa..qd hold the zeta neighbours k-ZB .. k-ZB+3, qe receives k+ZA (already fetched into qn)
+// One plane. The march along z runs TOWARDS the short side of the one-sided zeta operator (upwards for
+// offsets {-3..1}, downwards for {-1..3}), so that three of its neighbours are planes already visited and only one
+// lies ahead: q0,q1,q2 = planes k-3d, k-2d, k-d (d = march direction), q3 = plane k, q4 receives plane k+d, which was
+// requested one iteration earlier (qn) -- at the same time as the TMA of that plane, so it is one DRAM read.
 template <int DX, int DY, int DZ, int KIND>
-__device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, const TmaCtx &C, int k, int it,
-                                          const float (&qa)[9], const float (&qb)[9], const float (&qc)[9],
-                                          const float (&qd)[9], float (&qe)[9], float (&qn)[9])
+__device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, const TmaCtx &C, int k, int it, int nplanes,
+                                          const float (&q0)[9], const float (&q1)[9], const float (&q2)[9],
+                                          const float (&q3)[9], float (&q4)[9], float (&qn)[9])
 {
-  constexpr int YL = Ofs<DY>::left, ZA = Ofs<DZ>::right;
+  constexpr int YL = Ofs<DY>::left;
   constexpr int FX = Ofs<DX>::first, FY = Ofs<DY>::first;
+  constexpr int DIR = DZ ? 1 : -1;
   const int s = it % NST;
   const uint32_t parity = (it / NST) & 1;
   const float *cx = c_fd.coef[DX], *cy = c_fd.coef[DY], *cz = c_fd.coef[DZ];
 #pragma unroll
-  for (int c = 0; c < 9; c++) qe[c] = qn[c];
-  if (C.inarr && k + 1 <= C.k1) {
+  for (int c = 0; c < 9; c++) q4[c] = qn[c];
+  if (C.inarr && it + 1 < nplanes) {
 #pragma unroll
-    for (int c = 0; c < 9; c++) qn[c] = __ldg(P.cur + c * P.siz_vol + (size_t)(k + 1 + ZA) * P.siz_slice + C.pij);
+    for (int c = 0; c < 9; c++) qn[c] = __ldg(P.cur + c * P.siz_vol + (size_t)(k + 2 * DIR) * P.siz_slice + C.pij);
   }
   mbar_wait(C.full + s, parity);
   if (C.active) {
@@ -209,7 +213,7 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
     const float *sd = (const float *)(b + OFF_MED) + C.t;
     const float *sp = (const float *)(b + OFF_PRE) + C.t;
     const float *se = (const float *)(b + OFF_END) + C.t;
-    const float(&qz)[9] = DZ ? qd : qb;   // centre plane of the queue
+    const float(&qz)[9] = q3;   // centre plane of the queue
     const size_t p = (size_t)k * P.siz_slice + C.pij;
     Met m;
     m.xix = sm[0 * TX * TY]; m.xiy = sm[1 * TX * TY]; m.xiz = sm[2 * TX * TY];
@@ -225,7 +229,8 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
       const float *r = sc + c * SY * SXT;
       d.x[c] = cx[0] * r[FX] + cx[1] * r[FX + 1] + cx[2] * r[FX + 2] + cx[3] * r[FX + 3] + cx[4] * r[FX + 4];
       d.y[c] = cy[0] * r[FY * SXT] + cy[1] * r[(FY + 1) * SXT] + cy[2] * r[(FY + 2) * SXT] + cy[3] * r[(FY + 3) * SXT] + cy[4] * r[(FY + 4) * SXT];
-      d.z[c] = cz[0] * qa[c] + cz[1] * qb[c] + cz[2] * qc[c] + cz[3] * qd[c] + cz[4] * qe[c];
+      d.z[c] = DZ ? cz[0] * q0[c] + cz[1] * q1[c] + cz[2] * q2[c] + cz[3] * q3[c] + cz[4] * q4[c]
+                  : cz[0] * q4[c] + cz[1] * q3[c] + cz[2] * q2[c] + cz[3] * q1[c] + cz[4] * q0[c];
     }
     hooke_iso(d, m, lam, mu, lam2mu, h);
     pml_all_iso<KIND, 0>(P, C.i, C.j, k, d, m, lam, mu, lam2mu, slw, h);
@@ -239,7 +244,8 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
       const float *r = sc + c * SY * SXT;
       d.x[c] = cx[0] * r[FX] + cx[1] * r[FX + 1] + cx[2] * r[FX + 2] + cx[3] * r[FX + 3] + cx[4] * r[FX + 4];
       d.y[c] = cy[0] * r[FY * SXT] + cy[1] * r[(FY + 1) * SXT] + cy[2] * r[(FY + 2) * SXT] + cy[3] * r[(FY + 3) * SXT] + cy[4] * r[(FY + 4) * SXT];
-      d.z[c] = cz[0] * qa[c] + cz[1] * qb[c] + cz[2] * qc[c] + cz[3] * qd[c] + cz[4] * qe[c];
+      d.z[c] = DZ ? cz[0] * q0[c] + cz[1] * q1[c] + cz[2] * q2[c] + cz[3] * q3[c] + cz[4] * q4[c]
+                  : cz[0] * q4[c] + cz[1] * q3[c] + cz[2] * q2[c] + cz[3] * q1[c] + cz[4] * q0[c];
     }
     momentum(d, m, slw, h);
     pml_all_iso<KIND, 1>(P, C.i, C.j, k, d, m, lam, mu, lam2mu, slw, h);
@@ -249,14 +255,13 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
                      (KIND != KIND_FIRST) ? se[c * TX * TY] : 0.0f, h[c], P.a, P.b);
   }
   __syncthreads();   // every thread is done with ring slot s
-  if (C.t == 0 && k + NST <= C.k1) tma_issue<DX, DY, KIND>(P, M, C, k + NST, s);
+  if (C.t == 0 && it + NST < nplanes) tma_issue<DX, DY, KIND>(P, M, C, k + NST * DIR, s);
 }
 
 template <int DX, int DY, int DZ, int KIND>
 __global__ void __launch_bounds__(TX *TY, 2) k_iso_main_tma(const StageArgs P, const __grid_constant__ TmaMaps M)
 {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  constexpr int ZB = Ofs<DZ>::left, ZA = Ofs<DZ>::right;
   TmaCtx C;
   C.ring = smem_raw;
   C.full = (uint64_t *)(C.ring + NST * STAGE_BYTES);
@@ -275,28 +280,31 @@ __global__ void __launch_bounds__(TX *TY, 2) k_iso_main_tma(const StageArgs P, c
     mbar_fence_init();
   }
   __syncthreads();
+  constexpr int DIR = DZ ? 1 : -1;
+  const int nplanes = C.k1 - k0 + 1;
+  const int kf = DZ ? k0 : C.k1;   // first plane of the march
   if (C.t == 0) {
 #pragma unroll
     for (int s = 0; s < NST; s++)
-      if (k0 + s <= C.k1) tma_issue<DX, DY, KIND>(P, M, C, k0 + s, s);
+      if (s < nplanes) tma_issue<DX, DY, KIND>(P, M, C, kf + s * DIR, s);
   }
 
   float q0[9], q1[9], q2[9], q3[9], q4[9], qn[9];
 #pragma unroll
   for (int c = 0; c < 9; c++) { q0[c] = q1[c] = q2[c] = q3[c] = q4[c] = qn[c] = 0.0f; }
   if (C.inarr) {
+    const long sd = (long)DIR * (long)P.siz_slice;
 #pragma unroll
     for (int c = 0; c < 9; c++) {
-      const float *w = P.cur + c * P.siz_vol + (size_t)(k0 - ZB) * P.siz_slice + C.pij;
-      q0[c] = __ldg(w); q1[c] = __ldg(w + P.siz_slice); q2[c] = __ldg(w + 2 * P.siz_slice); q3[c] = __ldg(w + 3 * P.siz_slice);
-      qn[c] = __ldg(w + 4 * P.siz_slice);   // plane k0 + ZA
+      const float *w = P.cur + c * P.siz_vol + (size_t)kf * P.siz_slice + C.pij;
+      q0[c] = __ldg(w - 3 * sd); q1[c] = __ldg(w - 2 * sd); q2[c] = __ldg(w - sd); q3[c] = __ldg(w);
+      qn[c] = __ldg(w + sd);
     }
   }
-  int it = 0;
-  for (int k = k0; k <= C.k1; k++, it++) {
-    tma_plane<DX, DY, DZ, KIND>(P, M, C, k, it, q0, q1, q2, q3, q4, qn);
+  for (int it = 0; it < nplanes; it++) {
+    tma_plane<DX, DY, DZ, KIND>(P, M, C, kf + it * DIR, it, nplanes, q0, q1, q2, q3, q4, qn);
     // rotate the zeta queue (register moves; unrolling by 5 instead makes the loop body outgrow the
-    // 32 KB instruction cache and the kernel instruction-fetch bound -- profiles/r1d)
+    // 32 KB instruction cache and the kernel instruction-fetch bound -- profiles/r1d_summary.txt)
 #pragma unroll
     for (int c = 0; c < 9; c++) { q0[c] = q1[c]; q1[c] = q2[c]; q2[c] = q3[c]; q3[c] = q4[c]; }
   }

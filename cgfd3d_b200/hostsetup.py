@@ -469,11 +469,22 @@ def build_problem(ni, nj, nk, *, dh=(100.0, 100.0, 100.0), topo="flat", hill=(10
         neigh = (-1, -1, -1, -1)
     else:
         gi0, gj0, gni, gnj, neigh = sub
+    # Inter-rank faces: the ghost metrics there must be the neighbour's own values (gd_curv_metric_exchange,
+    # forward/gd_t.c:407-475), not mirrored ones. The coordinates are analytic, so build a block that is 3 points
+    # wider on every side that has a neighbour, compute the metrics on it and crop: the cropped ghosts then hold
+    # exactly what the neighbour computes for its physical points; physical faces keep the mirrored ghosts.
+    ex = [NG if neigh[n] >= 0 else 0 for n in range(4)]
+    eni, enj = ni + ex[0] + ex[1], nj + ex[2] + ex[3]
+    egi0, egj0 = gi0 - ex[0], gj0 - ex[2]
     if topo == "flat":
-        x, y, z = cartesian_coords(ni, nj, nk, dh, origin=(gi0 * dh[0], gj0 * dh[1], -(nk - 1) * dh[2]))
+        x, y, z = cartesian_coords(eni, enj, nk, dh, origin=(egi0 * dh[0], egj0 * dh[1], -(nk - 1) * dh[2]))
     else:
-        x, y, z = hill_coords(ni, nj, nk, dh, hill[0], hill[1], gi0, gj0, gni, gnj)
+        x, y, z = hill_coords(eni, enj, nk, dh, hill[0], hill[1], egi0, egj0, gni, gnj)
     metric = metric_from_coords(x, y, z)
+    if any(ex):
+        cs = (slice(None), slice(ex[2], ex[2] + nj + 2 * NG), slice(ex[0], ex[0] + ni + 2 * NG))
+        x, y, z = (np.ascontiguousarray(a[cs]) for a in (x, y, z))
+        metric = [np.ascontiguousarray(m[cs]) for m in metric]
     if dt is None:
         dt = estimate_dt(x, y, z, vp) * dt_safety
     prob = HostProblem(ni=ni, nj=nj, nk=nk, dt=float(f32(dt)), free_top=1 if free_top else 0, timg_mode=timg_mode,

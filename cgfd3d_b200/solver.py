@@ -21,7 +21,7 @@ SYMBOLS = [
     "cgfd_b200_set_wavefield", "cgfd_b200_get_wavefield", "cgfd_b200_set_pml_aux", "cgfd_b200_get_pml_aux",
     "cgfd_b200_pml_aux_size", "cgfd_b200_onestage", "cgfd_b200_get_pml_aux_rhs", "cgfd_b200_run",
     "cgfd_b200_set_record_points", "cgfd_b200_get_record", "cgfd_b200_get_box", "cgfd_b200_get_pg",
-    "cgfd_b200_comm_unique_id", "cgfd_b200_comm_init", "cgfd_b200_set_profiling", "cgfd_b200_get_profile",
+    "cgfd_b200_comm_unique_id", "cgfd_b200_comm_init", "cgfd_b200_halo_plan", "cgfd_b200_set_profiling", "cgfd_b200_get_profile",
     "cgfd_b200_last_run_ms", "cgfd_b200_set_variant",
 ]
 
@@ -61,6 +61,7 @@ def load_library():
     L.cgfd_b200_get_pg.argtypes = [vp, fp]
     L.cgfd_b200_comm_unique_id.argtypes = [C.c_char_p]
     L.cgfd_b200_comm_init.argtypes = [vp, C.c_char_p, ci, ci]
+    L.cgfd_b200_halo_plan.argtypes = [C.POINTER(abi.Grid), ci, ci, ci, C.POINTER(ci * 6), C.POINTER(ci * 6)]
     L.cgfd_b200_set_profiling.argtypes = [vp, ci]
     L.cgfd_b200_get_profile.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.cgfd_b200_last_run_ms.argtypes = [vp, C.POINTER(C.c_double)]
@@ -188,6 +189,16 @@ class Solver:
 
     def set_variant(self, name: str):
         self._chk(self.L.cgfd_b200_set_variant(self.h, name.encode()))
+
+
+def halo_plan(grid: dict, dirx: int, diry: int, side: int):
+    """(send_box, recv_box) of one side as (i1, ni, j1, nj, k1, nk); pure host logic of the library."""
+    L = load_library()
+    g = abi.Grid(**grid)
+    sb, rb = (C.c_int * 6)(), (C.c_int * 6)()
+    if L.cgfd_b200_halo_plan(C.byref(g), dirx, diry, side, C.byref(sb), C.byref(rb)) != 0:
+        raise CgfdError(L.cgfd_b200_last_error().decode())
+    return tuple(sb), tuple(rb)
 
 
 def comm_unique_id() -> bytes:

@@ -197,6 +197,11 @@ int  cgfd_b200_get_pg(cgfd_b200_ctx *ctx, float *pg);
 int  cgfd_b200_comm_unique_id(char id[128]);
 int  cgfd_b200_comm_init(cgfd_b200_ctx *ctx, const char id[128], int rank, int nranks);
 
+/* The halo plan itself (pure host logic, no GPU needed): the strips of `side` (0..3 = x1,x2,y1,y2) that are
+ * sent / received for an operator with direction indices (dirx, diry), as {i1, ni, j1, nj, k1, nk} in local
+ * indices including ghosts. Mirrors blk_macdrp_pack_mesg / unpack_mesg (forward/blk_t.c:576-808). */
+int  cgfd_b200_halo_plan(const cgfd_grid_t *grid, int dirx, int diry, int side, int send_box[6], int recv_box[6]);
+
 /* ---- measurement ----------------------------------------------------------------------------- */
 /* When enabled, every launch of the dominant (interior RHS + RK) kernel is bracketed by CUDA
  * events on its own stream; get_profile returns the accumulated milliseconds and launch counts. */
