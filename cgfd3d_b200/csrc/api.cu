@@ -35,7 +35,13 @@ struct PmlFaceHost {
 
 struct cgfd_b200_ctx {
   int device = 0;
-  cudaStream_t st = nullptr;
+  cudaStream_t st = nullptr;        // compute stream
+  cudaStream_t st2 = nullptr;       // boundary phase: free-surface rows, tiles next to inter-rank faces, halo exchange
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int l2mode = 3;                   // L2 eviction hints of the interior kernel (CGFD_L2MODE)
+  int overlap = 1;                  // run the boundary phase concurrently with the interior kernel
+  int ntx = 0, nty = 0;             // tiles of the interior kernel along x / y
+  int src_nb = 0;                   // source footprint points that belong to the boundary phase (first in the list)
   cgfd_grid_t g;
   cgfd_fd_t fd;
   float dt = 0;
@@ -47,7 +53,7 @@ struct cgfd_b200_ctx {
   size_t hV = 0, hslice = 0;        // host (unpadded) volume / slice
   float *lev[4] = {nullptr, nullptr, nullptr, nullptr};   // bases (unshifted)
   float *metric_blk = nullptr, *media_blk = nullptr;
-  CUtensorMap map_halo[4], map_cen[4], map_met, map_med;
+  CUtensorMap map_halo[4], map_cen[4], map_out[4], map_met, map_med;
   bool have_maps = false;
   int zchunk = 0;
   int ipre = 0, ia = 1, ib = 2, iend = 3;   // roles of the four level buffers
@@ -134,11 +140,17 @@ static encode_tiled_fn get_encode()
   return fn;
 }
 // 4-D map over [ncomp][nz][ny][PX] float32 with box (bx, by, 1, bc)
-static int make_map(cgfd_b200_ctx *c, CUtensorMap *m, float *base, int ncomp, int bx, int by, int bc)
+// phys = true: origin at the first physical point of a row / column, extents ni x nj (store maps: nothing outside the
+// physical x-y range is ever written)
+static int make_map(cgfd_b200_ctx *c, CUtensorMap *m, float *base, int ncomp, int bx, int by, int bc, bool phys = false)
 {
   encode_tiled_fn enc = get_encode();
   if (!enc) return fail("cuTensorMapEncodeTiled is not available from this driver");
   cuuint64_t dim[4] = {(cuuint64_t)c->PX, (cuuint64_t)c->g.ny, (cuuint64_t)c->g.nz, (cuuint64_t)ncomp};
+  if (phys) {
+    dim[0] = (cuuint64_t)(c->g.ni2 - c->g.ni1 + 1); dim[1] = (cuuint64_t)(c->g.nj2 - c->g.nj1 + 1);
+    base += c->shift + c->g.ni1 + (size_t)c->g.nj1 * c->PX;
+  }
   cuuint64_t str[3] = {(cuuint64_t)c->PX * 4, (cuuint64_t)c->slice * 4, (cuuint64_t)c->V * 4};
   cuuint32_t box[4] = {(cuuint32_t)bx, (cuuint32_t)by, 1, (cuuint32_t)bc};
   cuuint32_t es[4] = {1, 1, 1, 1};
@@ -185,7 +197,15 @@ static int setup_sources(cgfd_b200_ctx *c, const cgfd_problem_t *p)
   const size_t L = g.nx, S = (size_t)g.nx * g.ny;
   const float *jac = p->metric[CGFD_JAC];
   const float *slw = p->media[(p->medium_type == CGFD_MEDIUM_ELASTIC_VTI) ? 5 : (p->medium_type == CGFD_MEDIUM_ELASTIC_ANISO) ? 21 : 2];
-  std::vector<int64_t> pt_iptr; std::vector<int> pt_src; std::vector<float> pt_wV, pt_wM;
+  std::vector<int64_t> pt_iptr; std::vector<int> pt_src, pt_bnd; std::vector<float> pt_wV, pt_wM;
+  // does point (i,j,k) belong to the boundary phase of a stage (free-surface rows, tiles next to an inter-rank face)?
+  auto bnd = [&](int i, int j, int k) -> int {
+    if (c->free_top && k >= g.nk2 - 3) return 1;
+    const int tx = (i - g.ni1) / TILE_X, ty = (j - g.nj1) / TILE_Y;
+    if (tx < 0 || ty < 0 || tx >= c->ntx || ty >= c->nty) return 1;
+    return (c->neigh[0] >= 0 && tx == 0) || (c->neigh[1] >= 0 && tx == c->ntx - 1) || (c->neigh[2] >= 0 && ty == 0) ||
+           (c->neigh[3] >= 0 && ty == c->nty - 1);
+  };
   const int H = s.ext_half_npoint;
   std::vector<float> ext;
   for (int is = 0; is < s.total_number; is++) {
@@ -195,7 +215,7 @@ static int setup_sources(cgfd_b200_ctx *c, const cgfd_problem_t *p)
       float wV = 0.0f, wM = 0.0f;
       if (s.force_actived && (s.is_surface_force_strict == 0 || sk < g.nk2)) wV = slw[ip] / jac[ip];
       if (s.moment_actived) wM = (float)(1.0 / jac[ip]);
-      pt_iptr.push_back(dev_index(c, (int64_t)ip)); pt_src.push_back(is); pt_wV.push_back(wV); pt_wM.push_back(wM);
+      pt_iptr.push_back(dev_index(c, (int64_t)ip)); pt_src.push_back(is); pt_wV.push_back(wV); pt_wM.push_back(wM); pt_bnd.push_back(bnd(si, sj, sk));
     } else {
       int k2 = (sk + H < g.nk2) ? H : g.nk2 - sk;
       norm_delt3d_z2fre(ext, s.si_inc[is], s.sj_inc[is], s.sk_inc[is], s.ext_func_coef, H, k2);
@@ -209,9 +229,18 @@ static int setup_sources(cgfd_b200_ctx *c, const cgfd_problem_t *p)
             float coef = ext[ie], wV = 0.0f, wM = 0.0f;
             if (s.force_actived && (s.is_surface_force_strict == 0 || k < g.nk2)) wV = coef * slw[ip] / jac[ip];
             if (s.moment_actived) wM = coef / jac[ip];
-            pt_iptr.push_back(dev_index(c, (int64_t)ip)); pt_src.push_back(is); pt_wV.push_back(wV); pt_wM.push_back(wM);
+            pt_iptr.push_back(dev_index(c, (int64_t)ip)); pt_src.push_back(is); pt_wV.push_back(wV); pt_wM.push_back(wM); pt_bnd.push_back(bnd(i, j, k));
           }
     }
+  }
+  {  // boundary-phase points first (stable, so the order of additions into one grid point is kept)
+    std::vector<size_t> ord;
+    for (size_t n = 0; n < pt_bnd.size(); n++) if (pt_bnd[n]) ord.push_back(n);
+    c->src_nb = (int)ord.size();
+    for (size_t n = 0; n < pt_bnd.size(); n++) if (!pt_bnd[n]) ord.push_back(n);
+    std::vector<int64_t> a(ord.size()); std::vector<int> b(ord.size()); std::vector<float> v(ord.size()), m(ord.size());
+    for (size_t n = 0; n < ord.size(); n++) { a[n] = pt_iptr[ord[n]]; b[n] = pt_src[ord[n]]; v[n] = pt_wV[ord[n]]; m[n] = pt_wM[ord[n]]; }
+    pt_iptr.swap(a); pt_src.swap(b); pt_wV.swap(v); pt_wM.swap(m);
   }
   SrcDev &d = c->src;
   d.nsrc = s.total_number; d.max_nt = s.max_nt; d.max_stage = s.max_stage;
@@ -322,7 +351,17 @@ extern "C" int cgfd_b200_create(const cgfd_problem_t *p, int device, cgfd_b200_c
   c->slice = (size_t)c->PX * g.ny; c->V = c->slice * g.nz;
   if (const char *e = getenv("CGFD_ZCHUNK")) c->zchunk = atoi(e);
   if (const char *e = getenv("CGFD_VARIANT")) c->variant = atoi(e);
-  CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+  if (const char *e = getenv("CGFD_OVERLAP")) c->overlap = atoi(e);
+  if (const char *e = getenv("CGFD_L2MODE")) c->l2mode = atoi(e);
+  {
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&c->st, cudaStreamNonBlocking, lo));
+    CK(cudaStreamCreateWithPriority(&c->st2, cudaStreamNonBlocking, hi));
+    CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  }
+  c->ntx = (g.ni2 - g.ni1 + 1 + TILE_X - 1) / TILE_X; c->nty = (g.nj2 - g.nj1 + 1 + TILE_Y - 1) / TILE_Y;
   if (iso_kernels_init()) { delete c; return fail("cgfd_b200_create: cudaFuncSetAttribute failed (needs sm_100 shared memory sizes)"); }
   CK(cudaEventCreate(&c->run0)); CK(cudaEventCreate(&c->run1));
 
@@ -355,6 +394,7 @@ extern "C" int cgfd_b200_create(const cgfd_problem_t *p, int device, cgfd_b200_c
     for (int l = 0; l < 4 && !mrc; l++) {
       mrc |= make_map(c, &c->map_halo[l], c->lev[l], 9, TILE_X + 2 * HALO_X, TILE_Y + 4, 9);
       mrc |= make_map(c, &c->map_cen[l], c->lev[l], 9, TILE_X, TILE_Y, 9);
+      mrc |= make_map(c, &c->map_out[l], c->lev[l], 9, TILE_X, TILE_Y, 9, true);
     }
     if (!mrc) mrc |= make_map(c, &c->map_met, c->metric_blk + c->V /* skip jac */, 9, TILE_X, TILE_Y, 9);
     if (!mrc) mrc |= make_map(c, &c->map_med, c->media_blk, p->nmedia, TILE_X, TILE_Y, 3);
@@ -408,6 +448,9 @@ extern "C" void cgfd_b200_destroy(cgfd_b200_ctx *c)
   for (auto e : c->ev) cudaEventDestroy(e);
   if (c->run0) cudaEventDestroy(c->run0);
   if (c->run1) cudaEventDestroy(c->run1);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->st2) cudaStreamDestroy(c->st2);
   if (c->st) cudaStreamDestroy(c->st);
   delete c;
 }
@@ -466,7 +509,7 @@ static void fill_args(cgfd_b200_ctx *c, StageArgs &P)
   for (int m = 0; m < c->nmedia; m++) P.media[m] = c->media[m];
   P.nmaxwell = c->nmaxwell;
   for (int n = 0; n < MAX_MAXWELL; n++) P.wl[n] = c->wl[n];
-  P.free_top = c->free_top; P.timg_mode = c->timg_mode;
+  P.free_top = c->free_top; P.timg_mode = c->timg_mode; P.l2mode = c->l2mode;
   P.matVx2Vz = c->mats[0]; P.matVy2Vz = c->mats[1]; P.matF2Vz = c->mats[2]; P.matD = c->mats[3];
   if (c->has_surf) {
     P.TxSrc = c->srcslice; P.TySrc = c->srcslice + c->hslice; P.TzSrc = c->srcslice + 2 * c->hslice;
@@ -483,9 +526,30 @@ static void fill_args(cgfd_b200_ctx *c, StageArgs &P)
   }
 }
 
-// launch everything of stage `istage` of step `it`; level roles: icur -> (itmp, iend), ipre
+// tile rectangles of the interior kernel: the tile columns / rows that touch an inter-rank face (boundary phase, at most
+// four rectangles) and the rest. rect = {bx0, bx1, by0, by1}.
+static int split_tiles(const cgfd_b200_ctx *c, bool split, int bnd[4][4], int inner[4])
+{
+  int x0 = 0, x1 = c->ntx, y0 = 0, y1 = c->nty, n = 0;
+  if (split) {
+    if (c->neigh[0] >= 0 && x1 - x0 > 0) { int r[4] = {x0, x0 + 1, 0, c->nty}; memcpy(bnd[n++], r, sizeof(r)); x0++; }
+    if (c->neigh[1] >= 0 && x1 - x0 > 0) { int r[4] = {x1 - 1, x1, 0, c->nty}; memcpy(bnd[n++], r, sizeof(r)); x1--; }
+    if (c->neigh[2] >= 0 && y1 - y0 > 0) { int r[4] = {x0, x1, y0, y0 + 1}; memcpy(bnd[n++], r, sizeof(r)); y0++; }
+    if (c->neigh[3] >= 0 && y1 - y0 > 0) { int r[4] = {x0, x1, y1 - 1, y1}; memcpy(bnd[n++], r, sizeof(r)); y1--; }
+  }
+  inner[0] = x0; inner[1] = x1; inner[2] = y0; inner[3] = y1;
+  return n;
+}
+
+// Launch everything of stage `istage` of step `it`; level roles: icur -> (itmp, iend), ipre.
+// Two phases on two streams:
+//   boundary phase (st2, high priority): the free-surface rows, the tiles next to inter-rank faces, the source points
+//        inside them, then -- when `halo_w` is given -- pack, NCCL send/recv and unpack of the ghosts of halo_w;
+//   interior phase (st): every other tile, the remaining source points.
+// The interior kernel never touches what the boundary phase writes (disjoint points; ghosts are written by the unpack
+// only), so the halo exchange is hidden behind it. The stage ends with st waiting for st2.
 static int run_stage(cgfd_b200_ctx *c, StageArgs &P, int it, int ipair, int istage, int kind, int icur, int ipre, int itmp,
-                     int iend, float a, float b)
+                     int iend, float a, float b, float *halo_w, int halo_dx, int halo_dy)
 {
   const int sh = c->shift;
   P.cur = c->lev[icur] + sh; P.pre = c->lev[ipre] + sh; P.tmp = c->lev[itmp] + sh; P.end = c->lev[iend] + sh;
@@ -494,7 +558,9 @@ static int run_stage(cgfd_b200_ctx *c, StageArgs &P, int it, int ipair, int ista
   if (c->have_maps) {
     maps.cur = c->map_halo[icur]; maps.pre = c->map_cen[ipre]; maps.end = c->map_cen[iend];
     maps.met = c->map_met; maps.med = c->map_med;
+    maps.out_tmp = c->map_out[itmp]; maps.out_end = c->map_out[iend];
   }
+  const TmaMaps *mp = c->have_maps ? &maps : nullptr;
   for (int idim = 0; idim < 3; idim++) for (int is = 0; is < 2; is++) {
     PmlFaceHost &h = c->pml[idim][is];
     if (!h.on) continue;
@@ -516,11 +582,31 @@ static int run_stage(cgfd_b200_ctx *c, StageArgs &P, int it, int ipair, int ista
     }
     e0 = c->ev[c->ev_used]; e1 = c->ev[c->ev_used + 1]; c->ev_used += 2;
   }
-  launch_iso_stage(P, c->have_maps ? &maps : nullptr, dir[0], dir[1], dir[2], kind, c->variant, c->zchunk, c->st, e0, e1, &nl);
-  if (c->has_src) {
-    k_src_inject<<<(c->src.npts + 127) / 128, 128, 0, c->st>>>(c->src, it, istage, c->lev[itmp] + sh, c->lev[iend] + sh, a, b, c->V, kind);
+  const bool two = c->overlap && halo_w;   // (running only the free-surface rows beside the interior kernel gains nothing: profiles/r1h)
+  cudaStream_t sb = two ? c->st2 : c->st;   // stream of the boundary phase
+  int bnd[4][4], inner[4];
+  const int nb = split_tiles(c, halo_w != nullptr, bnd, inner);
+  if (two) { CK(cudaEventRecord(c->ev_fork, c->st)); CK(cudaStreamWaitEvent(c->st2, c->ev_fork, 0)); }
+  // ---- boundary phase
+  launch_iso_top(P, dir[0], dir[1], dir[2], kind, sb, &nl);
+  for (int n = 0; n < nb; n++) launch_iso_main(P, mp, dir[0], dir[1], dir[2], kind, c->variant, c->zchunk, bnd[n], sb, nullptr, nullptr, &nl);
+  if (c->has_src && c->src_nb > 0) {
+    k_src_inject<<<(c->src_nb + 127) / 128, 128, 0, sb>>>(c->src, 0, c->src_nb, it, istage, c->lev[itmp] + sh, c->lev[iend] + sh, a, b, c->V, kind);
     nl++;
   }
+  if (halo_w) {
+    if (halo_exchange(c->halo, halo_w, halo_dx, halo_dy, sb)) return fail(halo_error());
+    nl += halo_launches_per_exchange(c->halo);
+  }
+  if (two) CK(cudaEventRecord(c->ev_join, c->st2));
+  // ---- interior phase
+  launch_iso_main(P, mp, dir[0], dir[1], dir[2], kind, c->variant, c->zchunk, inner, c->st, e0, e1, &nl);
+  if (c->has_src && c->src.npts > c->src_nb) {
+    const int cnt = c->src.npts - c->src_nb;
+    k_src_inject<<<(cnt + 127) / 128, 128, 0, c->st>>>(c->src, c->src_nb, cnt, it, istage, c->lev[itmp] + sh, c->lev[iend] + sh, a, b, c->V, kind);
+    nl++;
+  }
+  if (two) CK(cudaStreamWaitEvent(c->st, c->ev_join, 0));
   c->total_launches += nl;
   CK(cudaGetLastError());
   return 0;
@@ -553,16 +639,12 @@ extern "C" int cgfd_b200_run(cgfd_b200_ctx *c, int it0, int nsteps)
       const int icur = (s == 0) ? c->ipre : (s & 1) ? c->ia : c->ib;
       const int itmp = (s & 1) ? c->ib : c->ia;
       const float a = c->fd.rk_a[s] * dt, b = c->fd.rk_b[s] * dt;
-      if (run_stage(c, P, it, ipair, s, kind, icur, c->ipre, itmp, c->iend, a, b)) return 1;
-      if (c->halo) {
-        // ghosts of the level the NEXT rhs evaluation reads, widths of that evaluation's operator
-        // (forward/drv_rk_curv_col.c:193-199, 308-312, 448-469)
-        const int np = (s != CGFD_NUM_STAGES - 1) ? ipair : (it + 1) % CGFD_NUM_PAIRS;
-        const int ns = (s != CGFD_NUM_STAGES - 1) ? s + 1 : 0;
-        float *w = ((s != CGFD_NUM_STAGES - 1) ? c->lev[itmp] : c->lev[c->iend]) + c->shift;
-        if (halo_exchange(c->halo, w, c->fd.dir[np][ns][0], c->fd.dir[np][ns][1], c->st)) return fail(halo_error());
-        c->total_launches += halo_launches_per_exchange(c->halo);
-      }
+      // ghosts of the level the NEXT rhs evaluation reads, widths of that evaluation's operator
+      // (forward/drv_rk_curv_col.c:193-199, 308-312, 448-469)
+      const int np = (s != CGFD_NUM_STAGES - 1) ? ipair : (it + 1) % CGFD_NUM_PAIRS;
+      const int ns = (s != CGFD_NUM_STAGES - 1) ? s + 1 : 0;
+      float *hw = c->halo ? ((s != CGFD_NUM_STAGES - 1) ? c->lev[itmp] : c->lev[c->iend]) + c->shift : nullptr;
+      if (run_stage(c, P, it, ipair, s, kind, icur, c->ipre, itmp, c->iend, a, b, hw, c->fd.dir[np][ns][0], c->fd.dir[np][ns][1])) return 1;
     }
     float *wnew = c->lev[c->iend] + c->shift, *wold = c->lev[c->ipre] + c->shift;
     const cgfd_grid_t &g = c->g;
@@ -628,6 +710,7 @@ extern "C" int cgfd_b200_onestage(cgfd_b200_ctx *c, int it, int ipair, int istag
   if (c->have_maps) {
     maps.cur = c->map_halo[icur]; maps.pre = c->map_cen[iz2]; maps.end = c->map_cen[izero];
     maps.met = c->map_met; maps.med = c->map_med;
+    maps.out_tmp = c->map_out[iout]; maps.out_end = c->map_out[izero];
   }
   // aux: cur = copy of level n, pre = zeros, tmp = out, end = scratch
   // run_stage sets aux pointers from level indices; patch aux_pre to the zero buffer afterwards is not
@@ -646,9 +729,11 @@ extern "C" int cgfd_b200_onestage(cgfd_b200_ctx *c, int it, int ipair, int istag
         c->srcslice + 2 * c->hslice, c->srcslice + 3 * c->hslice, c->srcslice + 4 * c->hslice, c->srcslice + 5 * c->hslice);
   }
   const int *dir = c->fd.dir[ipair][istage];
-  launch_iso_stage(P, c->have_maps ? &maps : nullptr, dir[0], dir[1], dir[2], KIND_MID, c->variant, c->zchunk, c->st, nullptr, nullptr, &nl);
+  const int whole[4] = {0, c->ntx, 0, c->nty};
+  launch_iso_top(P, dir[0], dir[1], dir[2], KIND_MID, c->st, &nl);
+  launch_iso_main(P, c->have_maps ? &maps : nullptr, dir[0], dir[1], dir[2], KIND_MID, c->variant, c->zchunk, whole, c->st, nullptr, nullptr, &nl);
   if (c->has_src)
-    k_src_inject<<<(c->src.npts + 127) / 128, 128, 0, c->st>>>(c->src, it, istage, c->lev[iout] + sh, c->lev[izero] + sh, 1.0f, 0.0f, c->V, KIND_MID);
+    k_src_inject<<<(c->src.npts + 127) / 128, 128, 0, c->st>>>(c->src, 0, c->src.npts, it, istage, c->lev[iout] + sh, c->lev[izero] + sh, 1.0f, 0.0f, c->V, KIND_MID);
   CK(cudaGetLastError());
   if (copy_out3d(c, rhs, c->lev[iout], c->ncmp, c->st)) return 1;
   CK(cudaStreamSynchronize(c->st));

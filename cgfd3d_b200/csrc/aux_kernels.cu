@@ -7,10 +7,12 @@ namespace cgfd {
 // Point / Gaussian body sources added after the fused stage update: the reference adds
 // F*w*slw/J to hV and -M*w/J to hT before the RK axpy (forward/sv_curv_col_el.c:350-476);
 // here the same term is pushed through the axpy: tmp += a*s, end += b*s.
-__global__ void k_src_inject(SrcDev S, int it, int istage, float *tmp, float *end, float a, float b, size_t V, int kind)
+__global__ void k_src_inject(SrcDev S, int first, int count, int it, int istage, float *tmp, float *end, float a, float b, size_t V,
+                             int kind)
 {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= S.npts) return;
+  if (n >= count) return;
+  n += first;
   const int is = S.pt_src[n];
   const int itb = S.it_begin[is], ite = S.it_end[is];
   if (it < itb || it > ite) return;

@@ -50,6 +50,8 @@ struct StageArgs {
   int ni1, ni2, nj1, nj2, nk1, nk2;
   int kbeg, kend;               // rows handled by this launch, inclusive
   int zchunk;                   // rows per block along z (main kernel)
+  int bx0, by0;                 // first tile of this launch along x / y (main kernel)
+  int l2mode;                   // bit 0: wavefield tiles evict_last, bit 1: touch-once operands and results evict_first
   size_t siz_line, siz_slice, siz_vol;   // padded pitch, pitch*ny, pitch*ny*nz
   const float *cur;             // w_cur  [ncmp][nz][ny][nx]
   const float *pre;             // w_pre
@@ -74,11 +76,18 @@ struct TmaMaps {
   CUtensorMap med;   // media, box (TX, TY, 1, nmedia)
   CUtensorMap pre;   // w_pre, box (TX, TY, 1, 9)
   CUtensorMap end;   // w_end, box (TX, TY, 1, 9)
+  // store maps: the PHYSICAL x-y range only (origin (ni1,nj1), extents ni x nj), so that the parts of a tile that hang
+  // over the physical range are clipped by the TMA unit and ghosts are never written
+  CUtensorMap out_tmp, out_end;
 };
 
 // launchers (kernels_*.cu); dir = direction index per axis of this stage's operator
-void launch_iso_stage(const StageArgs &P, const TmaMaps *maps, int dx, int dy, int dz, int kind, int variant, int zchunk,
-                      cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1, int *nlaunch);
+// interior rows of the tile rectangle rect = {bx0, bx1, by0, by1} (tiles of TILE_X x TILE_Y points from (ni1, nj1))
+void launch_iso_main(const StageArgs &P, const TmaMaps *maps, int dx, int dy, int dz, int kind, int variant, int zchunk,
+                     const int rect[4], cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1, int *nlaunch);
+// the four free-surface rows, whole x-y range (no-op without a free top)
+void launch_iso_top(const StageArgs &P, int dx, int dy, int dz, int kind, cudaStream_t st, int *nlaunch);
+void iso_tile_counts(const StageArgs &P, int *ntx, int *nty);
 int iso_kernels_init();   // one-time function attributes (dynamic shared memory)
 constexpr int TILE_X = 32, TILE_Y = 8, HALO_X = 4;
 

@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(TX *TY, 2) k_iso_main(const StageArgs P)
   constexpr int XL = Ofs<DX>::left, YL = Ofs<DY>::left, ZB = Ofs<DZ>::left, ZA = Ofs<DZ>::right;
 
   const int tx = threadIdx.x, ty = threadIdx.y, t = ty * TX + tx;
-  const int i0 = P.ni1 + blockIdx.x * TX, j0 = P.nj1 + blockIdx.y * TY;
+  const int i0 = P.ni1 + (P.bx0 + blockIdx.x) * TX, j0 = P.nj1 + (P.by0 + blockIdx.y) * TY;
   const int i = i0 + tx, j = j0 + ty;
   const int k0 = P.kbeg + blockIdx.z * P.zchunk;
   const int k1 = min(k0 + P.zchunk - 1, P.kend);
@@ -168,6 +168,8 @@ struct TmaCtx {
   int tx, ty, t, i, j, i0, j0, k1;
   bool active, inarr;
   size_t pij;
+  const float *qptr;   // w_cur + pij: this thread's column of component 0
+  uint64_t pol_keep, pol_stream;   // L2 eviction policies (thread 0 only)
 };
 
 template <int DX, int DY, int KIND>
@@ -177,18 +179,19 @@ __device__ __forceinline__ void tma_issue(const StageArgs &P, const TmaMaps &M, 
   unsigned char *b = C.ring + s * STAGE_BYTES;
   uint64_t *bar = C.full + s;
   mbar_expect_tx(bar, stage_tx_bytes<KIND>());
-  tma_load_4d(b + OFF_CUR, &M.cur, bar, C.i0 - HX + P.shift, C.j0 - YL, kk, 0);
-  tma_load_4d(b + OFF_MET, &M.met, bar, C.i0 + P.shift, C.j0, kk, 0);
-  tma_load_4d(b + OFF_MED, &M.med, bar, C.i0 + P.shift, C.j0, kk, 0);
-  if (KIND == KIND_MID) tma_load_4d(b + OFF_PRE, &M.pre, bar, C.i0 + P.shift, C.j0, kk, 0);
-  if (KIND != KIND_FIRST) tma_load_4d(b + OFF_END, &M.end, bar, C.i0 + P.shift, C.j0, kk, 0);
+  // the wavefield tiles overlap their neighbours' (x-y halo): keep them in L2; everything else is touched once per stage
+  tma_load_4d_hint(b + OFF_CUR, &M.cur, bar, C.i0 - HX + P.shift, C.j0 - YL, kk, 0, C.pol_keep);
+  tma_load_4d_hint(b + OFF_MET, &M.met, bar, C.i0 + P.shift, C.j0, kk, 0, C.pol_stream);
+  tma_load_4d_hint(b + OFF_MED, &M.med, bar, C.i0 + P.shift, C.j0, kk, 0, C.pol_stream);
+  if (KIND == KIND_MID) tma_load_4d_hint(b + OFF_PRE, &M.pre, bar, C.i0 + P.shift, C.j0, kk, 0, C.pol_stream);
+  if (KIND != KIND_FIRST) tma_load_4d_hint(b + OFF_END, &M.end, bar, C.i0 + P.shift, C.j0, kk, 0, C.pol_stream);
 }
 
 // One plane. The march along z runs TOWARDS the short side of the one-sided zeta operator (upwards for
 // offsets {-3..1}, downwards for {-1..3}), so that three of its neighbours are planes already visited and only one
 // lies ahead: q0,q1,q2 = planes k-3d, k-2d, k-d (d = march direction), q3 = plane k, q4 receives plane k+d, which was
 // requested one iteration earlier (qn) -- at the same time as the TMA of that plane, so it is one DRAM read.
-template <int DX, int DY, int DZ, int KIND>
+template <int DX, int DY, int DZ, int KIND, bool PML>
 __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, const TmaCtx &C, int k, int it, int nplanes,
                                           const float (&q0)[9], const float (&q1)[9], const float (&q2)[9],
                                           const float (&q3)[9], float (&q4)[9], float (&qn)[9])
@@ -196,30 +199,31 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
   constexpr int YL = Ofs<DY>::left;
   constexpr int FX = Ofs<DX>::first, FY = Ofs<DY>::first;
   constexpr int DIR = DZ ? 1 : -1;
+  constexpr int NT = TX * TY;
   const int s = it % NST;
   const uint32_t parity = (it / NST) & 1;
   const float *cx = c_fd.coef[DX], *cy = c_fd.coef[DY], *cz = c_fd.coef[DZ];
 #pragma unroll
   for (int c = 0; c < 9; c++) q4[c] = qn[c];
   if (C.inarr && it + 1 < nplanes) {
+    const float *w = C.qptr + (long)(k + 2 * DIR) * (long)P.siz_slice;
 #pragma unroll
-    for (int c = 0; c < 9; c++) qn[c] = __ldg(P.cur + c * P.siz_vol + (size_t)(k + 2 * DIR) * P.siz_slice + C.pij);
+    for (int c = 0; c < 9; c++) qn[c] = __ldg(w + c * P.siz_vol);
   }
+  unsigned char *b = C.ring + s * STAGE_BYTES;
   mbar_wait(C.full + s, parity);
   if (C.active) {
-    const unsigned char *b = C.ring + s * STAGE_BYTES;
     const float *sc = (const float *)(b + OFF_CUR) + (C.ty + YL) * SXT + C.tx + HX;
     const float *sm = (const float *)(b + OFF_MET) + C.t;
     const float *sd = (const float *)(b + OFF_MED) + C.t;
-    const float *sp = (const float *)(b + OFF_PRE) + C.t;
-    const float *se = (const float *)(b + OFF_END) + C.t;
+    float *sp = (float *)(b + OFF_PRE) + C.t;   // w_pre in, w_tmp out
+    float *se = (float *)(b + OFF_END) + C.t;   // w_end in, w_end out
     const float(&qz)[9] = q3;   // centre plane of the queue
-    const size_t p = (size_t)k * P.siz_slice + C.pij;
     Met m;
-    m.xix = sm[0 * TX * TY]; m.xiy = sm[1 * TX * TY]; m.xiz = sm[2 * TX * TY];
-    m.etx = sm[3 * TX * TY]; m.ety = sm[4 * TX * TY]; m.etz = sm[5 * TX * TY];
-    m.ztx = sm[6 * TX * TY]; m.zty = sm[7 * TX * TY]; m.ztz = sm[8 * TX * TY];
-    const float lam = sd[0], mu = sd[TX * TY], slw = sd[2 * TX * TY];
+    m.xix = sm[0 * NT]; m.xiy = sm[1 * NT]; m.xiz = sm[2 * NT];
+    m.etx = sm[3 * NT]; m.ety = sm[4 * NT]; m.etz = sm[5 * NT];
+    m.ztx = sm[6 * NT]; m.zty = sm[7 * NT]; m.ztz = sm[8 * NT];
+    const float lam = sd[0], mu = sd[NT], slw = sd[2 * NT];
     const float lam2mu = lam + 2.0f * mu;
     Deriv d;
     float h[9];
@@ -233,11 +237,9 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
                   : cz[0] * q4[c] + cz[1] * q3[c] + cz[2] * q2[c] + cz[3] * q1[c] + cz[4] * q0[c];
     }
     hooke_iso(d, m, lam, mu, lam2mu, h);
-    pml_all_iso<KIND, 0>(P, C.i, C.j, k, d, m, lam, mu, lam2mu, slw, h);
+    if (PML) pml_all_iso<KIND, 0>(P, C.i, C.j, k, d, m, lam, mu, lam2mu, slw, h);
 #pragma unroll
-    for (int c = 3; c < 9; c++)
-      rk_store<KIND>(P.tmp, P.end, c * P.siz_vol + p, qz[c], (KIND == KIND_MID) ? sp[c * TX * TY] : 0.0f,
-                     (KIND != KIND_FIRST) ? se[c * TX * TY] : 0.0f, h[c], P.a, P.b);
+    for (int c = 3; c < 9; c++) rk_smem<KIND>(sp + c * NT, se + c * NT, qz[c], h[c], P.a, P.b);
     // ---- velocity half: needs the stress derivatives only
 #pragma unroll
     for (int c = 3; c < 9; c++) {
@@ -248,14 +250,22 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
                   : cz[0] * q4[c] + cz[1] * q3[c] + cz[2] * q2[c] + cz[3] * q1[c] + cz[4] * q0[c];
     }
     momentum(d, m, slw, h);
-    pml_all_iso<KIND, 1>(P, C.i, C.j, k, d, m, lam, mu, lam2mu, slw, h);
+    if (PML) pml_all_iso<KIND, 1>(P, C.i, C.j, k, d, m, lam, mu, lam2mu, slw, h);
 #pragma unroll
-    for (int c = 0; c < 3; c++)
-      rk_store<KIND>(P.tmp, P.end, c * P.siz_vol + p, qz[c], (KIND == KIND_MID) ? sp[c * TX * TY] : 0.0f,
-                     (KIND != KIND_FIRST) ? se[c * TX * TY] : 0.0f, h[c], P.a, P.b);
+    for (int c = 0; c < 3; c++) rk_smem<KIND>(sp + c * NT, se + c * NT, qz[c], h[c], P.a, P.b);
+    fence_proxy_async_smem();   // the results written above are read by the TMA store below
   }
-  __syncthreads();   // every thread is done with ring slot s
-  if (C.t == 0 && it + NST < nplanes) tma_issue<DX, DY, KIND>(P, M, C, k + NST * DIR, s);
+  __syncthreads();   // every thread is done with ring slot s; its PRE / END tiles now hold w_tmp / w_end of this plane
+  if (C.t == 0) {
+    const int tx0 = C.i0 - P.ni1, ty0 = C.j0 - P.nj1;
+    if (KIND != KIND_LAST) tma_store_4d_hint(&M.out_tmp, b + OFF_PRE, tx0, ty0, k, 0, C.pol_stream);
+    tma_store_4d_hint(&M.out_end, b + OFF_END, tx0, ty0, k, 0, C.pol_stream);
+    tma_store_commit();
+    if (it + NST < nplanes) {
+      tma_store_wait_read();   // the slot may be refilled once the stores have read it
+      tma_issue<DX, DY, KIND>(P, M, C, k + NST * DIR, s);
+    }
+  }
 }
 
 template <int DX, int DY, int DZ, int KIND>
@@ -266,13 +276,16 @@ __global__ void __launch_bounds__(TX *TY, 2) k_iso_main_tma(const StageArgs P, c
   C.ring = smem_raw;
   C.full = (uint64_t *)(C.ring + NST * STAGE_BYTES);
   C.tx = threadIdx.x; C.ty = threadIdx.y; C.t = C.ty * TX + C.tx;
-  C.i0 = P.ni1 + blockIdx.x * TX; C.j0 = P.nj1 + blockIdx.y * TY;
+  C.i0 = P.ni1 + (P.bx0 + blockIdx.x) * TX; C.j0 = P.nj1 + (P.by0 + blockIdx.y) * TY;
   C.i = C.i0 + C.tx; C.j = C.j0 + C.ty;
   const int k0 = P.kbeg + blockIdx.z * P.zchunk;
   C.k1 = min(k0 + P.zchunk - 1, P.kend);
   C.inarr = (C.i < P.nx) && (C.j < P.ny);
   C.active = (C.i <= P.ni2) && (C.j <= P.nj2);
   C.pij = (size_t)C.j * P.siz_line + C.i;
+  C.qptr = P.cur + C.pij;
+  C.pol_keep = (P.l2mode & 1) ? l2_policy_evict_last() : l2_policy_evict_normal();
+  C.pol_stream = (P.l2mode & 2) ? l2_policy_evict_first() : l2_policy_evict_normal();
 
   if (C.t == 0) {
 #pragma unroll
@@ -288,6 +301,16 @@ __global__ void __launch_bounds__(TX *TY, 2) k_iso_main_tma(const StageArgs P, c
     for (int s = 0; s < NST; s++)
       if (s < nplanes) tma_issue<DX, DY, KIND>(P, M, C, kf + s * DIR, s);
   }
+  // does this tile meet the slab of an x or y PML face? (block-uniform; the z faces are tested per plane)
+  bool pml_xy = false;
+#pragma unroll
+  for (int sd = 0; sd < 2; sd++) {
+    const PmlFaceDev &Fx = P.pml[0][sd], &Fy = P.pml[1][sd];
+    pml_xy |= Fx.on && C.i0 <= Fx.i2 && C.i0 + TX - 1 >= Fx.i1;
+    pml_xy |= Fy.on && C.j0 <= Fy.j2 && C.j0 + TY - 1 >= Fy.j1;
+  }
+  const int zk1 = P.pml[2][0].on ? P.pml[2][0].k2 : -1;            // planes k <= zk1 lie in the bottom slab
+  const int zk2 = P.pml[2][1].on ? P.pml[2][1].k1 : (1 << 30);     // planes k >= zk2 lie in the top slab
 
   float q0[9], q1[9], q2[9], q3[9], q4[9], qn[9];
 #pragma unroll
@@ -302,12 +325,15 @@ __global__ void __launch_bounds__(TX *TY, 2) k_iso_main_tma(const StageArgs P, c
     }
   }
   for (int it = 0; it < nplanes; it++) {
-    tma_plane<DX, DY, DZ, KIND>(P, M, C, kf + it * DIR, it, nplanes, q0, q1, q2, q3, q4, qn);
+    const int k = kf + it * DIR;
+    if (pml_xy || k <= zk1 || k >= zk2) tma_plane<DX, DY, DZ, KIND, true>(P, M, C, k, it, nplanes, q0, q1, q2, q3, q4, qn);
+    else tma_plane<DX, DY, DZ, KIND, false>(P, M, C, k, it, nplanes, q0, q1, q2, q3, q4, qn);
     // rotate the zeta queue (register moves; unrolling by 5 instead makes the loop body outgrow the
-    // 32 KB instruction cache and the kernel instruction-fetch bound -- profiles/r1d_summary.txt)
+    // instruction cache and the kernel instruction-fetch bound -- profiles/r1d_summary.txt)
 #pragma unroll
     for (int c = 0; c < 9; c++) { q0[c] = q1[c]; q1[c] = q2[c]; q2[c] = q3[c]; q3[c] = q4[c]; }
   }
+  if (C.t == 0) tma_store_wait_all();
 }
 
 // =============================================================================================
@@ -456,40 +482,47 @@ __global__ void __launch_bounds__(128) k_iso_top(const StageArgs P)
 }
 
 // =============================================================================================
+// interior rows of the tile rectangle [bx0,bx1) x [by0,by1) (tiles of TX x TY points counted from (ni1,nj1))
 template <int DX, int DY, int DZ, int KIND>
-static void launch_t(const StageArgs &P0, const TmaMaps *maps, int variant, int zchunk, cudaStream_t st, cudaEvent_t ev0,
-                     cudaEvent_t ev1, int *nlaunch)
+static void launch_main_t(const StageArgs &P0, const TmaMaps *maps, int variant, int zchunk, const int rect[4], cudaStream_t st,
+                          cudaEvent_t ev0, cudaEvent_t ev1, int *nlaunch)
 {
   StageArgs P = P0;
-  const int ni = P.ni2 - P.ni1 + 1, nj = P.nj2 - P.nj1 + 1;
   const int ktop = P.free_top ? P.nk2 - 3 : P.nk2 + 1;   // first row of the free-surface kernel
-  // interior rows
   P.kbeg = P.nk1; P.kend = (P.free_top ? ktop - 1 : P.nk2);
-  if (P.kend >= P.kbeg) {
-    const int nk = P.kend - P.kbeg + 1;
-    const int bx = (ni + TX - 1) / TX, by = (nj + TY - 1) / TY;
-    int nzc;
-    if (zchunk > 0) nzc = (nk + zchunk - 1) / zchunk;
-    else {
-      // z chunks: at least ~8 waves of 148 SMs x 2 resident blocks, chunks no shorter than 24 rows
-      nzc = 1;
-      while (nzc < nk && (long)bx * by * nzc < 148L * 2 * 8 && nk / (nzc + 1) >= 24) nzc++;
-    }
-    P.zchunk = (nk + nzc - 1) / nzc;
-    nzc = (nk + P.zchunk - 1) / P.zchunk;
-    dim3 grid(bx, by, nzc), block(TX, TY);
-    if (ev0) cudaEventRecord(ev0, st);
-    if (variant == 1 || !maps) k_iso_main<DX, DY, DZ, KIND><<<grid, block, 0, st>>>(P);
-    else k_iso_main_tma<DX, DY, DZ, KIND><<<grid, block, TMA_SMEM_BYTES, st>>>(P, *maps);
-    if (ev1) cudaEventRecord(ev1, st);
-    (*nlaunch)++;
+  const int bx = rect[1] - rect[0], by = rect[3] - rect[2];
+  if (P.kend < P.kbeg || bx <= 0 || by <= 0) return;
+  P.bx0 = rect[0]; P.by0 = rect[2];
+  const int nk = P.kend - P.kbeg + 1;
+  int nzc;
+  if (zchunk > 0) nzc = (nk + zchunk - 1) / zchunk;
+  else {
+    // z chunks: at least ~8 waves of 148 SMs x 2 resident blocks, chunks no shorter than 24 rows
+    nzc = 1;
+    while (nzc < nk && (long)bx * by * nzc < 148L * 2 * 8 && nk / (nzc + 1) >= 24) nzc++;
   }
-  if (P.free_top) {
-    P.kbeg = (ktop < P.nk1) ? P.nk1 : ktop; P.kend = P.nk2;
-    dim3 block(128), grid((ni + 127) / 128, nj, P.kend - P.kbeg + 1);
-    k_iso_top<DX, DY, DZ, KIND><<<grid, block, 0, st>>>(P);
-    (*nlaunch)++;
-  }
+  P.zchunk = (nk + nzc - 1) / nzc;
+  nzc = (nk + P.zchunk - 1) / P.zchunk;
+  dim3 grid(bx, by, nzc), block(TX, TY);
+  if (ev0) cudaEventRecord(ev0, st);
+  if (variant == 1 || !maps) k_iso_main<DX, DY, DZ, KIND><<<grid, block, 0, st>>>(P);
+  else k_iso_main_tma<DX, DY, DZ, KIND><<<grid, block, TMA_SMEM_BYTES, st>>>(P, *maps);
+  if (ev1) cudaEventRecord(ev1, st);
+  (*nlaunch)++;
+}
+
+// the free-surface rows (whole x-y range)
+template <int DX, int DY, int DZ, int KIND>
+static void launch_top_t(const StageArgs &P0, cudaStream_t st, int *nlaunch)
+{
+  if (!P0.free_top) return;
+  StageArgs P = P0;
+  const int ni = P.ni2 - P.ni1 + 1, nj = P.nj2 - P.nj1 + 1;
+  const int ktop = P.nk2 - 3;
+  P.kbeg = (ktop < P.nk1) ? P.nk1 : ktop; P.kend = P.nk2;
+  dim3 block(128), grid((ni + 127) / 128, nj, P.kend - P.kbeg + 1);
+  k_iso_top<DX, DY, DZ, KIND><<<grid, block, 0, st>>>(P);
+  (*nlaunch)++;
 }
 
 template <int DX, int DY, int DZ, int KIND> static int set_attr_t()
@@ -506,28 +539,47 @@ template <int KIND> static int set_attr_k()
 }
 int iso_kernels_init() { return set_attr_k<KIND_FIRST>() | set_attr_k<KIND_MID>() | set_attr_k<KIND_LAST>(); }
 
-template <int KIND>
-static void launch_k(const StageArgs &P, const TmaMaps *maps, int dx, int dy, int dz, int variant, int zchunk, cudaStream_t st,
-                     cudaEvent_t e0, cudaEvent_t e1, int *n)
-{
-  switch (dx * 4 + dy * 2 + dz) {
-    case 0: launch_t<0, 0, 0, KIND>(P, maps, variant, zchunk, st, e0, e1, n); break;
-    case 1: launch_t<0, 0, 1, KIND>(P, maps, variant, zchunk, st, e0, e1, n); break;
-    case 2: launch_t<0, 1, 0, KIND>(P, maps, variant, zchunk, st, e0, e1, n); break;
-    case 3: launch_t<0, 1, 1, KIND>(P, maps, variant, zchunk, st, e0, e1, n); break;
-    case 4: launch_t<1, 0, 0, KIND>(P, maps, variant, zchunk, st, e0, e1, n); break;
-    case 5: launch_t<1, 0, 1, KIND>(P, maps, variant, zchunk, st, e0, e1, n); break;
-    case 6: launch_t<1, 1, 0, KIND>(P, maps, variant, zchunk, st, e0, e1, n); break;
-    default: launch_t<1, 1, 1, KIND>(P, maps, variant, zchunk, st, e0, e1, n); break;
+#define CGFD_DISPATCH_DIR(CALL)                                                                   \
+  switch (dx * 4 + dy * 2 + dz) {                                                                  \
+    case 0: CALL(0, 0, 0); break; case 1: CALL(0, 0, 1); break; case 2: CALL(0, 1, 0); break;      \
+    case 3: CALL(0, 1, 1); break; case 4: CALL(1, 0, 0); break; case 5: CALL(1, 0, 1); break;      \
+    case 6: CALL(1, 1, 0); break; default: CALL(1, 1, 1); break;                                   \
   }
+
+template <int KIND>
+static void launch_main_k(const StageArgs &P, const TmaMaps *maps, int dx, int dy, int dz, int variant, int zchunk,
+                          const int rect[4], cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, int *n)
+{
+#define CALL(a, b, c) launch_main_t<a, b, c, KIND>(P, maps, variant, zchunk, rect, st, e0, e1, n)
+  CGFD_DISPATCH_DIR(CALL)
+#undef CALL
+}
+template <int KIND> static void launch_top_k(const StageArgs &P, int dx, int dy, int dz, cudaStream_t st, int *n)
+{
+#define CALL(a, b, c) launch_top_t<a, b, c, KIND>(P, st, n)
+  CGFD_DISPATCH_DIR(CALL)
+#undef CALL
 }
 
-void launch_iso_stage(const StageArgs &P, const TmaMaps *maps, int dx, int dy, int dz, int kind, int variant, int zchunk,
-                      cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1, int *nlaunch)
+void iso_tile_counts(const StageArgs &P, int *ntx, int *nty)
 {
-  if (kind == KIND_FIRST) launch_k<KIND_FIRST>(P, maps, dx, dy, dz, variant, zchunk, st, ev0, ev1, nlaunch);
-  else if (kind == KIND_MID) launch_k<KIND_MID>(P, maps, dx, dy, dz, variant, zchunk, st, ev0, ev1, nlaunch);
-  else launch_k<KIND_LAST>(P, maps, dx, dy, dz, variant, zchunk, st, ev0, ev1, nlaunch);
+  *ntx = (P.ni2 - P.ni1 + 1 + TX - 1) / TX;
+  *nty = (P.nj2 - P.nj1 + 1 + TY - 1) / TY;
+}
+
+void launch_iso_main(const StageArgs &P, const TmaMaps *maps, int dx, int dy, int dz, int kind, int variant, int zchunk,
+                     const int rect[4], cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1, int *nlaunch)
+{
+  if (kind == KIND_FIRST) launch_main_k<KIND_FIRST>(P, maps, dx, dy, dz, variant, zchunk, rect, st, ev0, ev1, nlaunch);
+  else if (kind == KIND_MID) launch_main_k<KIND_MID>(P, maps, dx, dy, dz, variant, zchunk, rect, st, ev0, ev1, nlaunch);
+  else launch_main_k<KIND_LAST>(P, maps, dx, dy, dz, variant, zchunk, rect, st, ev0, ev1, nlaunch);
+}
+
+void launch_iso_top(const StageArgs &P, int dx, int dy, int dz, int kind, cudaStream_t st, int *nlaunch)
+{
+  if (kind == KIND_FIRST) launch_top_k<KIND_FIRST>(P, dx, dy, dz, st, nlaunch);
+  else if (kind == KIND_MID) launch_top_k<KIND_MID>(P, dx, dy, dz, st, nlaunch);
+  else launch_top_k<KIND_LAST>(P, dx, dy, dz, st, nlaunch);
 }
 
 }  // namespace cgfd

@@ -76,6 +76,22 @@ __device__ __forceinline__ void rk_store(float *__restrict__ tmp, float *__restr
   }
 }
 
+// the same update done in place in shared memory: sp holds w_pre (mid) and receives w_tmp, se holds w_end (mid, last)
+// and receives the new w_end; the tiles are then written out by one TMA store each
+template <int KIND>
+__device__ __forceinline__ void rk_smem(float *sp, float *se, float cur_c, float rhs, float a, float b)
+{
+  if (KIND == KIND_FIRST) {
+    *sp = cur_c + a * rhs;
+    *se = cur_c + b * rhs;
+  } else if (KIND == KIND_MID) {
+    *sp = *sp + a * rhs;
+    *se = *se + b * rhs;
+  } else {
+    *se = *se + b * rhs;
+  }
+}
+
 // ADE CFS-PML correction of one face at one slab point, isotropic
 // (forward/sv_curv_col_el_iso.c:763-905 for x, 915-1054 for y, 1058-1137 for z):
 //   rhs_n  = RHS terms holding the face-normal derivative only
