@@ -91,7 +91,10 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(self.rows)}
 
 
-def build_rank_problem(size, rank, nranks):
+def build_rank_problem(size, rank, nranks, device=None):
+    """One rank's block of the global hill problem. device=None: numpy on the host (hostsetup); device='cuda:N': the same
+    formulas as torch expressions on that GPU (devsetup) -- used for the 800x800x400-per-GPU runs, where the numpy route
+    needs ~45 GB of host memory and minutes per rank."""
     from cgfd3d_b200 import hostsetup as hs
     ni, nj, nk = size
     px, py = proc_grid(nranks)
@@ -104,8 +107,13 @@ def build_rank_problem(size, rank, nranks):
     dh = (100.0, 100.0, 100.0)
     sigma = 0.1 * max(gni, gnj) * dh[0]
     # dt below the CFL bound of the stretched grid (estimate_dt on the full array is slow; checked in tests)
-    prob = hs.build_problem(ni, nj, nk, dh=dh, topo="hill", hill=(1000.0, sigma), pml_layers=10, free_top=True,
-                            dt=0.012, sub=(ix * ni, iy * nj, gni, gnj, neigh))
+    if device is None:
+        prob = hs.build_problem(ni, nj, nk, dh=dh, topo="hill", hill=(1000.0, sigma), pml_layers=10, free_top=True,
+                                dt=0.012, sub=(ix * ni, iy * nj, gni, gnj, neigh))
+    else:
+        from cgfd3d_b200 import devsetup
+        prob = devsetup.build_problem(ni, nj, nk, device=device, dh=dh, hill=(1000.0, sigma), pml_layers=10, free_top=True,
+                                      dt=0.012, sub=(ix * ni, iy * nj, gni, gnj, neigh))
     # one explosive moment source under the hill top, on the rank that owns it
     gsi, gsj = gni // 2, gnj // 2
     if ix * ni <= gsi < (ix + 1) * ni and iy * nj <= gsj < (iy + 1) * nj:
@@ -130,11 +138,15 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     size = args.size or ((400, 400, 200) if nranks == 1 else (800, 800, 400))
     t0 = time.time()
-    prob = build_rank_problem(size, rank, nranks)
+    on_device = size[0] * size[1] * size[2] > 64e6   # big blocks: build the set-up arrays on the GPU (see devsetup.py)
+    prob = build_rank_problem(size, rank, nranks, device=("cuda:%d" % local) if on_device else None)
     t_host = time.time() - t0
     t0 = time.time()
     S = solver.Solver(prob, device=local)
     t_upload = time.time() - t0
+    if on_device:   # the library holds its own padded copies
+        prob.metric = prob.media = None
+        torch.cuda.empty_cache()
     if nranks > 1:
         uid = [solver.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
@@ -219,12 +231,12 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
             "roofline": {"bound": "hbm", "kernel": "k_iso_main", "achieved": None if ach is None else round(ach, 1), "peak": peak,
-                         "unit": "GB/s", "frac": None if ach is None else round(ach / peak, 4), "traffic": None,
+                         "unit": "GB/s", "frac": None if ach is None else round(ach / peak, 4), "traffic": ncu_traffic(size),
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                          "launches_timed": int(main_n), "avg_launch_ms": round(main_ms / max(main_n, 1), 4),
                          "algorithmic_bytes_per_launch": int((BYTES_PER_POINT_STEP_ISO / 4.0) * main_pts),
                          "whole_step_frac": round(BYTES_PER_POINT_STEP_ISO * npts / (ms_max / K * 1e-3) / 1e9 / peak, 4)},
-            "setup_s": {"host_arrays": round(t_host, 2), "upload": round(t_upload, 2)},
+            "setup_s": {"arrays": round(t_host, 2), "arrays_built_on": "gpu (torch)" if on_device else "host (numpy)", "upload": round(t_upload, 2)},
             "wall_s_timed": round(tw1 - tw0, 4), "finite": finite,
         }
         if nranks == 1 and not args.no_cpu_baseline:
@@ -235,6 +247,16 @@ def run_ours(args):
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(out), flush=True)
+
+
+def ncu_traffic(size):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed ncu --set full
+    capture (profiles/traffic.json), valid for the workload it was captured on; None otherwise."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return t["bytes_per_launch"] if list(size) == t["size"] else None
+    except Exception:
+        return None
 
 
 # ---- reference CPU arm --------------------------------------------------------------------------
@@ -302,7 +324,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--size", type=parse_size, default=None)

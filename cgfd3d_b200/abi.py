@@ -106,6 +106,9 @@ def as_f(a: np.ndarray | None):
     """float32 C-contiguous ndarray -> POINTER(c_float) (NULL for None). Caller keeps `a` alive."""
     if a is None:
         return fptr()
+    if hasattr(a, "data_ptr"):   # torch tensor (host or device memory; the library takes either for metric / media)
+        assert str(a.dtype) == "torch.float32" and a.is_contiguous()
+        return C.cast(a.data_ptr(), fptr)
     assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"], (a.dtype, a.flags)
     return a.ctypes.data_as(fptr)
 

@@ -12,10 +12,50 @@
 #include "aux_kernels.cuh"
 #include "cgfd_dev.cuh"
 #include "halo.h"
+#include "physics.cuh"
 
 using namespace cgfd;
 
 static thread_local std::string g_err;
+
+// medium dispatch (ABI medium type -> kernel family)
+static int med_of(int medium_type)
+{
+  switch (medium_type) {
+    case CGFD_MEDIUM_ELASTIC_ISO: return MED_ISO;
+    case CGFD_MEDIUM_ELASTIC_VTI: return MED_VTI;
+    case CGFD_MEDIUM_ELASTIC_ANISO: return MED_ANISO;
+    case CGFD_MEDIUM_VISCOELASTIC_ISO: return MED_VIS;
+    default: return -1;
+  }
+}
+#define MED_SWITCH(med, CALL)                                                              \
+  switch (med) {                                                                           \
+    case MED_ISO: CALL(MED_ISO); break; case MED_VTI: CALL(MED_VTI); break;                \
+    case MED_ANISO: CALL(MED_ANISO); break; default: CALL(MED_VIS); break;                 \
+  }
+static int kernels_init(int med)
+{
+  int rc = 1;
+#define CALL(M) rc = med_kernels_init<M>()
+  MED_SWITCH(med, CALL)
+#undef CALL
+  return rc;
+}
+static void launch_main(int med, const StageArgs &P, const TmaMaps *maps, const int *dir, int kind, int zchunk, const int rect[4],
+                        cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, int *nl)
+{
+#define CALL(M) med_launch_main<M>(P, maps, dir[0], dir[1], dir[2], kind, zchunk, rect, st, e0, e1, nl)
+  MED_SWITCH(med, CALL)
+#undef CALL
+}
+static void launch_top(int med, const StageArgs &P, const int *dir, int kind, cudaStream_t st, int *nl)
+{
+#define CALL(M) med_launch_top<M>(P, dir[0], dir[1], dir[2], kind, st, nl)
+  MED_SWITCH(med, CALL)
+#undef CALL
+}
+
 static int fail(const std::string &m) { g_err = m; return 1; }
 #define CK(call)                                                                                   \
   do {                                                                                             \
@@ -45,7 +85,7 @@ struct cgfd_b200_ctx {
   cgfd_grid_t g;
   cgfd_fd_t fd;
   float dt = 0;
-  int medium = 0, nmaxwell = 0, ncmp = 9, nmedia = 0;
+  int medium = 0, med = 0, nmaxwell = 0, ncmp = 9, nmedia = 0;
   float wl[CGFD_MAX_MAXWELL];
   // padded device layout (see cgfd_dev.cuh): pitch PX, index 0 of a row sits `shift` floats in
   int PX = 0, shift = 0;
@@ -160,6 +200,25 @@ static int make_map(cgfd_b200_ctx *c, CUtensorMap *m, float *base, int ncomp, in
   return 0;
 }
 
+// metric / media arrays may be handed over as host or as device pointers (unified addressing tells which)
+static bool is_device_ptr(const void *p)
+{
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice;
+}
+struct Peek {   // read single elements of such an array on the host
+  const float *p; bool dev;
+  explicit Peek(const float *q) : p(q), dev(is_device_ptr(q)) {}
+  float operator[](size_t i) const
+  {
+    if (!dev) return p[i];
+    float v = 0.0f;
+    cudaMemcpy(&v, p + i, sizeof(float), cudaMemcpyDeviceToHost);
+    return v;
+  }
+};
+
 static float fun_gauss(float t, float a, float t0)
 {
   // forward/src_t.c:2178-2184
@@ -195,8 +254,8 @@ static int setup_sources(cgfd_b200_ctx *c, const cgfd_problem_t *p)
   if (s.total_number <= 0) return 0;
   const cgfd_grid_t &g = c->g;
   const size_t L = g.nx, S = (size_t)g.nx * g.ny;
-  const float *jac = p->metric[CGFD_JAC];
-  const float *slw = p->media[(p->medium_type == CGFD_MEDIUM_ELASTIC_VTI) ? 5 : (p->medium_type == CGFD_MEDIUM_ELASTIC_ANISO) ? 21 : 2];
+  const Peek jac(p->metric[CGFD_JAC]);
+  const Peek slw(p->media[(p->medium_type == CGFD_MEDIUM_ELASTIC_VTI) ? 5 : (p->medium_type == CGFD_MEDIUM_ELASTIC_ANISO) ? 21 : 2]);
   std::vector<int64_t> pt_iptr; std::vector<int> pt_src, pt_bnd; std::vector<float> pt_wV, pt_wM;
   // does point (i,j,k) belong to the boundary phase of a stage (free-surface rows, tiles next to an inter-rank face)?
   auto bnd = [&](int i, int j, int k) -> int {
@@ -327,8 +386,16 @@ extern "C" int cgfd_b200_create(const cgfd_problem_t *p, int device, cgfd_b200_c
 {
   *out = nullptr;
   if (!p || p->abi_version != CGFD_ABI_VERSION) return fail("cgfd_b200_create: ABI version mismatch");
-  if (p->medium_type != CGFD_MEDIUM_ELASTIC_ISO)
-    return fail("cgfd_b200_create: medium type " + std::to_string(p->medium_type) + " is not implemented on the GPU yet");
+  const int med = med_of(p->medium_type);
+  if (med < 0) return fail("cgfd_b200_create: unknown medium type " + std::to_string(p->medium_type));
+  {
+    const int N = (med == MED_VIS) ? p->nmaxwell : 0;
+    const int want_media = (med == MED_ISO) ? 3 : (med == MED_VTI) ? 6 : (med == MED_ANISO) ? 22 : 3 + 2 * N;
+    if (med == MED_VIS && (N < 1 || N > CGFD_MAX_MAXWELL)) return fail("cgfd_b200_create: visco-elastic medium needs 1..8 Maxwell bodies");
+    if (p->nmedia != want_media) return fail("cgfd_b200_create: medium type " + std::to_string(p->medium_type) + " expects " + std::to_string(want_media) + " media arrays");
+    if (p->ncmp != 9 + 6 * N) return fail("cgfd_b200_create: ncmp must be 9 + 6 * nmaxwell");
+    for (int m = 0; m < p->nmedia; m++) if (!p->media[m]) return fail("cgfd_b200_create: media array missing");
+  }
   int ndev = cgfd_b200_device_count();
   if (ndev <= 0) return fail("cgfd_b200_create: no CUDA device visible; this library has no CPU fallback");
   if (device < 0 || device >= ndev) return fail("cgfd_b200_create: bad device ordinal");
@@ -337,7 +404,7 @@ extern "C" int cgfd_b200_create(const cgfd_problem_t *p, int device, cgfd_b200_c
   cgfd_b200_ctx *c = new cgfd_b200_ctx();
   c->device = device;
   c->g = p->grid; c->fd = p->fd; c->dt = p->dt;
-  c->medium = p->medium_type; c->nmaxwell = p->nmaxwell; c->ncmp = p->ncmp; c->nmedia = p->nmedia;
+  c->medium = p->medium_type; c->med = med; c->nmaxwell = (med == MED_VIS) ? p->nmaxwell : 0; c->ncmp = p->ncmp; c->nmedia = p->nmedia;
   for (int n = 0; n < CGFD_MAX_MAXWELL; n++) c->wl[n] = p->visco_wl[n];
   c->free_top = p->free_top; c->timg_mode = p->timg_mode;
   for (int n = 0; n < 4; n++) c->neigh[n] = p->neigh[n];
@@ -362,7 +429,7 @@ extern "C" int cgfd_b200_create(const cgfd_problem_t *p, int device, cgfd_b200_c
     CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   }
   c->ntx = (g.ni2 - g.ni1 + 1 + TILE_X - 1) / TILE_X; c->nty = (g.nj2 - g.nj1 + 1 + TILE_Y - 1) / TILE_Y;
-  if (iso_kernels_init()) { delete c; return fail("cgfd_b200_create: cudaFuncSetAttribute failed (needs sm_100 shared memory sizes)"); }
+  if (kernels_init(c->med)) { delete c; return fail("cgfd_b200_create: cudaFuncSetAttribute failed (needs sm_100 shared memory sizes)"); }
   CK(cudaEventCreate(&c->run0)); CK(cudaEventCreate(&c->run1));
 
   FdConst fc;
@@ -392,14 +459,15 @@ extern "C" int cgfd_b200_create(const cgfd_problem_t *p, int device, cgfd_b200_c
   {
     int mrc = 0;
     for (int l = 0; l < 4 && !mrc; l++) {
-      mrc |= make_map(c, &c->map_halo[l], c->lev[l], 9, TILE_X + 2 * HALO_X, TILE_Y + 4, 9);
-      mrc |= make_map(c, &c->map_cen[l], c->lev[l], 9, TILE_X, TILE_Y, 9);
-      mrc |= make_map(c, &c->map_out[l], c->lev[l], 9, TILE_X, TILE_Y, 9, true);
+      mrc |= make_map(c, &c->map_halo[l], c->lev[l], c->ncmp, TILE_X + 2 * HALO_X, TILE_Y + 4, 9);
+      mrc |= make_map(c, &c->map_cen[l], c->lev[l], c->ncmp, TILE_X, TILE_Y, 9);
+      mrc |= make_map(c, &c->map_out[l], c->lev[l], c->ncmp, TILE_X, TILE_Y, 9, true);
     }
     if (!mrc) mrc |= make_map(c, &c->map_met, c->metric_blk + c->V /* skip jac */, 9, TILE_X, TILE_Y, 9);
-    if (!mrc) mrc |= make_map(c, &c->map_med, c->media_blk, p->nmedia, TILE_X, TILE_Y, 3);
+    const int ntile = (med == MED_ISO || med == MED_VIS) ? 3 : p->nmedia;   // media arrays staged per plane (Med<MED>::NTILE)
+    if (!mrc) mrc |= make_map(c, &c->map_med, c->media_blk, p->nmedia, TILE_X, TILE_Y, ntile);
     c->have_maps = (mrc == 0);
-    if (mrc && c->variant != 1) { cgfd_b200_destroy(c); return 1; }
+    if (mrc) { cgfd_b200_destroy(c); return 1; }
   }
 
   for (int idim = 0; idim < 3; idim++) for (int is = 0; is < 2; is++) {
@@ -588,8 +656,8 @@ static int run_stage(cgfd_b200_ctx *c, StageArgs &P, int it, int ipair, int ista
   const int nb = split_tiles(c, halo_w != nullptr, bnd, inner);
   if (two) { CK(cudaEventRecord(c->ev_fork, c->st)); CK(cudaStreamWaitEvent(c->st2, c->ev_fork, 0)); }
   // ---- boundary phase
-  launch_iso_top(P, dir[0], dir[1], dir[2], kind, sb, &nl);
-  for (int n = 0; n < nb; n++) launch_iso_main(P, mp, dir[0], dir[1], dir[2], kind, c->variant, c->zchunk, bnd[n], sb, nullptr, nullptr, &nl);
+  launch_top(c->med, P, dir, kind, sb, &nl);
+  for (int n = 0; n < nb; n++) launch_main(c->med, P, mp, dir, kind, c->zchunk, bnd[n], sb, nullptr, nullptr, &nl);
   if (c->has_src && c->src_nb > 0) {
     k_src_inject<<<(c->src_nb + 127) / 128, 128, 0, sb>>>(c->src, 0, c->src_nb, it, istage, c->lev[itmp] + sh, c->lev[iend] + sh, a, b, c->V, kind);
     nl++;
@@ -600,7 +668,7 @@ static int run_stage(cgfd_b200_ctx *c, StageArgs &P, int it, int ipair, int ista
   }
   if (two) CK(cudaEventRecord(c->ev_join, c->st2));
   // ---- interior phase
-  launch_iso_main(P, mp, dir[0], dir[1], dir[2], kind, c->variant, c->zchunk, inner, c->st, e0, e1, &nl);
+  launch_main(c->med, P, mp, dir, kind, c->zchunk, inner, c->st, e0, e1, &nl);
   if (c->has_src && c->src.npts > c->src_nb) {
     const int cnt = c->src.npts - c->src_nb;
     k_src_inject<<<(cnt + 127) / 128, 128, 0, c->st>>>(c->src, c->src_nb, cnt, it, istage, c->lev[itmp] + sh, c->lev[iend] + sh, a, b, c->V, kind);
@@ -648,6 +716,13 @@ extern "C" int cgfd_b200_run(cgfd_b200_ctx *c, int it0, int nsteps)
     }
     float *wnew = c->lev[c->iend] + c->shift, *wold = c->lev[c->ipre] + c->shift;
     const cgfd_grid_t &g = c->g;
+    if (c->med == MED_VIS && c->free_top) {
+      // after the halo exchange of w_end, like the reference (forward/drv_rk_curv_col.c:419-445)
+      if (!c->mats[3]) return fail("visco-elastic free surface needs matD");
+      dim3 blk(128), grd((g.ni2 - g.ni1 + 128) / 128, g.nj2 - g.nj1 + 1);
+      k_vis_free<<<grd, blk, 0, c->st>>>(wnew, c->V, c->PX, g.nx, g.ny, g.ni1, g.ni2, g.nj1, g.nj2, g.nk2, c->mats[3]);
+      c->total_launches++;
+    }
     if (c->ablexp) {
       for (int n = 0; n < 6; n++) {
         const int *B = c->ablexp_blk[n];
@@ -730,8 +805,8 @@ extern "C" int cgfd_b200_onestage(cgfd_b200_ctx *c, int it, int ipair, int istag
   }
   const int *dir = c->fd.dir[ipair][istage];
   const int whole[4] = {0, c->ntx, 0, c->nty};
-  launch_iso_top(P, dir[0], dir[1], dir[2], KIND_MID, c->st, &nl);
-  launch_iso_main(P, c->have_maps ? &maps : nullptr, dir[0], dir[1], dir[2], KIND_MID, c->variant, c->zchunk, whole, c->st, nullptr, nullptr, &nl);
+  launch_top(c->med, P, dir, KIND_MID, c->st, &nl);
+  launch_main(c->med, P, &maps, dir, KIND_MID, c->zchunk, whole, c->st, nullptr, nullptr, &nl);
   if (c->has_src)
     k_src_inject<<<(c->src.npts + 127) / 128, 128, 0, c->st>>>(c->src, 0, c->src.npts, it, istage, c->lev[iout] + sh, c->lev[izero] + sh, 1.0f, 0.0f, c->V, KIND_MID);
   CK(cudaGetLastError());
@@ -806,7 +881,9 @@ extern "C" int cgfd_b200_comm_init(cgfd_b200_ctx *c, const char id[128], int ran
 {
   CK(cudaSetDevice(c->device));
   if (c->halo) return fail("comm_init: already initialised");
-  c->halo = halo_create(id, rank, nranks, c->neigh, c->g, c->ncmp, c->V, c->PX, c->st);
+  // the 6*N memory variables of the visco-elastic medium have no stencil; only the 9 wavefield components travel
+  // (the reference sends all ncmp, forward/drv_rk_curv_col.c:308)
+  c->halo = halo_create(id, rank, nranks, c->neigh, c->g, 9, c->V, c->PX, c->st);
   if (!c->halo) return fail(halo_error());
   return 0;
 }

@@ -105,6 +105,39 @@ __global__ void k_pg(const float *w_new, const float *w_old, size_t V, int pitch
   }
 }
 
+// visco-elastic free surface: after the last RK stage the surface stress is rotated into the local frame of the surface,
+// its normal components are dropped and it is rotated back (sv_curv_col_vis_iso_free, forward/sv_curv_col_vis_iso.c:509-623):
+// Tl = (D T D^T) restricted to the two tangential directions, T <- D^T Tl D, with D = matD[(j*nx+i)*9 ..].
+__global__ void k_vis_free(float *w, size_t V, int pitch, int nx, int ny, int ni1, int ni2, int nj1, int nj2, int nk2, const float *matD)
+{
+  int i = ni1 + blockIdx.x * blockDim.x + threadIdx.x;
+  int j = nj1 + blockIdx.y;
+  if (i > ni2 || j > nj2) return;
+  const size_t p = ((size_t)nk2 * ny + j) * pitch + i;
+  const float *D = matD + ((size_t)j * nx + i) * 9;
+  const float d11 = D[0], d12 = D[1], d13 = D[2], d21 = D[3], d22 = D[4], d23 = D[5], d31 = D[6], d32 = D[7], d33 = D[8];
+  const float Txx = w[TXX * V + p], Tyy = w[TYY * V + p], Tzz = w[TZZ * V + p], Tyz = w[TYZ * V + p], Txz = w[TXZ * V + p],
+              Txy = w[TXY * V + p];
+  float Tl[3][3] = {{0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.0f}};
+  Tl[0][0] = d11 * d11 * Txx + d12 * d12 * Tyy + d13 * d13 * Tzz + 2 * (d11 * d12 * Txy + d11 * d13 * Txz + d12 * d13 * Tyz);
+  Tl[0][1] = d11 * d21 * Txx + d12 * d22 * Tyy + d13 * d23 * Tzz + (d11 * d22 + d12 * d21) * Txy + (d11 * d23 + d21 * d13) * Txz
+           + (d12 * d23 + d22 * d13) * Tyz;
+  Tl[1][1] = d21 * d21 * Txx + d22 * d22 * Tyy + d23 * d23 * Tzz + 2 * (d21 * d22 * Txy + d21 * d23 * Txz + d22 * d23 * Tyz);
+  Tl[1][0] = Tl[0][1];
+  const float Dm[3][3] = {{d11, d12, d13}, {d21, d22, d23}, {d31, d32, d33}};
+  float DTl[3][3], Tg[3][3];   // DTl = D^T Tl ; Tg = DTl D (fdlib_math_matmul3x3, lib/fdlib_math.c:37-49)
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) DTl[r][c] = Dm[0][r] * Tl[0][c] + Dm[1][r] * Tl[1][c] + Dm[2][r] * Tl[2][c];
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) Tg[r][c] = DTl[r][0] * Dm[0][c] + DTl[r][1] * Dm[1][c] + DTl[r][2] * Dm[2][c];
+  w[TXX * V + p] = Tg[0][0]; w[TYY * V + p] = Tg[1][1]; w[TZZ * V + p] = Tg[2][2];
+  w[TXY * V + p] = Tg[0][1]; w[TXZ * V + p] = Tg[0][2]; w[TYZ * V + p] = Tg[1][2];
+}
+
 // exponential sponge: W *= min(Ex[i],Ey[j],Ez[k]) inside one shell block (forward/bdry_t.c:840-890)
 __global__ void k_ablexp(float *w, size_t V, int ncmp, int nx, int ny, int i1, int i2, int j1, int j2, int k1, int k2,
                          const float *Ex, const float *Ey, const float *Ez)

@@ -30,6 +30,7 @@ __global__ void k_pack_box(const float *w, int nx, int ny, int i1, int ni, int d
                            int dk, float *out);
 __global__ void k_pg(const float *w_new, const float *w_old, size_t V, int pitch, int nx, int ny, int ni1, int ni2, int nj1,
                      int nj2, int nk2, float dt, float *PG, float *Dis);
+__global__ void k_vis_free(float *w, size_t V, int pitch, int nx, int ny, int ni1, int ni2, int nj1, int nj2, int nk2, const float *matD);
 __global__ void k_ablexp(float *w, size_t V, int ncmp, int nx, int ny, int i1, int i2, int j1, int j2, int k1, int k2,
                          const float *Ex, const float *Ey, const float *Ez);
 __global__ void k_halo_copy(float *w, float *buf, size_t V, int ncmp, int nx, int ny, int i1, int ni, int j1, int nj, int k1,

@@ -51,7 +51,8 @@ struct StageArgs {
   int kbeg, kend;               // rows handled by this launch, inclusive
   int zchunk;                   // rows per block along z (main kernel)
   int bx0, by0;                 // first tile of this launch along x / y (main kernel)
-  int l2mode;                   // bit 0: wavefield tiles evict_last, bit 1: touch-once operands and results evict_first
+  int l2mode;                   // bit 0: wavefield tiles evict_last, bit 1: touch-once operands and results evict_first;
+                                // bit 2: no PML-free fast path (every block-plane runs the PML copy of the loop body)
   size_t siz_line, siz_slice, siz_vol;   // padded pitch, pitch*ny, pitch*ny*nz
   const float *cur;             // w_cur  [ncmp][nz][ny][nx]
   const float *pre;             // w_pre
@@ -81,14 +82,15 @@ struct TmaMaps {
   CUtensorMap out_tmp, out_end;
 };
 
-// launchers (kernels_*.cu); dir = direction index per axis of this stage's operator
+// launchers, one explicit instantiation per medium (kernels_{iso,vti,aniso,vis}.cu); dir = direction index per axis of
+// this stage's operator; MED = MED_* of physics.cuh
+template <int MED> int med_kernels_init();   // one-time function attributes (dynamic shared memory)
 // interior rows of the tile rectangle rect = {bx0, bx1, by0, by1} (tiles of TILE_X x TILE_Y points from (ni1, nj1))
-void launch_iso_main(const StageArgs &P, const TmaMaps *maps, int dx, int dy, int dz, int kind, int variant, int zchunk,
-                     const int rect[4], cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1, int *nlaunch);
+template <int MED>
+void med_launch_main(const StageArgs &P, const TmaMaps *maps, int dx, int dy, int dz, int kind, int zchunk, const int rect[4],
+                     cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1, int *nlaunch);
 // the four free-surface rows, whole x-y range (no-op without a free top)
-void launch_iso_top(const StageArgs &P, int dx, int dy, int dz, int kind, cudaStream_t st, int *nlaunch);
-void iso_tile_counts(const StageArgs &P, int *ntx, int *nty);
-int iso_kernels_init();   // one-time function attributes (dynamic shared memory)
+template <int MED> void med_launch_top(const StageArgs &P, int dx, int dy, int dz, int kind, cudaStream_t st, int *nlaunch);
 constexpr int TILE_X = 32, TILE_Y = 8, HALO_X = 4;
 
 }  // namespace cgfd

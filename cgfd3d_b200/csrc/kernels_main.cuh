@@ -1,0 +1,494 @@
+// RHS + CFS-PML + free surface + RK stage update, one fused pass per stage, for one medium (template parameter MED).
+// Included by kernels_{iso,vti,aniso,vis}.cu, each of which instantiates one medium.
+//
+//   k_main_tma : all rows below the free-surface rows. One thread per (i,j) column of a 32x8 tile marching along z.
+//                Every operand of a plane -- the 9 wavefield components with their x-y halo, 9 metric and the media
+//                arrays, w_pre and w_end -- is brought into a 2-slot shared-memory ring by TMA (cp.async.bulk.tensor,
+//                one elected thread, mbarrier completion), two planes ahead of the arithmetic; the zeta stencil lives
+//                in a 5-deep register queue per component; the RK update is done in place in the ring slot and
+//                written back by TMA stores.
+//                Restates *_rhs_inner (forward/sv_curv_col_el_iso.c:208-441, vti.c:200-397, aniso.c:233-497),
+//                *_rhs_cfspml (iso.c:644-1146, vti.c:592-1077, aniso.c:717-1259), sv_curv_col_vis_iso_atten
+//                (forward/sv_curv_col_vis_iso.c:250-347) and the RK axpy loops of forward/drv_rk_curv_col.c:292-446
+//                without ever writing the RHS to memory.
+//   k_top      : the top four rows when the top is a free surface: traction-image momentum RHS
+//                (sv_curv_col_el_rhs_timg_z2, forward/sv_curv_col_el.c:30-305), reduced-order / matrix Dz for the
+//                stress RHS (*_rhs_vlow_z2, iso.c:451-634, vti.c:407-582, aniso.c:507-707), PML with its
+//                free-surface terms, attenuation, RK update.
+#pragma once
+#include "physics.cuh"
+#include "tma.cuh"
+
+namespace cgfd {
+
+extern __constant__ FdConst c_fd;
+
+template <int D> struct Ofs {            // stencil offsets of direction index D
+  static constexpr int first = D ? -3 : -1;
+  static constexpr int left = D ? 3 : 1;   // points on the negative side
+  static constexpr int right = D ? 1 : 3;
+};
+
+constexpr int TX = TILE_X, TY = TILE_Y;
+constexpr int SX = TX + 4, SY = TY + 4;
+
+// =============================================================================================
+// interior kernel: TMA-fed shared-memory ring
+// =============================================================================================
+constexpr int NST = 2;                               // ring depth (planes in flight per block)
+// TMA needs a 16-byte aligned start along x, so the halo tile carries 4 columns on either side of
+// the 32 centre columns (the operators reach at most 3): pitch 40 floats, centre at column 4.
+constexpr int HX = HALO_X;
+constexpr int SXT = TX + 2 * HX;
+constexpr int CEN_BYTES = TX * TY * 4;               // one centre tile of one array
+constexpr int CUR_BYTES = 9 * SY * SXT * 4;          // 9 components with halo
+constexpr int OFF_CUR = 0;
+constexpr int OFF_MET = ((CUR_BYTES + 127) / 128) * 128;
+constexpr int OFF_PRE = OFF_MET + 9 * CEN_BYTES;
+constexpr int OFF_END = OFF_PRE + 9 * CEN_BYTES;
+constexpr int OFF_MED = OFF_END + 9 * CEN_BYTES;
+template <int MED> struct Lay {   // the media tiles come last: their number depends on the medium
+  static constexpr int NMT = Med<MED>::NTILE;
+  static constexpr int STAGE_BYTES = OFF_MED + NMT * CEN_BYTES;
+  static constexpr int SMEM_BYTES = NST * STAGE_BYTES + 128 /*alignment slack*/ + 64 /*barriers*/;
+  // blocks per SM the shared memory allows (227 KB usable, 1 KB reserved per block)
+  static constexpr int BLOCKS = (2 * (SMEM_BYTES + 1024) <= 233472) ? 2 : 1;
+};
+
+template <int KIND, int MED> __device__ __forceinline__ constexpr uint32_t stage_tx_bytes()
+{
+  return CUR_BYTES + (9 + Lay<MED>::NMT) * CEN_BYTES + (KIND == KIND_MID ? 9 * CEN_BYTES : 0) + (KIND != KIND_FIRST ? 9 * CEN_BYTES : 0);
+}
+
+struct TmaCtx {
+  unsigned char *ring;
+  uint64_t *full;
+  int tx, ty, t, i, j, i0, j0, k1;
+  bool active, inarr;
+  size_t pij;
+  const float *qptr;   // w_cur + pij: this thread's column of component 0
+  uint64_t pol_keep, pol_stream;   // L2 eviction policies (thread 0 only)
+};
+
+template <int DX, int DY, int KIND, int MED>
+__device__ __forceinline__ void tma_issue(const StageArgs &P, const TmaMaps &M, const TmaCtx &C, int kk, int s)
+{
+  constexpr int YL = Ofs<DY>::left;
+  unsigned char *b = C.ring + s * Lay<MED>::STAGE_BYTES;
+  uint64_t *bar = C.full + s;
+  mbar_expect_tx(bar, stage_tx_bytes<KIND, MED>());
+  // the wavefield tiles overlap their neighbours' (x-y halo): keep them in L2; everything else is touched once per stage
+  tma_load_4d_hint(b + OFF_CUR, &M.cur, bar, C.i0 - HX + P.shift, C.j0 - YL, kk, 0, C.pol_keep);
+  tma_load_4d_hint(b + OFF_MET, &M.met, bar, C.i0 + P.shift, C.j0, kk, 0, C.pol_stream);
+  tma_load_4d_hint(b + OFF_MED, &M.med, bar, C.i0 + P.shift, C.j0, kk, 0, C.pol_stream);
+  if (KIND == KIND_MID) tma_load_4d_hint(b + OFF_PRE, &M.pre, bar, C.i0 + P.shift, C.j0, kk, 0, C.pol_stream);
+  if (KIND != KIND_FIRST) tma_load_4d_hint(b + OFF_END, &M.end, bar, C.i0 + P.shift, C.j0, kk, 0, C.pol_stream);
+}
+
+// One plane. The march along z runs TOWARDS the short side of the one-sided zeta operator (upwards for
+// offsets {-3..1}, downwards for {-1..3}), so that three of its neighbours are planes already visited and only one
+// lies ahead: q0,q1,q2 = planes k-3d, k-2d, k-d (d = march direction), q3 = plane k, q4 receives plane k+d, which was
+// requested one iteration earlier (qn) -- at the same time as the TMA of that plane, so it is one DRAM read.
+template <int DX, int DY, int DZ, int KIND, int MED, bool PML>
+__device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, const TmaCtx &C, int k, int it, int nplanes,
+                                          const float (&q0)[9], const float (&q1)[9], const float (&q2)[9],
+                                          const float (&q3)[9], float (&q4)[9], float (&qn)[9])
+{
+  constexpr int YL = Ofs<DY>::left;
+  constexpr int FX = Ofs<DX>::first, FY = Ofs<DY>::first;
+  constexpr int DIR = DZ ? 1 : -1;
+  constexpr int NT = TX * TY;
+  const int s = it % NST;
+  const uint32_t parity = (it / NST) & 1;
+  const float *cx = c_fd.coef[DX], *cy = c_fd.coef[DY], *cz = c_fd.coef[DZ];
+#pragma unroll
+  for (int c = 0; c < 9; c++) q4[c] = qn[c];
+  if (C.inarr && it + 1 < nplanes) {
+    const float *w = C.qptr + (long)(k + 2 * DIR) * (long)P.siz_slice;
+#pragma unroll
+    for (int c = 0; c < 9; c++) qn[c] = __ldg(w + c * P.siz_vol);
+  }
+  unsigned char *b = C.ring + s * Lay<MED>::STAGE_BYTES;
+  mbar_wait(C.full + s, parity);
+  if (C.active) {
+    const float *sc = (const float *)(b + OFF_CUR) + (C.ty + YL) * SXT + C.tx + HX;
+    const float *sm = (const float *)(b + OFF_MET) + C.t;
+    const float *sd = (const float *)(b + OFF_MED) + C.t;
+    float *sp = (float *)(b + OFF_PRE) + C.t;   // w_pre in, w_tmp out
+    float *se = (float *)(b + OFF_END) + C.t;   // w_end in, w_end out
+    const float(&qz)[9] = q3;   // centre plane of the queue
+    Met m;
+    m.xix = sm[0 * NT]; m.xiy = sm[1 * NT]; m.xiz = sm[2 * NT];
+    m.etx = sm[3 * NT]; m.ety = sm[4 * NT]; m.etz = sm[5 * NT];
+    m.ztx = sm[6 * NT]; m.zty = sm[7 * NT]; m.ztz = sm[8 * NT];
+    Med<MED> md;
+    md.load([&](int n) { return sd[n * NT]; });
+    const float slw = md.slw;
+    Deriv d;
+    float h[9];
+    // ---- stress half: needs the velocity derivatives only
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const float *r = sc + c * SY * SXT;
+      d.x[c] = cx[0] * r[FX] + cx[1] * r[FX + 1] + cx[2] * r[FX + 2] + cx[3] * r[FX + 3] + cx[4] * r[FX + 4];
+      d.y[c] = cy[0] * r[FY * SXT] + cy[1] * r[(FY + 1) * SXT] + cy[2] * r[(FY + 2) * SXT] + cy[3] * r[(FY + 3) * SXT] + cy[4] * r[(FY + 4) * SXT];
+      d.z[c] = DZ ? cz[0] * q0[c] + cz[1] * q1[c] + cz[2] * q2[c] + cz[3] * q3[c] + cz[4] * q4[c]
+                  : cz[0] * q4[c] + cz[1] * q3[c] + cz[2] * q2[c] + cz[3] * q1[c] + cz[4] * q0[c];
+    }
+    hooke<MED>(d, m, md, h);
+    if (PML) pml_all<KIND, 0, MED>(P, C.i, C.j, k, d, m, md, h);
+    if constexpr (MED == MED_VIS) atten_update<KIND>(P, (size_t)k * P.siz_slice + C.pij, md.lam, md.mu, h);
+#pragma unroll
+    for (int c = 3; c < 9; c++) rk_smem<KIND>(sp + c * NT, se + c * NT, qz[c], h[c], P.a, P.b);
+    // ---- velocity half: needs the stress derivatives only
+#pragma unroll
+    for (int c = 3; c < 9; c++) {
+      const float *r = sc + c * SY * SXT;
+      d.x[c] = cx[0] * r[FX] + cx[1] * r[FX + 1] + cx[2] * r[FX + 2] + cx[3] * r[FX + 3] + cx[4] * r[FX + 4];
+      d.y[c] = cy[0] * r[FY * SXT] + cy[1] * r[(FY + 1) * SXT] + cy[2] * r[(FY + 2) * SXT] + cy[3] * r[(FY + 3) * SXT] + cy[4] * r[(FY + 4) * SXT];
+      d.z[c] = DZ ? cz[0] * q0[c] + cz[1] * q1[c] + cz[2] * q2[c] + cz[3] * q3[c] + cz[4] * q4[c]
+                  : cz[0] * q4[c] + cz[1] * q3[c] + cz[2] * q2[c] + cz[3] * q1[c] + cz[4] * q0[c];
+    }
+    momentum(d, m, slw, h);
+    if (PML) pml_all<KIND, 1, MED>(P, C.i, C.j, k, d, m, md, h);
+#pragma unroll
+    for (int c = 0; c < 3; c++) rk_smem<KIND>(sp + c * NT, se + c * NT, qz[c], h[c], P.a, P.b);
+    fence_proxy_async_smem();   // the results written above are read by the TMA store below
+  }
+  __syncthreads();   // every thread is done with ring slot s; its PRE / END tiles now hold w_tmp / w_end of this plane
+  if (C.t == 0) {
+    const int tx0 = C.i0 - P.ni1, ty0 = C.j0 - P.nj1;
+    if (KIND != KIND_LAST) tma_store_4d_hint(&M.out_tmp, b + OFF_PRE, tx0, ty0, k, 0, C.pol_stream);
+    tma_store_4d_hint(&M.out_end, b + OFF_END, tx0, ty0, k, 0, C.pol_stream);
+    tma_store_commit();
+    if (it + NST < nplanes) {
+      tma_store_wait_read();   // the slot may be refilled once the stores have read it
+      tma_issue<DX, DY, KIND, MED>(P, M, C, k + NST * DIR, s);
+    }
+  }
+}
+
+template <int DX, int DY, int DZ, int KIND, int MED>
+__global__ void __launch_bounds__(TX *TY, Lay<MED>::BLOCKS) k_main_tma(const StageArgs P, const __grid_constant__ TmaMaps M)
+{
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  TmaCtx C;
+  C.ring = smem_raw;
+  C.full = (uint64_t *)(C.ring + NST * Lay<MED>::STAGE_BYTES);
+  C.tx = threadIdx.x; C.ty = threadIdx.y; C.t = C.ty * TX + C.tx;
+  C.i0 = P.ni1 + (P.bx0 + blockIdx.x) * TX; C.j0 = P.nj1 + (P.by0 + blockIdx.y) * TY;
+  C.i = C.i0 + C.tx; C.j = C.j0 + C.ty;
+  const int k0 = P.kbeg + blockIdx.z * P.zchunk;
+  C.k1 = min(k0 + P.zchunk - 1, P.kend);
+  C.inarr = (C.i < P.nx) && (C.j < P.ny);
+  C.active = (C.i <= P.ni2) && (C.j <= P.nj2);
+  C.pij = (size_t)C.j * P.siz_line + C.i;
+  C.qptr = P.cur + C.pij;
+  C.pol_keep = (P.l2mode & 1) ? l2_policy_evict_last() : l2_policy_evict_normal();
+  C.pol_stream = (P.l2mode & 2) ? l2_policy_evict_first() : l2_policy_evict_normal();
+
+  if (C.t == 0) {
+#pragma unroll
+    for (int s = 0; s < NST; s++) mbar_init(C.full + s, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  constexpr int DIR = DZ ? 1 : -1;
+  const int nplanes = C.k1 - k0 + 1;
+  const int kf = DZ ? k0 : C.k1;   // first plane of the march
+  if (C.t == 0) {
+#pragma unroll
+    for (int s = 0; s < NST; s++)
+      if (s < nplanes) tma_issue<DX, DY, KIND, MED>(P, M, C, kf + s * DIR, s);
+  }
+  // does this tile meet the slab of an x or y PML face? (block-uniform; the z faces are tested per plane)
+  bool pml_xy = false;
+#pragma unroll
+  for (int sd = 0; sd < 2; sd++) {
+    const PmlFaceDev &Fx = P.pml[0][sd], &Fy = P.pml[1][sd];
+    pml_xy |= Fx.on && C.i0 <= Fx.i2 && C.i0 + TX - 1 >= Fx.i1;
+    pml_xy |= Fy.on && C.j0 <= Fy.j2 && C.j0 + TY - 1 >= Fy.j1;
+  }
+  const int zk1 = P.pml[2][0].on ? P.pml[2][0].k2 : -1;            // planes k <= zk1 lie in the bottom slab
+  const int zk2 = P.pml[2][1].on ? P.pml[2][1].k1 : (1 << 30);     // planes k >= zk2 lie in the top slab
+
+  float q0[9], q1[9], q2[9], q3[9], q4[9], qn[9];
+#pragma unroll
+  for (int c = 0; c < 9; c++) { q0[c] = q1[c] = q2[c] = q3[c] = q4[c] = qn[c] = 0.0f; }
+  if (C.inarr) {
+    const long sd = (long)DIR * (long)P.siz_slice;
+#pragma unroll
+    for (int c = 0; c < 9; c++) {
+      const float *w = P.cur + c * P.siz_vol + (size_t)kf * P.siz_slice + C.pij;
+      q0[c] = __ldg(w - 3 * sd); q1[c] = __ldg(w - 2 * sd); q2[c] = __ldg(w - sd); q3[c] = __ldg(w);
+      qn[c] = __ldg(w + sd);
+    }
+  }
+  for (int it = 0; it < nplanes; it++) {
+    const int k = kf + it * DIR;
+    if (pml_xy || k <= zk1 || k >= zk2 || (P.l2mode & 4)) tma_plane<DX, DY, DZ, KIND, MED, true>(P, M, C, k, it, nplanes, q0, q1, q2, q3, q4, qn);
+    else tma_plane<DX, DY, DZ, KIND, MED, false>(P, M, C, k, it, nplanes, q0, q1, q2, q3, q4, qn);
+    // rotate the zeta queue (register moves; unrolling by 5 instead makes the loop body outgrow the
+    // instruction cache and the kernel instruction-fetch bound -- profiles/r1d_summary.txt)
+#pragma unroll
+    for (int c = 0; c < 9; c++) { q0[c] = q1[c]; q1[c] = q2[c]; q2[c] = q3[c]; q3[c] = q4[c]; }
+  }
+  if (C.t == 0) tma_store_wait_all();
+}
+
+// =============================================================================================
+// free-surface rows: k in [nk2-3, nk2], one thread per point, neighbours straight from L1/L2
+// =============================================================================================
+template <int DX, int DY, int DZ, int KIND, int MED>
+__global__ void __launch_bounds__(128, 3) k_top(const StageArgs P)
+{
+  const int i = P.ni1 + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = P.nj1 + blockIdx.y;
+  const int k = P.kbeg + blockIdx.z;
+  if (i > P.ni2 || j > P.nj2 || k > P.kend) return;
+  const size_t L = P.siz_line, S = P.siz_slice, V = P.siz_vol;
+  const size_t p = (size_t)k * S + (size_t)j * L + i;
+  const size_t p2 = (size_t)j * P.nx + i;
+  const float *cx = c_fd.coef[DX], *cy = c_fd.coef[DY], *cz = c_fd.coef[DZ];
+  constexpr int FX = Ofs<DX>::first, FY = Ofs<DY>::first, FZ = Ofs<DZ>::first;
+  const int nsurf = P.nk2 - k;   // 0 at the surface
+
+  Deriv d;
+  float cur[9], pv[9], ev[9];
+#pragma unroll
+  for (int c = 0; c < 9; c++) {
+    if (KIND == KIND_MID) pv[c] = __ldg(P.pre + c * V + p);
+    if (KIND != KIND_FIRST) ev[c] = P.end[c * V + p];
+  }
+#pragma unroll
+  for (int c = 0; c < 9; c++) {
+    const float *w = P.cur + c * V + p;
+    cur[c] = __ldg(w);
+    d.x[c] = cx[0] * __ldg(w + FX) + cx[1] * __ldg(w + FX + 1) + cx[2] * __ldg(w + FX + 2) + cx[3] * __ldg(w + FX + 3)
+           + cx[4] * __ldg(w + FX + 4);
+    d.y[c] = cy[0] * __ldg(w + (FY + 0) * (long)L) + cy[1] * __ldg(w + (FY + 1) * (long)L)
+           + cy[2] * __ldg(w + (FY + 2) * (long)L) + cy[3] * __ldg(w + (FY + 3) * (long)L)
+           + cy[4] * __ldg(w + (FY + 4) * (long)L);
+    // interior zeta operator; rows whose stencil leaves the grid get replaced below
+    d.z[c] = cz[0] * __ldg(w + (FZ + 0) * (long)S) + cz[1] * __ldg(w + (FZ + 1) * (long)S)
+           + cz[2] * __ldg(w + (FZ + 2) * (long)S) + cz[3] * __ldg(w + (FZ + 3) * (long)S)
+           + cz[4] * __ldg(w + (FZ + 4) * (long)S);
+  }
+  const Met m = load_metric(P, p);
+  Med<MED> md;
+  md.load([&](int n) { return __ldg(P.media[n] + p); });
+  const float slw = md.slw;
+
+  // --- velocity gradient along zeta in the top three rows (vlow, iso.c:503-593)
+  if (nsurf == 0) {
+    // the surface point-force term exists in the isotropic operator only (iso.c:583-592)
+    constexpr bool FSRC = (MED == MED_ISO || MED == MED_VIS);
+    const float *A = P.matVx2Vz + p2 * 9, *B = P.matVy2Vz + p2 * 9, *F = P.matF2Vz + p2 * 9;
+    float sx = (FSRC && P.VxSrc) ? __ldg(P.VxSrc + p2) : 0.0f, sy = (FSRC && P.VySrc) ? __ldg(P.VySrc + p2) : 0.0f,
+          sz = (FSRC && P.VzSrc) ? __ldg(P.VzSrc + p2) : 0.0f;
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      float v = __ldg(A + 3 * r + 0) * d.x[VX] + __ldg(A + 3 * r + 1) * d.x[VY] + __ldg(A + 3 * r + 2) * d.x[VZ]
+              + __ldg(B + 3 * r + 0) * d.y[VX] + __ldg(B + 3 * r + 1) * d.y[VY] + __ldg(B + 3 * r + 2) * d.y[VZ];
+      if (FSRC) v += __ldg(F + 3 * r + 0) * sx + __ldg(F + 3 * r + 1) * sy + __ldg(F + 3 * r + 2) * sz;
+      d.z[r] = v;
+    }
+  } else if (nsurf == 1) {
+    const long o0 = DZ ? -(long)S : 0, o1 = DZ ? 0 : (long)S;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const float *w = P.cur + c * V + p;
+      d.z[c] = c_fd.lay2[DZ][0] * __ldg(w + o0) + c_fd.lay2[DZ][1] * __ldg(w + o1);
+    }
+  } else if (nsurf == 2) {
+    const long o0 = DZ ? -2 * (long)S : 0;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const float *w = P.cur + c * V + p + o0;
+      d.z[c] = c_fd.lay3[DZ][0] * __ldg(w) + c_fd.lay3[DZ][1] * __ldg(w + S) + c_fd.lay3[DZ][2] * __ldg(w + 2 * S);
+    }
+  }
+
+  float h[9];
+  momentum(d, m, slw, h);
+  hooke<MED>(d, m, md, h);
+
+  // --- traction image: momentum RHS in conservative form (sv_curv_col_el.c:84-304)
+  const int kmin = P.nk2 - (FZ + 4);
+  if (k >= kmin) {
+    const int n_free = P.nk2 - k - FZ;
+    const float jac = __ldg(P.metric[M_JAC] + p);
+    const float slwjac = slw / jac;
+    // component triplets (T1,T2,T3) with flux_n = J*(e_x T1 + e_y T2 + e_z T3)
+    const int T1[3] = {TXX, TXY, TXZ}, T2[3] = {TXY, TYY, TYZ}, T3[3] = {TXZ, TYZ, TZZ};
+    const float *Ts[3] = {P.TxSrc, P.TySrc, P.TzSrc};
+    // the xi / eta flux derivatives are accumulated term by term (left to right, like M_FD_NOINDX, forward/fd_t.h:33-38);
+    // only the zeta fluxes are kept, because the image terms refer back to them
+    float Dxf[3], Dyf[3], fz[3][5];
+#pragma unroll
+    for (int n = 0; n < 5; n++) {
+      {
+        const size_t pp = p + (FX + n);
+        const float jn = __ldg(P.metric[M_JAC] + pp), ex = __ldg(P.metric[M_XIX] + pp), ey = __ldg(P.metric[M_XIY] + pp),
+                    ez = __ldg(P.metric[M_XIZ] + pp);
+#pragma unroll
+        for (int v = 0; v < 3; v++) {
+          const float f = jn * (ex * __ldg(P.cur + T1[v] * V + pp) + ey * __ldg(P.cur + T2[v] * V + pp) + ez * __ldg(P.cur + T3[v] * V + pp));
+          if (n == 0) Dxf[v] = cx[0] * f; else Dxf[v] += cx[n] * f;
+        }
+      }
+      {
+        const size_t pp = p + (long)(FY + n) * (long)L;
+        const float jn = __ldg(P.metric[M_JAC] + pp), ex = __ldg(P.metric[M_ETX] + pp), ey = __ldg(P.metric[M_ETY] + pp),
+                    ez = __ldg(P.metric[M_ETZ] + pp);
+#pragma unroll
+        for (int v = 0; v < 3; v++) {
+          const float f = jn * (ex * __ldg(P.cur + T1[v] * V + pp) + ey * __ldg(P.cur + T2[v] * V + pp) + ez * __ldg(P.cur + T3[v] * V + pp));
+          if (n == 0) Dyf[v] = cy[0] * f; else Dyf[v] += cy[n] * f;
+        }
+      }
+      if (n < n_free) {
+        const size_t pp = p + (long)(FZ + n) * (long)S;
+        const float jn = __ldg(P.metric[M_JAC] + pp), ex = __ldg(P.metric[M_ZTX] + pp), ey = __ldg(P.metric[M_ZTY] + pp),
+                    ez = __ldg(P.metric[M_ZTZ] + pp);
+#pragma unroll
+        for (int v = 0; v < 3; v++)
+          fz[v][n] = jn * (ex * __ldg(P.cur + T1[v] * V + pp) + ey * __ldg(P.cur + T2[v] * V + pp) + ez * __ldg(P.cur + T3[v] * V + pp));
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < 3; v++) {
+      const float ts = Ts[v] ? __ldg(Ts[v] + p2) : 0.0f;
+#pragma unroll
+      for (int n = 0; n < 5; n++) {
+        if (n == n_free) fz[v][n] = ts;
+        else if (n > n_free) {
+          const int im = 2 * n_free - n;    // mirror index inside the window
+          float below;
+          if (im >= 0) below = fz[v][im < 0 ? 0 : im];
+          else if (P.timg_mode == 0) below = 0.0f;
+          else {
+            // image row k + indx[n] - 2(n - n_free) (sv_curv_col_el.c:154-159)
+            const size_t pp = p + (long)(FZ + n - 2 * (n - n_free)) * (long)S;
+            const float jn = __ldg(P.metric[M_JAC] + pp), ex = __ldg(P.metric[M_ZTX] + pp), ey = __ldg(P.metric[M_ZTY] + pp),
+                        ez = __ldg(P.metric[M_ZTZ] + pp);
+            below = jn * (ex * __ldg(P.cur + T1[v] * V + pp) + ey * __ldg(P.cur + T2[v] * V + pp) + ez * __ldg(P.cur + T3[v] * V + pp));
+          }
+          fz[v][n] = 2.0f * ts - below;
+        }
+      }
+      float Dz = cz[0] * fz[v][0]; Dz += cz[1] * fz[v][1]; Dz += cz[2] * fz[v][2]; Dz += cz[3] * fz[v][3]; Dz += cz[4] * fz[v][4];
+      h[v] = (Dxf[v] + Dyf[v] + Dz) * slwjac;
+    }
+  }
+
+  pml_all<KIND, 0, MED>(P, i, j, k, d, m, md, h);
+  pml_all<KIND, 1, MED>(P, i, j, k, d, m, md, h);
+  if constexpr (MED == MED_VIS) atten_update<KIND>(P, p, md.lam, md.mu, h);
+#pragma unroll
+  for (int c = 0; c < 9; c++) rk_store<KIND>(P.tmp, P.end, c * V + p, cur[c], pv[c], ev[c], h[c], P.a, P.b);
+}
+
+// =============================================================================================
+// interior rows of the tile rectangle [bx0,bx1) x [by0,by1) (tiles of TX x TY points counted from (ni1,nj1))
+template <int DX, int DY, int DZ, int KIND, int MED>
+static void launch_main_t(const StageArgs &P0, const TmaMaps *maps, int zchunk, const int rect[4], cudaStream_t st,
+                          cudaEvent_t ev0, cudaEvent_t ev1, int *nlaunch)
+{
+  StageArgs P = P0;
+  const int ktop = P.free_top ? P.nk2 - 3 : P.nk2 + 1;   // first row of the free-surface kernel
+  P.kbeg = P.nk1; P.kend = (P.free_top ? ktop - 1 : P.nk2);
+  const int bx = rect[1] - rect[0], by = rect[3] - rect[2];
+  if (P.kend < P.kbeg || bx <= 0 || by <= 0) return;
+  P.bx0 = rect[0]; P.by0 = rect[2];
+  const int nk = P.kend - P.kbeg + 1;
+  int nzc;
+  if (zchunk > 0) nzc = (nk + zchunk - 1) / zchunk;
+  else {
+    // z chunks: at least ~8 waves of 148 SMs x 2 resident blocks, chunks no shorter than 24 rows
+    nzc = 1;
+    while (nzc < nk && (long)bx * by * nzc < 148L * Lay<MED>::BLOCKS * 8 && nk / (nzc + 1) >= 24) nzc++;
+  }
+  P.zchunk = (nk + nzc - 1) / nzc;
+  nzc = (nk + P.zchunk - 1) / P.zchunk;
+  dim3 grid(bx, by, nzc), block(TX, TY);
+  if (ev0) cudaEventRecord(ev0, st);
+  k_main_tma<DX, DY, DZ, KIND, MED><<<grid, block, Lay<MED>::SMEM_BYTES, st>>>(P, *maps);
+  if (ev1) cudaEventRecord(ev1, st);
+  (*nlaunch)++;
+}
+
+// the free-surface rows (whole x-y range)
+template <int DX, int DY, int DZ, int KIND, int MED>
+static void launch_top_t(const StageArgs &P0, cudaStream_t st, int *nlaunch)
+{
+  if (!P0.free_top) return;
+  StageArgs P = P0;
+  const int ni = P.ni2 - P.ni1 + 1, nj = P.nj2 - P.nj1 + 1;
+  const int ktop = P.nk2 - 3;
+  P.kbeg = (ktop < P.nk1) ? P.nk1 : ktop; P.kend = P.nk2;
+  dim3 block(128), grid((ni + 127) / 128, nj, P.kend - P.kbeg + 1);
+  k_top<DX, DY, DZ, KIND, MED><<<grid, block, 0, st>>>(P);
+  (*nlaunch)++;
+}
+
+template <int DX, int DY, int DZ, int KIND, int MED> static int set_attr_t()
+{
+  cudaError_t e = cudaFuncSetAttribute(k_main_tma<DX, DY, DZ, KIND, MED>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<MED>::SMEM_BYTES);
+  if (e != cudaSuccess) return 1;
+  e = cudaFuncSetAttribute(k_main_tma<DX, DY, DZ, KIND, MED>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  return e != cudaSuccess;
+}
+template <int KIND, int MED> static int set_attr_k()
+{
+  return set_attr_t<0, 0, 0, KIND, MED>() | set_attr_t<0, 0, 1, KIND, MED>() | set_attr_t<0, 1, 0, KIND, MED>() | set_attr_t<0, 1, 1, KIND, MED>() |
+         set_attr_t<1, 0, 0, KIND, MED>() | set_attr_t<1, 0, 1, KIND, MED>() | set_attr_t<1, 1, 0, KIND, MED>() | set_attr_t<1, 1, 1, KIND, MED>();
+}
+template <int MED> int med_kernels_init() { return set_attr_k<KIND_FIRST, MED>() | set_attr_k<KIND_MID, MED>() | set_attr_k<KIND_LAST, MED>(); }
+
+#define CGFD_DISPATCH_DIR(CALL)                                                                   \
+  switch (dx * 4 + dy * 2 + dz) {                                                                  \
+    case 0: CALL(0, 0, 0); break; case 1: CALL(0, 0, 1); break; case 2: CALL(0, 1, 0); break;      \
+    case 3: CALL(0, 1, 1); break; case 4: CALL(1, 0, 0); break; case 5: CALL(1, 0, 1); break;      \
+    case 6: CALL(1, 1, 0); break; default: CALL(1, 1, 1); break;                                   \
+  }
+
+template <int KIND, int MED>
+static void launch_main_k(const StageArgs &P, const TmaMaps *maps, int dx, int dy, int dz, int zchunk,
+                          const int rect[4], cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, int *n)
+{
+#define CALL(a, b, c) launch_main_t<a, b, c, KIND, MED>(P, maps, zchunk, rect, st, e0, e1, n)
+  CGFD_DISPATCH_DIR(CALL)
+#undef CALL
+}
+template <int KIND, int MED> static void launch_top_k(const StageArgs &P, int dx, int dy, int dz, cudaStream_t st, int *n)
+{
+#define CALL(a, b, c) launch_top_t<a, b, c, KIND, MED>(P, st, n)
+  CGFD_DISPATCH_DIR(CALL)
+#undef CALL
+}
+
+template <int MED>
+void med_launch_main(const StageArgs &P, const TmaMaps *maps, int dx, int dy, int dz, int kind, int zchunk, const int rect[4],
+                     cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1, int *nlaunch)
+{
+  if (kind == KIND_FIRST) launch_main_k<KIND_FIRST, MED>(P, maps, dx, dy, dz, zchunk, rect, st, ev0, ev1, nlaunch);
+  else if (kind == KIND_MID) launch_main_k<KIND_MID, MED>(P, maps, dx, dy, dz, zchunk, rect, st, ev0, ev1, nlaunch);
+  else launch_main_k<KIND_LAST, MED>(P, maps, dx, dy, dz, zchunk, rect, st, ev0, ev1, nlaunch);
+}
+
+template <int MED> void med_launch_top(const StageArgs &P, int dx, int dy, int dz, int kind, cudaStream_t st, int *nlaunch)
+{
+  if (kind == KIND_FIRST) launch_top_k<KIND_FIRST, MED>(P, dx, dy, dz, st, nlaunch);
+  else if (kind == KIND_MID) launch_top_k<KIND_MID, MED>(P, dx, dy, dz, st, nlaunch);
+  else launch_top_k<KIND_LAST, MED>(P, dx, dy, dz, st, nlaunch);
+}
+
+// one medium per translation unit
+#define CGFD_INSTANTIATE_MEDIUM(MED)                                                                                  \
+  template int med_kernels_init<MED>();                                                                                \
+  template void med_launch_main<MED>(const StageArgs &, const TmaMaps *, int, int, int, int, int, const int[4], cudaStream_t, \
+                                     cudaEvent_t, cudaEvent_t, int *);                                                 \
+  template void med_launch_top<MED>(const StageArgs &, int, int, int, int, cudaStream_t, int *);
+
+}  // namespace cgfd

@@ -92,19 +92,125 @@ __device__ __forceinline__ void rk_smem(float *sp, float *se, float cur_c, float
   }
 }
 
-// ADE CFS-PML correction of one face at one slab point, isotropic
-// (forward/sv_curv_col_el_iso.c:763-905 for x, 915-1054 for y, 1058-1137 for z):
+// ---------------------------------------------------------------------------------------------------------
+// media. MED selects the constitutive law; the media arrays arrive in the order of include/cgfd3d_b200.h:
+//   iso / visco : lambda, mu, 1/rho (+ Ylam[N], Ymu[N] for visco, read separately by the attenuation step)
+//   vti         : c11, c13, c33, c55, c66, 1/rho          (c12 = c11 - 2 c66, forward/sv_curv_col_el_vti.c:344-352)
+//   aniso       : the 21 Cij of the upper triangle row by row, 1/rho (forward/sv_curv_col_el_aniso.c:426-453)
+// NTILE = arrays staged per plane by the interior kernel.
+enum { MED_ISO = 0, MED_VTI = 1, MED_ANISO = 2, MED_VIS = 3 };
+
+template <int MED> struct Med;
+template <> struct Med<MED_ISO> {
+  static constexpr int NTILE = 3;
+  float lam, mu, lam2mu, slw;
+  template <class F> __device__ __forceinline__ void load(F g) { lam = g(0); mu = g(1); slw = g(2); lam2mu = lam + 2.0f * mu; }
+};
+template <> struct Med<MED_VIS> : Med<MED_ISO> {};
+template <> struct Med<MED_VTI> {
+  static constexpr int NTILE = 6;
+  float c11, c13, c33, c55, c66, c12, slw;
+  template <class F> __device__ __forceinline__ void load(F g)
+  {
+    c11 = g(0); c13 = g(1); c33 = g(2); c55 = g(3); c66 = g(4); slw = g(5); c12 = c11 - 2.0f * c66;
+  }
+};
+template <> struct Med<MED_ANISO> {
+  static constexpr int NTILE = 22;
+  float c[21], slw;
+  template <class F> __device__ __forceinline__ void load(F g)
+  {
+#pragma unroll
+    for (int n = 0; n < 21; n++) c[n] = g(n);
+    slw = g(21);
+  }
+};
+
+// stress rate from a velocity gradient g[j][l] = dV_j/dx_l (or one axis' share of it): hT_I = sum_J C_IJ E_J with
+// E = (g00, g11, g22, g12+g21, g02+g20, g01+g10). Same products as the reference's Hooke blocks
+// (vti.c:366-389, aniso.c:466-491), which expand C_IJ e_l D V_j term by term; association differs, values agree to
+// float32 round-off.
+__device__ __forceinline__ void stress_from_grad(const float (&g)[3][3], const Med<MED_ISO> &M, float *h)
+{
+  h[TXX] = M.lam2mu * g[0][0] + M.lam * (g[1][1] + g[2][2]);
+  h[TYY] = M.lam2mu * g[1][1] + M.lam * (g[0][0] + g[2][2]);
+  h[TZZ] = M.lam2mu * g[2][2] + M.lam * (g[0][0] + g[1][1]);
+  h[TXY] = M.mu * (g[0][1] + g[1][0]);
+  h[TXZ] = M.mu * (g[0][2] + g[2][0]);
+  h[TYZ] = M.mu * (g[1][2] + g[2][1]);
+}
+__device__ __forceinline__ void stress_from_grad(const float (&g)[3][3], const Med<MED_VTI> &M, float *h)
+{
+  h[TXX] = M.c11 * g[0][0] + M.c12 * g[1][1] + M.c13 * g[2][2];
+  h[TYY] = M.c12 * g[0][0] + M.c11 * g[1][1] + M.c13 * g[2][2];
+  h[TZZ] = M.c13 * g[0][0] + M.c13 * g[1][1] + M.c33 * g[2][2];
+  h[TYZ] = M.c55 * (g[1][2] + g[2][1]);
+  h[TXZ] = M.c55 * (g[0][2] + g[2][0]);
+  h[TXY] = M.c66 * (g[0][1] + g[1][0]);
+}
+__device__ __forceinline__ void stress_from_grad(const float (&g)[3][3], const Med<MED_ANISO> &M, float *h)
+{
+  const float E[6] = {g[0][0], g[1][1], g[2][2], g[1][2] + g[2][1], g[0][2] + g[2][0], g[0][1] + g[1][0]};
+  // upper triangle, row by row: row I starts at I*6 - I*(I-1)/2 and holds columns I..5
+  const float *c = M.c;
+#define CIJ(I, J) ((I) <= (J) ? c[(I) * 6 - (I) * ((I) - 1) / 2 + (J) - (I)] : c[(J) * 6 - (J) * ((J) - 1) / 2 + (I) - (J)])
+#pragma unroll
+  for (int I = 0; I < 6; I++)
+    h[TXX + I] = CIJ(I, 0) * E[0] + CIJ(I, 1) * E[1] + CIJ(I, 2) * E[2] + CIJ(I, 3) * E[3] + CIJ(I, 4) * E[4] + CIJ(I, 5) * E[5];
+#undef CIJ
+}
+static_assert(TXX == 3 && TYY == 4 && TZZ == 5 && TYZ == 6 && TXZ == 7 && TXY == 8, "stress components follow the Voigt order");
+
+// Hooke's law on the velocity entries of d. The isotropic media keep the reference's own expression
+// (forward/sv_curv_col_el_iso.c:409-435); vti / aniso go through the physical velocity gradient.
+template <int MED> __device__ __forceinline__ void hooke(const Deriv &d, const Met &m, const Med<MED> &M, float *h)
+{
+  if constexpr (MED == MED_ISO || MED == MED_VIS) {
+    hooke_iso(d, m, M.lam, M.mu, M.lam2mu, h);
+  } else {
+    float g[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      g[j][0] = m.xix * d.x[j] + m.etx * d.y[j] + m.ztx * d.z[j];
+      g[j][1] = m.xiy * d.x[j] + m.ety * d.y[j] + m.zty * d.z[j];
+      g[j][2] = m.xiz * d.x[j] + m.etz * d.y[j] + m.ztz * d.z[j];
+    }
+    stress_from_grad(g, M, h);
+  }
+}
+
+// stress rate caused by the derivative along ONE grid axis with direction cosines (e1,e2,e3): D_[VX..VZ] are the three
+// velocity derivatives along that axis (PML normal terms, free-surface terms)
+template <int MED>
+__device__ __forceinline__ void stress_one_axis(const float *D_, float e1, float e2, float e3, const Med<MED> &M, float *r)
+{
+  if constexpr (MED == MED_ISO || MED == MED_VIS) {
+    r[TXX] = M.lam2mu * e1 * D_[VX] + M.lam * e2 * D_[VY] + M.lam * e3 * D_[VZ];
+    r[TYY] = M.lam * e1 * D_[VX] + M.lam2mu * e2 * D_[VY] + M.lam * e3 * D_[VZ];
+    r[TZZ] = M.lam * e1 * D_[VX] + M.lam * e2 * D_[VY] + M.lam2mu * e3 * D_[VZ];
+    r[TXY] = M.mu * (e2 * D_[VX] + e1 * D_[VY]);
+    r[TXZ] = M.mu * (e3 * D_[VX] + e1 * D_[VZ]);
+    r[TYZ] = M.mu * (e3 * D_[VY] + e2 * D_[VZ]);
+  } else {
+    float g[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) { g[j][0] = e1 * D_[j]; g[j][1] = e2 * D_[j]; g[j][2] = e3 * D_[j]; }
+    stress_from_grad(g, M, r);
+  }
+}
+
+// ADE CFS-PML correction of one face at one slab point
+// (forward/sv_curv_col_el_iso.c:763-905 for x, 915-1054 for y, 1058-1137 for z; vti.c:592-1077, aniso.c:717-1259):
 //   rhs_n  = RHS terms holding the face-normal derivative only
 //   h     += (B-1)*rhs_n - B*aux ;  aux_rhs = D*rhs_n - A*aux
-// with the free-surface terms at k == nk2 for x/y faces (:841-901, :989-1048), followed by the RK
+// with the free-surface terms at k == nk2 for x/y faces (iso.c:841-901, 989-1048), followed by the RK
 // update of the auxiliary variables (forward/drv_rk_curv_col.c:315-346, 371-402, 426-438).
 // PART 0 handles the 6 stress components (needs the velocity derivatives along the normal),
 // PART 1 the 3 velocity components (needs the stress derivatives), so that a caller can finish one
 // half of the RHS before it forms the other.
-template <int AXIS, int KIND, int PART>
-__device__ __forceinline__ void pml_face_iso(const StageArgs &P, const PmlFaceDev &F, int i, int j, int k,
-                                             const Deriv &d, const Met &m, float lam, float mu, float lam2mu, float slw,
-                                             float *h)
+template <int AXIS, int KIND, int PART, int MED>
+__device__ __forceinline__ void pml_face(const StageArgs &P, const PmlFaceDev &F, int i, int j, int k,
+                                         const Deriv &d, const Met &m, const Med<MED> &M, float *h)
 {
   constexpr int C0 = PART ? 0 : 3, C1 = PART ? 3 : 9;
   const int ia = (AXIS == 0) ? (i - F.i1) : (AXIS == 1) ? (j - F.j1) : (k - F.k1);
@@ -125,16 +231,11 @@ __device__ __forceinline__ void pml_face_iso(const StageArgs &P, const PmlFaceDe
   }
   float r[9];
   if (PART) {
-    r[VX] = slw * (e1 * D_[TXX] + e2 * D_[TXY] + e3 * D_[TXZ]);
-    r[VY] = slw * (e1 * D_[TXY] + e2 * D_[TYY] + e3 * D_[TYZ]);
-    r[VZ] = slw * (e1 * D_[TXZ] + e2 * D_[TYZ] + e3 * D_[TZZ]);
+    r[VX] = M.slw * (e1 * D_[TXX] + e2 * D_[TXY] + e3 * D_[TXZ]);
+    r[VY] = M.slw * (e1 * D_[TXY] + e2 * D_[TYY] + e3 * D_[TYZ]);
+    r[VZ] = M.slw * (e1 * D_[TXZ] + e2 * D_[TYZ] + e3 * D_[TZZ]);
   } else {
-    r[TXX] = lam2mu * e1 * D_[VX] + lam * e2 * D_[VY] + lam * e3 * D_[VZ];
-    r[TYY] = lam * e1 * D_[VX] + lam2mu * e2 * D_[VY] + lam * e3 * D_[VZ];
-    r[TZZ] = lam * e1 * D_[VX] + lam * e2 * D_[VY] + lam2mu * e3 * D_[VZ];
-    r[TXY] = mu * (e2 * D_[VX] + e1 * D_[VY]);
-    r[TXZ] = mu * (e3 * D_[VX] + e1 * D_[VZ]);
-    r[TYZ] = mu * (e3 * D_[VY] + e2 * D_[VZ]);
+    stress_one_axis<MED>(D_, e1, e2, e3, M, r);
   }
   float ar[9];
 #pragma unroll
@@ -143,17 +244,22 @@ __device__ __forceinline__ void pml_face_iso(const StageArgs &P, const PmlFaceDe
     ar[c] = cD * r[c] - cA * au[c];
   }
   if (PART == 0 && AXIS < 2 && P.free_top && k == P.nk2) {
-    const float *M = ((AXIS == 0) ? P.matVx2Vz : P.matVy2Vz) + ((size_t)j * P.nx + i) * 9;
-    float z0 = __ldg(M + 0) * D_[VX] + __ldg(M + 1) * D_[VY] + __ldg(M + 2) * D_[VZ];
-    float z1 = __ldg(M + 3) * D_[VX] + __ldg(M + 4) * D_[VY] + __ldg(M + 5) * D_[VZ];
-    float z2 = __ldg(M + 6) * D_[VX] + __ldg(M + 7) * D_[VY] + __ldg(M + 8) * D_[VZ];
+    const float *Mt = ((AXIS == 0) ? P.matVx2Vz : P.matVy2Vz) + ((size_t)j * P.nx + i) * 9;
+    float z[3];
+    z[0] = __ldg(Mt + 0) * D_[VX] + __ldg(Mt + 1) * D_[VY] + __ldg(Mt + 2) * D_[VZ];
+    z[1] = __ldg(Mt + 3) * D_[VX] + __ldg(Mt + 4) * D_[VY] + __ldg(Mt + 5) * D_[VZ];
+    z[2] = __ldg(Mt + 6) * D_[VX] + __ldg(Mt + 7) * D_[VY] + __ldg(Mt + 8) * D_[VZ];
     float q[9];
-    q[TXX] = lam2mu * (m.ztx * z0) + lam * (m.zty * z1 + m.ztz * z2);
-    q[TYY] = lam2mu * (m.zty * z1) + lam * (m.ztx * z0 + m.ztz * z2);
-    q[TZZ] = lam2mu * (m.ztz * z2) + lam * (m.ztx * z0 + m.zty * z1);
-    q[TXY] = mu * (m.zty * z0 + m.ztx * z1);
-    q[TXZ] = mu * (m.ztz * z0 + m.ztx * z2);
-    q[TYZ] = mu * (m.ztz * z1 + m.zty * z2);
+    if constexpr (MED == MED_ISO || MED == MED_VIS) {
+      q[TXX] = M.lam2mu * (m.ztx * z[0]) + M.lam * (m.zty * z[1] + m.ztz * z[2]);
+      q[TYY] = M.lam2mu * (m.zty * z[1]) + M.lam * (m.ztx * z[0] + m.ztz * z[2]);
+      q[TZZ] = M.lam2mu * (m.ztz * z[2]) + M.lam * (m.ztx * z[0] + m.zty * z[1]);
+      q[TXY] = M.mu * (m.zty * z[0] + m.ztx * z[1]);
+      q[TXZ] = M.mu * (m.ztz * z[0] + m.ztx * z[2]);
+      q[TYZ] = M.mu * (m.ztz * z[1] + m.zty * z[2]);
+    } else {
+      stress_one_axis<MED>(z, m.ztx, m.zty, m.ztz, M, q);
+    }
 #pragma unroll
     for (int c = 3; c < 9; c++) {
       h[c] += cB1 * q[c];
@@ -176,25 +282,66 @@ __device__ __forceinline__ void pml_face_iso(const StageArgs &P, const PmlFaceDe
 }
 
 // all PML faces a point belongs to, in the reference's face order x1,x2,y1,y2,z1,z2
-template <int KIND, int PART>
-__device__ __forceinline__ void pml_all_iso(const StageArgs &P, int i, int j, int k, const Deriv &d, const Met &m,
-                                            float lam, float mu, float lam2mu, float slw, float *h)
+template <int KIND, int PART, int MED>
+__device__ __forceinline__ void pml_all(const StageArgs &P, int i, int j, int k, const Deriv &d, const Met &m, const Med<MED> &M,
+                                        float *h)
 {
 #pragma unroll
   for (int s = 0; s < 2; s++) {
     const PmlFaceDev &F = P.pml[0][s];
-    if (F.on && i >= F.i1 && i <= F.i2) pml_face_iso<0, KIND, PART>(P, F, i, j, k, d, m, lam, mu, lam2mu, slw, h);
+    if (F.on && i >= F.i1 && i <= F.i2) pml_face<0, KIND, PART, MED>(P, F, i, j, k, d, m, M, h);
   }
 #pragma unroll
   for (int s = 0; s < 2; s++) {
     const PmlFaceDev &F = P.pml[1][s];
-    if (F.on && j >= F.j1 && j <= F.j2) pml_face_iso<1, KIND, PART>(P, F, i, j, k, d, m, lam, mu, lam2mu, slw, h);
+    if (F.on && j >= F.j1 && j <= F.j2) pml_face<1, KIND, PART, MED>(P, F, i, j, k, d, m, M, h);
   }
 #pragma unroll
   for (int s = 0; s < 2; s++) {
     const PmlFaceDev &F = P.pml[2][s];
-    if (F.on && k >= F.k1 && k <= F.k2) pml_face_iso<2, KIND, PART>(P, F, i, j, k, d, m, lam, mu, lam2mu, slw, h);
+    if (F.on && k >= F.k1 && k <= F.k2) pml_face<2, KIND, PART, MED>(P, F, i, j, k, d, m, M, h);
   }
+}
+
+// Generalised-Maxwell-body attenuation (sv_curv_col_vis_iso_atten, forward/sv_curv_col_vis_iso.c:250-347) fused with the RK
+// update of the 6*N memory variables (components 9 + 6n + {Jxx,Jyy,Jzz,Jyz,Jxz,Jxy}, forward/wav_t.c:138-172):
+// strain rate from the stress RHS, hJ_n = wl_n (EV - J_n), hT -= lam sum Ylam_n tr(J_n) + 2 mu sum Ymu_n J_n.
+// h[TXX..TXY] must hold the complete stress RHS (after PML and free-surface corrections); p = point offset.
+template <int KIND>
+__device__ __forceinline__ void atten_update(const StageArgs &P, size_t p, float lam, float mu, float *h)
+{
+  const float sum_hxyz = (h[TXX] + h[TYY] + h[TZZ]) / (3.0f * lam + 2.0f * mu);
+  float EV[6];   // order of the J components: xx, yy, zz, yz, xz, xy
+  EV[0] = ((2.0f * h[TXX] - h[TYY] - h[TZZ]) / (2.0f * mu) + sum_hxyz) / 3.0f;
+  EV[1] = ((2.0f * h[TYY] - h[TXX] - h[TZZ]) / (2.0f * mu) + sum_hxyz) / 3.0f;
+  EV[2] = ((2.0f * h[TZZ] - h[TXX] - h[TYY]) / (2.0f * mu) + sum_hxyz) / 3.0f;
+  EV[3] = h[TYZ] / mu * 0.5f;
+  EV[4] = h[TXZ] / mu * 0.5f;
+  EV[5] = h[TXY] / mu * 0.5f;
+  float sum_tr = 0.0f, sum[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+  const int N = P.nmaxwell;
+  for (int n = 0; n < N; n++) {
+    const float ylam = __ldg(P.media[3 + n] + p), ymu = __ldg(P.media[3 + N + n] + p), wl = P.wl[n];
+    float J[6];
+#pragma unroll
+    for (int q = 0; q < 6; q++) J[q] = __ldg(P.cur + (size_t)(9 + 6 * n + q) * P.siz_vol + p);
+    sum_tr += ylam * (J[0] + J[1] + J[2]);
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+      sum[q] += ymu * J[q];
+      const float hJ = wl * (EV[q] - J[q]);
+      const size_t o = (size_t)(9 + 6 * n + q) * P.siz_vol + p;
+      const float pv = (KIND == KIND_MID) ? __ldg(P.pre + o) : 0.0f;
+      const float ev = (KIND != KIND_FIRST) ? P.end[o] : 0.0f;
+      rk_store<KIND>(P.tmp, P.end, o, J[q], pv, ev, hJ, P.a, P.b);
+    }
+  }
+  h[TXX] -= lam * sum_tr + 2.0f * mu * sum[0];
+  h[TYY] -= lam * sum_tr + 2.0f * mu * sum[1];
+  h[TZZ] -= lam * sum_tr + 2.0f * mu * sum[2];
+  h[TYZ] -= 2.0f * mu * sum[3];
+  h[TXZ] -= 2.0f * mu * sum[4];
+  h[TXY] -= 2.0f * mu * sum[5];
 }
 
 }  // namespace cgfd

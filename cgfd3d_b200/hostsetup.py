@@ -459,7 +459,7 @@ def make_source(prob: HostProblem, si, sj, sk, *, nt_total, kind="moment", mech=
 def build_problem(ni, nj, nk, *, dh=(100.0, 100.0, 100.0), topo="flat", hill=(1000.0, 2000.0),
                   vp=3000.0, vs=2000.0, rho=1500.0, pml_layers=10,
                   pml_faces=((0, 0), (0, 1), (1, 0), (1, 1), (2, 0)), free_top=True, dt=None, dt_safety=1.0,
-                  timg_mode=abi.TIMG_ZERO, sub=None) -> HostProblem:
+                  timg_mode=abi.TIMG_ZERO, sub=None, medium="iso", nmaxwell=3, seed=None) -> HostProblem:
     """Homogeneous isotropic half-space (medium 'code' of forward/md_t.c:456-463: Vp 3000, Vs 2000, rho 1500)
     on a Cartesian or Gaussian-hill grid with CFS-PML + free top.
     sub = (gi0, gj0, gni, gnj, neigh) places this block inside a global x-y decomposition."""
@@ -485,8 +485,9 @@ def build_problem(ni, nj, nk, *, dh=(100.0, 100.0, 100.0), topo="flat", hill=(10
         cs = (slice(None), slice(ex[2], ex[2] + nj + 2 * NG), slice(ex[0], ex[0] + ni + 2 * NG))
         x, y, z = (np.ascontiguousarray(a[cs]) for a in (x, y, z))
         metric = [np.ascontiguousarray(m[cs]) for m in metric]
+    vp_max = vp if medium in ("iso", "visco") else math.sqrt(25.2e9 * 1.1 / rho)
     if dt is None:
-        dt = estimate_dt(x, y, z, vp) * dt_safety
+        dt = estimate_dt(x, y, z, vp_max) * dt_safety
     prob = HostProblem(ni=ni, nj=nj, nk=nk, dt=float(f32(dt)), free_top=1 if free_top else 0, timg_mode=timg_mode,
                        neigh=tuple(neigh), coords=(x, y, z))
     prob.metric = metric
@@ -494,13 +495,66 @@ def build_problem(ni, nj, nk, *, dh=(100.0, 100.0, 100.0), topo="flat", hill=(10
     mu = f32(rho * vs * vs)
     lam = f32(rho * vp * vp - 2.0 * rho * vs * vs)
     prob.media = [np.full(shape, lam, f32), np.full(shape, mu, f32), np.full(shape, f32(1.0) / f32(rho), f32)]
+    if medium != "iso":
+        set_test_medium(prob, medium, rho=rho, nmaxwell=nmaxwell, seed=seed)
     g = prob.grid
     for (idim, iside) in pml_faces:
         if idim < 2 and neigh[idim * 2 + iside] >= 0:
             continue  # inter-rank face: no PML (forward/bdry_t.c:154-158)
         A, B, D = pml_profiles(x, y, z, g, idim, iside, pml_layers)
         prob.pml[(idim, iside)] = (pml_layers, A, B, D)
-    if free_top:
+    if free_top and medium == "iso":
         mvx, mvy, mf = dvh2dvz_iso(metric, prob.media[0], prob.media[1], g)
         prob.mats = dict(matVx2Vz=mvx, matVy2Vz=mvy, matF2Vz=mf, matD=np.zeros_like(mf))
+    elif free_top:
+        # vti / aniso / visco: the 3x3 surface matrices come from the reference's own one-shot *_dvh2dvz set-up code
+        # (kept as host code by the drop-in driver); callers fill prob.mats from it
+        z9 = np.zeros(prob.nx * prob.ny * 9, f32)
+        prob.mats = dict(matVx2Vz=z9.copy(), matVy2Vz=z9.copy(), matF2Vz=z9.copy(), matD=z9.copy())
+    return prob
+
+
+def set_test_medium(prob: HostProblem, medium: str, rho=1500.0, nmaxwell=3, seed=None):
+    """Synthetic media of the other three constitutive laws (values after forward/md_t.c:501-595, 912-952), optionally with
+    a +-10 % point-wise random perturbation so that every array matters."""
+    shape = (prob.nz, prob.ny, prob.nx)
+    rng = np.random.default_rng(seed if seed is not None else 0)
+
+    def fld(v, amp=0.1):
+        a = np.full(shape, v, np.float64)
+        if seed is not None:
+            a *= 1.0 + amp * rng.uniform(-1, 1, shape)
+        return a.astype(f32)
+
+    slw = fld(1.0 / rho)
+    if medium == "vti":
+        prob.medium_type = abi.MEDIUM_ELASTIC_VTI
+        prob.media = [fld(25.2e9), fld(10.962e9), fld(18.0e9), fld(5.12e9), fld(7.168e9), slw]   # c11 c13 c33 c55 c66 1/rho
+    elif medium == "aniso":
+        prob.medium_type = abi.MEDIUM_ELASTIC_ANISO
+        c11, c13, c33, c55, c66 = 25.2e9, 10.962e9, 18.0e9, 5.12e9, 7.168e9
+        c12 = c11 - 2 * c66
+        # upper triangle row by row; the off-diagonal couplings a VTI medium lacks get small non-zero values
+        e = 0.15e9
+        C = [c11, c12, c13, e, -e, 0.5 * e,
+             c11, c13, -0.5 * e, e, 0.7 * e,
+             c33, 0.3 * e, -0.6 * e, e,
+             c55, 0.4 * e, -0.2 * e,
+             c55, 0.8 * e,
+             c66]
+        prob.media = [fld(v) for v in C] + [slw]
+    elif medium == "visco":
+        prob.medium_type = abi.MEDIUM_VISCOELASTIC_ISO
+        prob.nmaxwell = nmaxwell
+        lam, mu = prob.media[0], prob.media[1]
+        if seed is not None:
+            lam = (lam * (1.0 + 0.1 * rng.uniform(-1, 1, shape))).astype(f32)
+            mu = (mu * (1.0 + 0.1 * rng.uniform(-1, 1, shape))).astype(f32)
+        ylam = [fld(0.03 + 0.01 * n) for n in range(nmaxwell)]
+        ymu = [fld(0.05 + 0.01 * n) for n in range(nmaxwell)]
+        prob.media = [lam, mu, slw] + ylam + ymu
+        # relaxation frequencies log-spaced over 0.1 .. 10 Hz (md_vis_GMB_cal_Y, forward/md_t.c:642-792)
+        prob.visco_wl = tuple(float(f32(2.0 * math.pi * 10 ** (-1.0 + 2.0 * n / max(nmaxwell - 1, 1)))) for n in range(nmaxwell))
+    else:
+        raise ValueError(medium)
     return prob

@@ -113,7 +113,7 @@ typedef struct {
   int32_t medium_type;                    /* CGFD_MEDIUM_* */
   int32_t nmaxwell;                       /* visco GMB only; ncmp = 9 + 6*nmaxwell */
   int32_t ncmp;
-  const float *metric[CGFD_NUM_METRIC];   /* each [nz][ny][nx] */
+  const float *metric[CGFD_NUM_METRIC];   /* each [nz][ny][nx]; metric and media may be host OR device pointers */
   /* media arrays, each [nz][ny][nx] (forward/md_t.c:57-260), rho already holds 1/rho
    * (forward/main_curv_col_el_3d.c:843):
    *   iso   : lambda, mu, rho

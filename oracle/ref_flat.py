@@ -31,6 +31,7 @@ def lib():
         L.cgfd_ref_create.restype = C.c_void_p
         L.cgfd_ref_create.argtypes = [C.c_void_p]
         L.cgfd_ref_ncmp.argtypes = [C.c_void_p]
+        L.cgfd_ref_set_coords.argtypes = [C.c_void_p, fptr, fptr, fptr]
         L.cgfd_ref_pml_aux_size.restype = C.c_size_t
         L.cgfd_ref_pml_aux_size.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.cgfd_ref_set_pml_aux.argtypes = [C.c_void_p, C.c_int, C.c_int, fptr]
@@ -58,20 +59,26 @@ class RefSolver:
         if not self.h:
             raise RuntimeError("cgfd_ref_create failed")
         self.ncmp = lib().cgfd_ref_ncmp(self.h)
+        if getattr(prob, "coords", None) is not None:
+            x, y, z = (np.ascontiguousarray(a, np.float32) for a in prob.coords)
+            assert lib().cgfd_ref_set_coords(self.h, _f(x), _f(y), _f(z)) == 0
         self.shape = (self.ncmp, prob.nz, prob.ny, prob.nx)
 
     def pml_aux_size(self, idim, iside):
         return lib().cgfd_ref_pml_aux_size(self.h, idim, iside)
 
     def set_pml_aux(self, idim, iside, aux):
-        aux = np.ascontiguousarray(aux, np.float32)
-        assert aux.size == self.pml_aux_size(idim, iside)
-        assert lib().cgfd_ref_set_pml_aux(self.h, idim, iside, _f(aux)) == 0
+        """aux: the 9 components in use; the reference allocates ncmp per level (forward/bdry_t.c:300), the rest stays 0"""
+        aux = np.ascontiguousarray(aux, np.float32).ravel()
+        full = np.zeros(self.pml_aux_size(idim, iside), np.float32)
+        assert aux.size == full.size // self.ncmp * 9
+        full[:aux.size] = aux
+        assert lib().cgfd_ref_set_pml_aux(self.h, idim, iside, _f(full)) == 0
 
     def get_pml_aux(self, idim, iside, level=0):
         out = np.zeros(self.pml_aux_size(idim, iside), np.float32)
         assert lib().cgfd_ref_get_pml_aux(self.h, idim, iside, level, _f(out)) == 0
-        return out
+        return out[:out.size // self.ncmp * 9].copy()
 
     def get_pml_aux_rhs(self, idim, iside):
         return self.get_pml_aux(idim, iside, 2)

@@ -223,6 +223,15 @@ void *cgfd_ref_create(const cgfd_problem_t *p)
 
 int cgfd_ref_ncmp(void *h) { return ((ref_t *)h)->wav.ncmp; }
 
+/* grid coordinates [nz][ny][nx] (gd->x3d/y3d/z3d, forward/gd_t.c:23-95): only sv_curv_col_vis_iso_dvh2dvz reads them
+ * (surface tangents for matD, forward/sv_curv_col_vis_iso.c:375-507); the C ABI problem does not carry coordinates */
+int cgfd_ref_set_coords(void *h, const float *x, const float *y, const float *z)
+{
+  ref_t *r = (ref_t *)h;
+  r->gd.x3d = dupf(x, r->nvol); r->gd.y3d = dupf(y, r->nvol); r->gd.z3d = dupf(z, r->nvol);
+  return 0;
+}
+
 size_t cgfd_ref_pml_aux_size(void *h, int idim, int iside)
 {
   return ((ref_t *)h)->bdry.auxvar[idim][iside].siz_ilevel;

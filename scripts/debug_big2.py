@@ -1,0 +1,28 @@
+#!/usr/bin/env python
+"""which planes / tiles hold non-finite values after a few steps of a big block"""
+import os, sys
+import numpy as np
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench
+from cgfd3d_b200 import solver
+
+size = tuple(int(v) for v in sys.argv[1].split("x"))
+nsteps = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+torch.cuda.set_device(0)
+prob = bench.build_rank_problem(size, 0, 1, device="cuda:0")
+S = solver.Solver(prob, device=0)
+prob.metric = prob.media = None
+torch.cuda.empty_cache()
+S.run(nsteps, it0=0)
+bad_k = []
+for k in range(prob.nz):
+    b = S.get_box(3, 0, prob.nx, 1, 0, prob.ny, 1, k, 1, 1)[0]
+    bad = ~np.isfinite(b)
+    if bad.any():
+        jj, ii = np.nonzero(bad)
+        bad_k.append((k, int(bad.sum()), int(ii.min()), int(ii.max()), int(jj.min()), int(jj.max())))
+print("size", size, "steps", nsteps, "bad planes", len(bad_k))
+for r in bad_k[:12] + bad_k[-4:]:
+    print("  k=%d nbad=%d i[%d..%d] j[%d..%d]" % r)

@@ -7,12 +7,12 @@ CMP = abi.CMP_NAMES
 
 
 def small_problem(ni=26, nj=22, nk=20, topo="hill", pml_layers=4, free_top=True, pml_faces=None, src="moment",
-                  spatial="point", nt_total=40, timg_mode=abi.TIMG_ZERO, dt=None, seed=None):
+                  spatial="point", nt_total=40, timg_mode=abi.TIMG_ZERO, dt=None, seed=None, medium="iso"):
     if pml_faces is None:
         pml_faces = ((0, 0), (0, 1), (1, 0), (1, 1), (2, 0)) if free_top else ((0, 0), (0, 1), (1, 0), (1, 1), (2, 0), (2, 1))
     prob = hs.build_problem(ni, nj, nk, topo=topo, hill=(300.0, 600.0), pml_layers=pml_layers, pml_faces=pml_faces,
-                            free_top=free_top, timg_mode=timg_mode, dt=dt, dt_safety=0.9)
-    if seed is not None:
+                            free_top=free_top, timg_mode=timg_mode, dt=dt, dt_safety=0.9, medium=medium, seed=seed)
+    if seed is not None and medium == "iso":
         # heterogeneous medium: +-20 % smooth-free random perturbation keeps the scheme stable for short runs
         rng = np.random.default_rng(seed)
         shape = prob.media[0].shape
@@ -32,6 +32,13 @@ def small_problem(ni=26, nj=22, nk=20, topo="hill", pml_layers=4, free_top=True,
     return prob
 
 
+def fill_surface_matrices(prob, R):
+    """free-surface matrices of a non-isotropic problem from the reference's own *_dvh2dvz (R = ref_flat.RefSolver(prob))"""
+    if prob.free_top and prob.medium_type != abi.MEDIUM_ELASTIC_ISO:
+        prob.mats = R.dvh2dvz()
+    return prob
+
+
 def random_state(prob, seed=12345, scale_t=1.0e6):
     """wavefield U(-0.5,0.5) (stress scaled so both halves of the RHS matter), zero in the ghosts of
     physical faces like the reference keeps them; random PML aux of matching magnitudes."""
@@ -40,6 +47,8 @@ def random_state(prob, seed=12345, scale_t=1.0e6):
     ph = (slice(None), slice(3, prob.nz - 3), slice(3, prob.ny - 3), slice(3, prob.nx - 3))
     w[ph] = rng.uniform(-0.5, 0.5, w[ph].shape)
     w[3:9] *= scale_t
+    if prob.ncmp > 9:
+        w[9:] *= 1.0e-4   # memory variables are strains
     aux = {}
     for key in prob.pml:
         shp = prob.pml_aux_shape(*key)
