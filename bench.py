@@ -34,6 +34,9 @@ os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 
 METRIC = "Gpoint-updates/s per RK4 step"
 BYTES_PER_POINT_STEP_ISO = 768.0  # 4*(16*C + 4*M), C = 9, M = 12
+# the same formula for the other media (visco: 3 Maxwell bodies, C = 27, M = 9 + 3 + 6)
+BYTES_PER_POINT_STEP = {"iso": 768.0, "vti": 816.0, "aniso": 1072.0, "visco": 2016.0}
+WORKLOAD = {"iso": "isotropic elastic", "vti": "VTI elastic", "aniso": "general anisotropic elastic", "visco": "visco-elastic isotropic (GMB, 3 Maxwell bodies)"}
 
 
 def parse_size(s):
@@ -91,7 +94,7 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(self.rows)}
 
 
-def build_rank_problem(size, rank, nranks, device=None):
+def build_rank_problem(size, rank, nranks, device=None, medium="iso"):
     """One rank's block of the global hill problem. device=None: numpy on the host (hostsetup); device='cuda:N': the same
     formulas as torch expressions on that GPU (devsetup) -- used for the 800x800x400-per-GPU runs, where the numpy route
     needs ~45 GB of host memory and minutes per rank."""
@@ -107,7 +110,13 @@ def build_rank_problem(size, rank, nranks, device=None):
     dh = (100.0, 100.0, 100.0)
     sigma = 0.1 * max(gni, gnj) * dh[0]
     # dt below the CFL bound of the stretched grid (estimate_dt on the full array is slow; checked in tests)
-    if device is None:
+    if medium != "iso":
+        # the other constitutive laws (BASELINE.json configs[3], [4] are parity cases, not bench lines): CFS-PML on all six
+        # faces, because their free-surface matrices come from the reference's own host set-up code
+        prob = hs.build_problem(ni, nj, nk, dh=dh, topo="hill", hill=(1000.0, sigma), pml_layers=10, free_top=False,
+                                pml_faces=((0, 0), (0, 1), (1, 0), (1, 1), (2, 0), (2, 1)), dt=0.008,
+                                sub=(ix * ni, iy * nj, gni, gnj, neigh), medium=medium)
+    elif device is None:
         prob = hs.build_problem(ni, nj, nk, dh=dh, topo="hill", hill=(1000.0, sigma), pml_layers=10, free_top=True,
                                 dt=0.012, sub=(ix * ni, iy * nj, gni, gnj, neigh))
     else:
@@ -138,8 +147,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     size = args.size or ((400, 400, 200) if nranks == 1 else (800, 800, 400))
     t0 = time.time()
-    on_device = size[0] * size[1] * size[2] > 64e6   # big blocks: build the set-up arrays on the GPU (see devsetup.py)
-    prob = build_rank_problem(size, rank, nranks, device=("cuda:%d" % local) if on_device else None)
+    on_device = size[0] * size[1] * size[2] > 64e6 and args.medium == "iso"   # big blocks: set-up arrays built on the GPU (devsetup.py)
+    prob = build_rank_problem(size, rank, nranks, device=("cuda:%d" % local) if on_device else None, medium=args.medium)
     t_host = time.time() - t0
     t0 = time.time()
     S = solver.Solver(prob, device=local)
@@ -187,9 +196,10 @@ def run_ours(args):
     rec = [prob.iptr(ni // 2 + 5 * n, nj // 2 + 3 * n, nk - 1) for n in range(-4, 5)]
     S.set_record_points(rec, K + 8)
     w_host = torch.zeros(S.shape, dtype=torch.float32).pin_memory().numpy()
+    ncmp = S.shape[0]
     snap = torch.zeros((3, nj, ni), dtype=torch.float32).pin_memory().numpy()
     h2d = w_host.nbytes / K
-    d2h = w_host.nbytes / K + len(rec) * 9 * 4 + snap.nbytes
+    d2h = w_host.nbytes / K + len(rec) * ncmp * 4 + snap.nbytes
     barrier()
     te0 = time.time()
     S.set_wavefield(w_host)
@@ -216,26 +226,28 @@ def run_ours(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         kb = (main_ms / max(main_n, 1)) * 1e-3
         # algorithmic bytes of one interior-kernel launch = 768/4 B per point-stage x the points it covers
-        main_pts = ni * nj * (nk - 4)   # the free-surface kernel owns the top 4 rows
-        ach = (BYTES_PER_POINT_STEP_ISO / 4.0) * main_pts / kb / 1e9 if main_n else None
+        bpps = BYTES_PER_POINT_STEP[args.medium]
+        main_pts = ni * nj * (nk - 4 if prob.free_top else nk)   # the free-surface kernel owns the top 4 rows
+        ach = (bpps / 4.0) * main_pts / kb / 1e9 if main_n else None
         out = {
             "metric": METRIC, "value": round(value, 4), "unit": "Gpoint-updates/s", "n_gpus": nranks, "steps": K, "warmup": W,
             "ms_per_step": round(ms_max / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "isotropic elastic, Gaussian-hill topography (curvilinear), %dx%dx%d per GPU, CFS-PML 10 layers x 5 faces, "
-                                   "traction-image free surface, 1 moment source" % size,
+            "config": {"workload": ("%s, Gaussian-hill topography (curvilinear), %dx%dx%d per GPU, " % ((WORKLOAD[args.medium],) + tuple(size)))
+                                   + ("CFS-PML 10 layers x 5 faces, traction-image free surface, 1 moment source" if prob.free_top
+                                      else "CFS-PML 10 layers x 6 faces, 1 moment source"),
                        "proc_grid": "%dx%d" % proc_grid(nranks), "l2": "working set >> 126 MB L2 (no flush needed)",
                        "variant": args.variant or "default"},
             "e2e": {"value": round(e2e, 4), "unit": "Gpoint-updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "what": "set_wavefield + K x (run(1) + receivers + surface Vx/Vy/Vz snapshot to host) + get_wavefield"},
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
-            "roofline": {"bound": "hbm", "kernel": "k_iso_main", "achieved": None if ach is None else round(ach, 1), "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "k_main_tma", "achieved": None if ach is None else round(ach, 1), "peak": peak,
                          "unit": "GB/s", "frac": None if ach is None else round(ach / peak, 4), "traffic": ncu_traffic(size),
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                          "launches_timed": int(main_n), "avg_launch_ms": round(main_ms / max(main_n, 1), 4),
-                         "algorithmic_bytes_per_launch": int((BYTES_PER_POINT_STEP_ISO / 4.0) * main_pts),
-                         "whole_step_frac": round(BYTES_PER_POINT_STEP_ISO * npts / (ms_max / K * 1e-3) / 1e9 / peak, 4)},
+                         "algorithmic_bytes_per_launch": int((bpps / 4.0) * main_pts),
+                         "whole_step_frac": round(bpps * npts / (ms_max / K * 1e-3) / 1e9 / peak, 4)},
             "setup_s": {"arrays": round(t_host, 2), "arrays_built_on": "gpu (torch)" if on_device else "host (numpy)", "upload": round(t_upload, 2)},
             "wall_s_timed": round(tw1 - tw0, 4), "finite": finite,
         }
@@ -329,6 +341,8 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--size", type=parse_size, default=None)
     ap.add_argument("--variant", default="")
+    ap.add_argument("--medium", default="iso", choices=["iso", "vti", "aniso", "visco"],
+                    help="constitutive law (default iso = the BASELINE.json metric; the others are side measurements)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=4)
     args = ap.parse_args()

@@ -139,8 +139,12 @@ template <typename T> static int upload(cgfd_b200_ctx *c, T **dst, const T *src,
   if (n == 0) return 0;
   CK(cudaMalloc((void **)dst, n * sizeof(T)));
   c->owned.push_back(*dst);
-  if (src) CK(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
-  else CK(cudaMemset(*dst, 0, n * sizeof(T)));
+  // everything goes through the context's own stream: it is a non-blocking stream, so work issued on the legacy default
+  // stream (a plain cudaMemset is asynchronous for device memory) would NOT be ordered before the copies and kernels
+  // that follow on c->st -- with device-to-device set-up copies that race was real (zeroed metrics, NaN at the surface)
+  if (src) CK(cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyDefault, c->st));
+  else CK(cudaMemsetAsync(*dst, 0, n * sizeof(T), c->st));
+  CK(cudaStreamSynchronize(c->st));
   return 0;
 }
 
@@ -543,7 +547,8 @@ extern "C" int cgfd_b200_set_pml_aux(cgfd_b200_ctx *c, int idim, int is, const f
   PmlFaceHost &h = c->pml[idim][is];
   if (!h.on) return fail("set_pml_aux: face has no PML");
   CK(cudaSetDevice(c->device));
-  CK(cudaMemcpy(h.aux[c->ipre], aux, h.siz * 9 * sizeof(float), cudaMemcpyHostToDevice));
+  CK(cudaMemcpyAsync(h.aux[c->ipre], aux, h.siz * 9 * sizeof(float), cudaMemcpyHostToDevice, c->st));
+  CK(cudaStreamSynchronize(c->st));
   return 0;
 }
 extern "C" int cgfd_b200_get_pml_aux(cgfd_b200_ctx *c, int idim, int is, float *aux)
@@ -552,7 +557,8 @@ extern "C" int cgfd_b200_get_pml_aux(cgfd_b200_ctx *c, int idim, int is, float *
   if (!h.on) return fail("get_pml_aux: face has no PML");
   CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->st));
-  CK(cudaMemcpy(aux, h.aux[c->ipre], h.siz * 9 * sizeof(float), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpyAsync(aux, h.aux[c->ipre], h.siz * 9 * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
   return 0;
 }
 extern "C" int cgfd_b200_get_pml_aux_rhs(cgfd_b200_ctx *c, int idim, int is, float *aux)
@@ -561,7 +567,8 @@ extern "C" int cgfd_b200_get_pml_aux_rhs(cgfd_b200_ctx *c, int idim, int is, flo
   if (!h.on) return fail("get_pml_aux_rhs: face has no PML");
   CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->st));
-  CK(cudaMemcpy(aux, h.aux[c->ib], h.siz * 9 * sizeof(float), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpyAsync(aux, h.aux[c->ib], h.siz * 9 * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
   return 0;
 }
 
@@ -617,11 +624,11 @@ static int split_tiles(const cgfd_b200_ctx *c, bool split, int bnd[4][4], int in
 // The interior kernel never touches what the boundary phase writes (disjoint points; ghosts are written by the unpack
 // only), so the halo exchange is hidden behind it. The stage ends with st waiting for st2.
 static int run_stage(cgfd_b200_ctx *c, StageArgs &P, int it, int ipair, int istage, int kind, int icur, int ipre, int itmp,
-                     int iend, float a, float b, float *halo_w, int halo_dx, int halo_dy)
+                     int iend, float a, float b, float cc, float *halo_w, int halo_dx, int halo_dy)
 {
   const int sh = c->shift;
   P.cur = c->lev[icur] + sh; P.pre = c->lev[ipre] + sh; P.tmp = c->lev[itmp] + sh; P.end = c->lev[iend] + sh;
-  P.a = a; P.b = b;
+  P.a = a; P.b = b; P.c = cc;
   TmaMaps maps;
   if (c->have_maps) {
     maps.cur = c->map_halo[icur]; maps.pre = c->map_cen[ipre]; maps.end = c->map_cen[iend];
@@ -703,7 +710,9 @@ extern "C" int cgfd_b200_run(cgfd_b200_ctx *c, int it0, int nsteps)
   for (int it = it0; it < it0 + nsteps; it++) {
     const int ipair = it % CGFD_NUM_PAIRS;
     for (int s = 0; s < CGFD_NUM_STAGES; s++) {
-      const int kind = (s == 0) ? KIND_FIRST : (s == CGFD_NUM_STAGES - 1) ? KIND_LAST : KIND_MID;
+      const int kind = (s == 0) ? KIND_FIRST : (s == 1) ? KIND_MID : (s == 2) ? KIND_THIRD : KIND_LAST;
+      // weight of (w_cur - w_pre) = a_{s-1} dt h_{s-1} in the w_end update of stages 1 and 3
+      const float cc = (s == 1 || s == 3) ? (float)((double)c->fd.rk_b[s - 1] / (double)c->fd.rk_a[s - 1]) : 0.0f;
       const int icur = (s == 0) ? c->ipre : (s & 1) ? c->ia : c->ib;
       const int itmp = (s & 1) ? c->ib : c->ia;
       const float a = c->fd.rk_a[s] * dt, b = c->fd.rk_b[s] * dt;
@@ -712,7 +721,7 @@ extern "C" int cgfd_b200_run(cgfd_b200_ctx *c, int it0, int nsteps)
       const int np = (s != CGFD_NUM_STAGES - 1) ? ipair : (it + 1) % CGFD_NUM_PAIRS;
       const int ns = (s != CGFD_NUM_STAGES - 1) ? s + 1 : 0;
       float *hw = c->halo ? ((s != CGFD_NUM_STAGES - 1) ? c->lev[itmp] : c->lev[c->iend]) + c->shift : nullptr;
-      if (run_stage(c, P, it, ipair, s, kind, icur, c->ipre, itmp, c->iend, a, b, hw, c->fd.dir[np][ns][0], c->fd.dir[np][ns][1])) return 1;
+      if (run_stage(c, P, it, ipair, s, kind, icur, c->ipre, itmp, c->iend, a, b, cc, hw, c->fd.dir[np][ns][0], c->fd.dir[np][ns][1])) return 1;
     }
     float *wnew = c->lev[c->iend] + c->shift, *wold = c->lev[c->ipre] + c->shift;
     const cgfd_grid_t &g = c->g;
@@ -790,7 +799,7 @@ extern "C" int cgfd_b200_onestage(cgfd_b200_ctx *c, int it, int ipair, int istag
   // aux: cur = copy of level n, pre = zeros, tmp = out, end = scratch
   // run_stage sets aux pointers from level indices; patch aux_pre to the zero buffer afterwards is not
   // possible through indices, so do it by hand here.
-  P.a = 1.0f; P.b = 0.0f;
+  P.a = 1.0f; P.b = 0.0f; P.c = 0.0f;
   for (int idim = 0; idim < 3; idim++) for (int is = 0; is < 2; is++) {
     PmlFaceHost &h = c->pml[idim][is];
     if (!h.on) continue;
@@ -805,10 +814,10 @@ extern "C" int cgfd_b200_onestage(cgfd_b200_ctx *c, int it, int ipair, int istag
   }
   const int *dir = c->fd.dir[ipair][istage];
   const int whole[4] = {0, c->ntx, 0, c->nty};
-  launch_top(c->med, P, dir, KIND_MID, c->st, &nl);
-  launch_main(c->med, P, &maps, dir, KIND_MID, c->zchunk, whole, c->st, nullptr, nullptr, &nl);
+  launch_top(c->med, P, dir, KIND_THIRD, c->st, &nl);
+  launch_main(c->med, P, &maps, dir, KIND_THIRD, c->zchunk, whole, c->st, nullptr, nullptr, &nl);
   if (c->has_src)
-    k_src_inject<<<(c->src.npts + 127) / 128, 128, 0, c->st>>>(c->src, 0, c->src.npts, it, istage, c->lev[iout] + sh, c->lev[izero] + sh, 1.0f, 0.0f, c->V, KIND_MID);
+    k_src_inject<<<(c->src.npts + 127) / 128, 128, 0, c->st>>>(c->src, 0, c->src.npts, it, istage, c->lev[iout] + sh, c->lev[izero] + sh, 1.0f, 0.0f, c->V, KIND_THIRD);
   CK(cudaGetLastError());
   if (copy_out3d(c, rhs, c->lev[iout], c->ncmp, c->st)) return 1;
   CK(cudaStreamSynchronize(c->st));
@@ -838,7 +847,8 @@ extern "C" int cgfd_b200_get_record(cgfd_b200_ctx *c, int it_first, int nt, floa
   CK(cudaSetDevice(c->device));
   if (it_first < 0 || it_first + nt > c->rec_count) return fail("get_record: step range not recorded");
   CK(cudaStreamSynchronize(c->st));
-  CK(cudaMemcpy(out, c->rec + (size_t)it_first * c->ncmp * c->nrec, (size_t)nt * c->ncmp * c->nrec * sizeof(float), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpyAsync(out, c->rec + (size_t)it_first * c->ncmp * c->nrec, (size_t)nt * c->ncmp * c->nrec * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
   return 0;
 }
 extern "C" int cgfd_b200_get_box(cgfd_b200_ctx *c, int icmp, int i1, int ni, int di, int j1, int nj, int dj, int k1, int nk, int dk,
@@ -867,7 +877,8 @@ extern "C" int cgfd_b200_get_pg(cgfd_b200_ctx *c, float *pg)
   if (!c->PG) return fail("get_pg: no free surface");
   CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->st));
-  CK(cudaMemcpy(pg, c->PG, c->hslice * 15 * sizeof(float), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpyAsync(pg, c->PG, c->hslice * 15 * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
   return 0;
 }
 

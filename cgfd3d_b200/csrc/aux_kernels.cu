@@ -33,8 +33,9 @@ __global__ void k_src_inject(SrcDev S, int first, int count, int it, int istage,
 #pragma unroll
   for (int c = 0; c < 9; c++) {
     if (add[c] != 0.0f) {
+      // stages 0 and 2 reach w_end through w_tmp - w_pre one stage later (rk_wave, physics.cuh)
       if (kind != KIND_LAST) atomicAdd(tmp + c * V + p, a * add[c]);
-      atomicAdd(end + c * V + p, b * add[c]);
+      if (kind == KIND_MID || kind == KIND_LAST) atomicAdd(end + c * V + p, b * add[c]);
     }
   }
 }

@@ -12,7 +12,15 @@ enum { VX = 0, VY, VZ, TXX, TYY, TZZ, TYZ, TXZ, TXY, NCMP_EL = 9 };
 // metric order, forward/gd_t.c:101-180
 enum { M_JAC = 0, M_XIX, M_XIY, M_XIZ, M_ETX, M_ETY, M_ETZ, M_ZTX, M_ZTY, M_ZTZ, NMETRIC = 10 };
 
-enum { KIND_FIRST = 0, KIND_MID = 1, KIND_LAST = 2 };
+// RK stage kinds. The wavefield update skips every w_end access that can be reconstructed (see rk_wave in physics.cuh):
+//   FIRST (stage 0): tmp = cur + a h                                   loads cur            stores tmp
+//   MID   (stage 1): tmp = pre + a h ; end = pre + c (cur-pre) + b h   loads cur, pre       stores tmp, end
+//   THIRD (stage 2): tmp = pre + a h                                   loads cur, pre       stores tmp
+//   LAST  (stage 3): end = end + c (cur-pre) + b h                     loads cur, pre, end  stores end
+// with c = b_prev / a_prev, because cur = pre + a_prev h_prev. PML auxiliary variables and visco-elastic memory variables
+// keep the plain three-kind update (FIRST / MID / LAST; THIRD behaves like MID there).
+enum { KIND_FIRST = 0, KIND_MID = 1, KIND_LAST = 2, KIND_THIRD = 3 };
+__host__ __device__ constexpr int aux_kind(int kind) { return kind == KIND_THIRD ? KIND_MID : kind; }
 
 constexpr int MAX_MEDIA = 24;
 constexpr int MAX_MAXWELL = 8;
@@ -59,6 +67,7 @@ struct StageArgs {
   float *tmp;                   // w_tmp written for the next stage
   float *end;                   // w_end
   float a, b;                   // rk_a[s]*dt, rk_b[s]*dt (forward/drv_rk_curv_col.c:294-295)
+  float c;                      // rk_b[s-1]/rk_a[s-1]: weight of (cur - pre) in the w_end update of stages 1 and 3
   const float *metric[NMETRIC];
   const float *media[MAX_MEDIA];
   int nmaxwell;

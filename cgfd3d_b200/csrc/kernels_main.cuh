@@ -57,7 +57,7 @@ template <int MED> struct Lay {   // the media tiles come last: their number dep
 
 template <int KIND, int MED> __device__ __forceinline__ constexpr uint32_t stage_tx_bytes()
 {
-  return CUR_BYTES + (9 + Lay<MED>::NMT) * CEN_BYTES + (KIND == KIND_MID ? 9 * CEN_BYTES : 0) + (KIND != KIND_FIRST ? 9 * CEN_BYTES : 0);
+  return CUR_BYTES + (9 + Lay<MED>::NMT) * CEN_BYTES + (KIND != KIND_FIRST ? 9 * CEN_BYTES : 0) + (KIND == KIND_LAST ? 9 * CEN_BYTES : 0);
 }
 
 struct TmaCtx {
@@ -81,8 +81,8 @@ __device__ __forceinline__ void tma_issue(const StageArgs &P, const TmaMaps &M, 
   tma_load_4d_hint(b + OFF_CUR, &M.cur, bar, C.i0 - HX + P.shift, C.j0 - YL, kk, 0, C.pol_keep);
   tma_load_4d_hint(b + OFF_MET, &M.met, bar, C.i0 + P.shift, C.j0, kk, 0, C.pol_stream);
   tma_load_4d_hint(b + OFF_MED, &M.med, bar, C.i0 + P.shift, C.j0, kk, 0, C.pol_stream);
-  if (KIND == KIND_MID) tma_load_4d_hint(b + OFF_PRE, &M.pre, bar, C.i0 + P.shift, C.j0, kk, 0, C.pol_stream);
-  if (KIND != KIND_FIRST) tma_load_4d_hint(b + OFF_END, &M.end, bar, C.i0 + P.shift, C.j0, kk, 0, C.pol_stream);
+  if (KIND != KIND_FIRST) tma_load_4d_hint(b + OFF_PRE, &M.pre, bar, C.i0 + P.shift, C.j0, kk, 0, C.pol_stream);
+  if (KIND == KIND_LAST) tma_load_4d_hint(b + OFF_END, &M.end, bar, C.i0 + P.shift, C.j0, kk, 0, C.pol_stream);
 }
 
 // One plane. The march along z runs TOWARDS the short side of the one-sided zeta operator (upwards for
@@ -136,10 +136,10 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
                   : cz[0] * q4[c] + cz[1] * q3[c] + cz[2] * q2[c] + cz[3] * q1[c] + cz[4] * q0[c];
     }
     hooke<MED>(d, m, md, h);
-    if (PML) pml_all<KIND, 0, MED>(P, C.i, C.j, k, d, m, md, h);
-    if constexpr (MED == MED_VIS) atten_update<KIND>(P, (size_t)k * P.siz_slice + C.pij, md.lam, md.mu, h);
+    if (PML) pml_all<aux_kind(KIND), 0, MED>(P, C.i, C.j, k, d, m, md, h);
+    if constexpr (MED == MED_VIS) atten_update<aux_kind(KIND)>(P, (size_t)k * P.siz_slice + C.pij, md.lam, md.mu, h);
 #pragma unroll
-    for (int c = 3; c < 9; c++) rk_smem<KIND>(sp + c * NT, se + c * NT, qz[c], h[c], P.a, P.b);
+    for (int c = 3; c < 9; c++) rk_smem<KIND>(sp + c * NT, se + c * NT, qz[c], h[c], P.a, P.b, P.c);
     // ---- velocity half: needs the stress derivatives only
 #pragma unroll
     for (int c = 3; c < 9; c++) {
@@ -150,17 +150,18 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
                   : cz[0] * q4[c] + cz[1] * q3[c] + cz[2] * q2[c] + cz[3] * q1[c] + cz[4] * q0[c];
     }
     momentum(d, m, slw, h);
-    if (PML) pml_all<KIND, 1, MED>(P, C.i, C.j, k, d, m, md, h);
+    if (PML) pml_all<aux_kind(KIND), 1, MED>(P, C.i, C.j, k, d, m, md, h);
 #pragma unroll
-    for (int c = 0; c < 3; c++) rk_smem<KIND>(sp + c * NT, se + c * NT, qz[c], h[c], P.a, P.b);
+    for (int c = 0; c < 3; c++) rk_smem<KIND>(sp + c * NT, se + c * NT, qz[c], h[c], P.a, P.b, P.c);
     fence_proxy_async_smem();   // the results written above are read by the TMA store below
   }
   __syncthreads();   // every thread is done with ring slot s; its PRE / END tiles now hold w_tmp / w_end of this plane
   if (C.t == 0) {
     const int tx0 = C.i0 - P.ni1, ty0 = C.j0 - P.nj1;
     if (KIND != KIND_LAST) tma_store_4d_hint(&M.out_tmp, b + OFF_PRE, tx0, ty0, k, 0, C.pol_stream);
-    tma_store_4d_hint(&M.out_end, b + OFF_END, tx0, ty0, k, 0, C.pol_stream);
+    if (KIND == KIND_MID || KIND == KIND_LAST) tma_store_4d_hint(&M.out_end, b + OFF_END, tx0, ty0, k, 0, C.pol_stream);
     tma_store_commit();
+    if (P.l2mode & 8) tma_store_wait_all();   // debugging switch: synchronous stores
     if (it + NST < nplanes) {
       tma_store_wait_read();   // the slot may be refilled once the stores have read it
       tma_issue<DX, DY, KIND, MED>(P, M, C, k + NST * DIR, s);
@@ -234,6 +235,7 @@ __global__ void __launch_bounds__(TX *TY, Lay<MED>::BLOCKS) k_main_tma(const Sta
     for (int c = 0; c < 9; c++) { q0[c] = q1[c]; q1[c] = q2[c]; q2[c] = q3[c]; q3[c] = q4[c]; }
   }
   if (C.t == 0) tma_store_wait_all();
+  if (P.l2mode & 16) __syncthreads();   // debugging switch: no thread leaves before the stores are complete
 }
 
 // =============================================================================================
@@ -257,8 +259,8 @@ __global__ void __launch_bounds__(128, 3) k_top(const StageArgs P)
   float cur[9], pv[9], ev[9];
 #pragma unroll
   for (int c = 0; c < 9; c++) {
-    if (KIND == KIND_MID) pv[c] = __ldg(P.pre + c * V + p);
-    if (KIND != KIND_FIRST) ev[c] = P.end[c * V + p];
+    if (KIND != KIND_FIRST) pv[c] = __ldg(P.pre + c * V + p);
+    if (KIND == KIND_LAST) ev[c] = P.end[c * V + p];
   }
 #pragma unroll
   for (int c = 0; c < 9; c++) {
@@ -382,11 +384,11 @@ __global__ void __launch_bounds__(128, 3) k_top(const StageArgs P)
     }
   }
 
-  pml_all<KIND, 0, MED>(P, i, j, k, d, m, md, h);
-  pml_all<KIND, 1, MED>(P, i, j, k, d, m, md, h);
-  if constexpr (MED == MED_VIS) atten_update<KIND>(P, p, md.lam, md.mu, h);
+  pml_all<aux_kind(KIND), 0, MED>(P, i, j, k, d, m, md, h);
+  pml_all<aux_kind(KIND), 1, MED>(P, i, j, k, d, m, md, h);
+  if constexpr (MED == MED_VIS) atten_update<aux_kind(KIND)>(P, p, md.lam, md.mu, h);
 #pragma unroll
-  for (int c = 0; c < 9; c++) rk_store<KIND>(P.tmp, P.end, c * V + p, cur[c], pv[c], ev[c], h[c], P.a, P.b);
+  for (int c = 0; c < 9; c++) rk_wave<KIND>(P.tmp, P.end, c * V + p, cur[c], pv[c], ev[c], h[c], P.a, P.b, P.c);
 }
 
 // =============================================================================================
@@ -444,7 +446,10 @@ template <int KIND, int MED> static int set_attr_k()
   return set_attr_t<0, 0, 0, KIND, MED>() | set_attr_t<0, 0, 1, KIND, MED>() | set_attr_t<0, 1, 0, KIND, MED>() | set_attr_t<0, 1, 1, KIND, MED>() |
          set_attr_t<1, 0, 0, KIND, MED>() | set_attr_t<1, 0, 1, KIND, MED>() | set_attr_t<1, 1, 0, KIND, MED>() | set_attr_t<1, 1, 1, KIND, MED>();
 }
-template <int MED> int med_kernels_init() { return set_attr_k<KIND_FIRST, MED>() | set_attr_k<KIND_MID, MED>() | set_attr_k<KIND_LAST, MED>(); }
+template <int MED> int med_kernels_init()
+{
+  return set_attr_k<KIND_FIRST, MED>() | set_attr_k<KIND_MID, MED>() | set_attr_k<KIND_THIRD, MED>() | set_attr_k<KIND_LAST, MED>();
+}
 
 #define CGFD_DISPATCH_DIR(CALL)                                                                   \
   switch (dx * 4 + dy * 2 + dz) {                                                                  \
@@ -474,6 +479,7 @@ void med_launch_main(const StageArgs &P, const TmaMaps *maps, int dx, int dy, in
 {
   if (kind == KIND_FIRST) launch_main_k<KIND_FIRST, MED>(P, maps, dx, dy, dz, zchunk, rect, st, ev0, ev1, nlaunch);
   else if (kind == KIND_MID) launch_main_k<KIND_MID, MED>(P, maps, dx, dy, dz, zchunk, rect, st, ev0, ev1, nlaunch);
+  else if (kind == KIND_THIRD) launch_main_k<KIND_THIRD, MED>(P, maps, dx, dy, dz, zchunk, rect, st, ev0, ev1, nlaunch);
   else launch_main_k<KIND_LAST, MED>(P, maps, dx, dy, dz, zchunk, rect, st, ev0, ev1, nlaunch);
 }
 
@@ -481,6 +487,7 @@ template <int MED> void med_launch_top(const StageArgs &P, int dx, int dy, int d
 {
   if (kind == KIND_FIRST) launch_top_k<KIND_FIRST, MED>(P, dx, dy, dz, st, nlaunch);
   else if (kind == KIND_MID) launch_top_k<KIND_MID, MED>(P, dx, dy, dz, st, nlaunch);
+  else if (kind == KIND_THIRD) launch_top_k<KIND_THIRD, MED>(P, dx, dy, dz, st, nlaunch);
   else launch_top_k<KIND_LAST, MED>(P, dx, dy, dz, st, nlaunch);
 }
 

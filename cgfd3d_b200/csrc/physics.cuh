@@ -76,19 +76,41 @@ __device__ __forceinline__ void rk_store(float *__restrict__ tmp, float *__restr
   }
 }
 
-// the same update done in place in shared memory: sp holds w_pre (mid) and receives w_tmp, se holds w_end (mid, last)
-// and receives the new w_end; the tiles are then written out by one TMA store each
+// Wavefield update of the four RK stages with the reconstructed w_end (kinds in cgfd_dev.cuh). The reference accumulates
+// w_end += b_s dt h_s in every stage (forward/drv_rk_curv_col.c:298-300, 330-332, 354-356, 386-388, 409-411); here the
+// contributions of stages 0 and 2 are recovered one stage later from w_tmp - w_pre = a dt h, which removes one w_end write
+// and two w_end reads per point and step (27 of 192 floats). Same value up to float32 round-off of the field itself.
 template <int KIND>
-__device__ __forceinline__ void rk_smem(float *sp, float *se, float cur_c, float rhs, float a, float b)
+__device__ __forceinline__ void rk_wave(float *__restrict__ tmp, float *__restrict__ end, size_t off, float cur_c, float pre_v,
+                                        float end_v, float rhs, float a, float b, float c)
+{
+  if (KIND == KIND_FIRST) {
+    tmp[off] = cur_c + a * rhs;
+  } else if (KIND == KIND_MID) {
+    tmp[off] = pre_v + a * rhs;
+    end[off] = (pre_v + c * (cur_c - pre_v)) + b * rhs;
+  } else if (KIND == KIND_THIRD) {
+    tmp[off] = pre_v + a * rhs;
+  } else {
+    end[off] = (end_v + c * (cur_c - pre_v)) + b * rhs;
+  }
+}
+
+// the same update done in place in shared memory: sp holds w_pre (all kinds but FIRST) and receives w_tmp, se holds w_end
+// (LAST) and receives the new w_end (MID, LAST); the tiles are then written out by one TMA store each
+template <int KIND>
+__device__ __forceinline__ void rk_smem(float *sp, float *se, float cur_c, float rhs, float a, float b, float c)
 {
   if (KIND == KIND_FIRST) {
     *sp = cur_c + a * rhs;
-    *se = cur_c + b * rhs;
   } else if (KIND == KIND_MID) {
+    const float pv = *sp;
+    *sp = pv + a * rhs;
+    *se = (pv + c * (cur_c - pv)) + b * rhs;
+  } else if (KIND == KIND_THIRD) {
     *sp = *sp + a * rhs;
-    *se = *se + b * rhs;
   } else {
-    *se = *se + b * rhs;
+    *se = (*se + c * (cur_c - *sp)) + b * rhs;
   }
 }
 

@@ -15,14 +15,18 @@ prob = bench.build_rank_problem(size, 0, 1, device="cuda:0")
 S = solver.Solver(prob, device=0)
 prob.metric = prob.media = None
 torch.cuda.empty_cache()
-S.run(nsteps, it0=0)
-bad_k = []
-for k in range(prob.nz):
-    b = S.get_box(3, 0, prob.nx, 1, 0, prob.ny, 1, k, 1, 1)[0]
-    bad = ~np.isfinite(b)
-    if bad.any():
-        jj, ii = np.nonzero(bad)
-        bad_k.append((k, int(bad.sum()), int(ii.min()), int(ii.max()), int(jj.min()), int(jj.max())))
-print("size", size, "steps", nsteps, "bad planes", len(bad_k))
-for r in bad_k[:12] + bad_k[-4:]:
-    print("  k=%d nbad=%d i[%d..%d] j[%d..%d]" % r)
+for it in range(nsteps):
+    S.run(1, it0=it)
+    for comp in (2, 3):
+        bad_k = []
+        for k in list(range(0, 8)) + list(range(prob.nz - 26, prob.nz)):
+            b = S.get_box(comp, 0, prob.nx, 1, 0, prob.ny, 1, k, 1, 1)[0]
+            bad = ~np.isfinite(b)
+            if bad.any():
+                jj, ii = np.nonzero(bad)
+                bad_k.append((k, int(bad.sum()), int(ii.min()), int(ii.max()), int(jj.min()), int(jj.max())))
+        print("size", size, "after step", it, "comp", comp, "bad planes", len(bad_k), flush=True)
+        for r in bad_k[:6] + bad_k[-3:]:
+            print("  k=%d nbad=%d i[%d..%d] j[%d..%d]" % r)
+    if bad_k:
+        break

@@ -134,3 +134,34 @@ def test_box_and_pg_taps():
     # PGVz is the running max of |Vz| on the surface: at least the final value
     assert (pg[4, 3:-3, 3:-3] + 1e-30 >= np.abs(w[2, prob.nz - 4, 3:-3, 3:-3])).all()
     G.close()
+
+
+@pytest.mark.parametrize("medium", ["iso", "vti"])
+def test_interior_tiles_without_pml(medium):
+    """A block wide enough that some 32x8 tiles meet no PML slab: those run the PML-free copy of the loop body
+    (the small cases above never do). One RHS evaluation and a 30-step run against the reference."""
+    _need()
+    nt = 30
+    prob = util.small_problem(ni=100, nj=44, nk=40, pml_layers=5, nt_total=nt, seed=21, medium=medium)
+    R = ref_flat.RefSolver(prob)
+    util.fill_surface_matrices(prob, R)
+    G = solver.Solver(prob)
+    w, aux = util.random_state(prob, 77)
+    for key, a in aux.items():
+        R.set_pml_aux(key[0], key[1], a.ravel())
+        G.set_pml_aux(key[0], key[1], a.ravel())
+    for (ipair, istage) in ((0, 0), (3, 1), (6, 2)):
+        rr, rg = R.onestage(1, ipair, istage, w), G.onestage(1, ipair, istage, w)
+        bad = [(util.CMP[c], util.rel_max(rg[c], rr[c])) for c in range(9) if not util.rel_max(rg[c], rr[c]) <= TOL_STAGE]
+        assert not bad, (ipair, istage, bad)
+    G.close()
+    R = ref_flat.RefSolver(prob)
+    util.fill_surface_matrices(prob, R)
+    wr, _, _ = R.run(nt)
+    G = solver.Solver(prob)
+    G.run(nt)
+    wg = G.get_wavefield()
+    G.close()
+    assert np.isfinite(wg).all() and float(np.abs(wr[0]).max()) > 0
+    bad = [(util.CMP[c], util.rel_l2(wg[c], wr[c])) for c in range(9) if not util.rel_l2(wg[c], wr[c]) <= TOL_RUN]
+    assert not bad, bad
