@@ -17,10 +17,9 @@ enum { M_JAC = 0, M_XIX, M_XIY, M_XIZ, M_ETX, M_ETY, M_ETZ, M_ZTX, M_ZTY, M_ZTZ,
 //   MID   (stage 1): tmp = pre + a h ; end = pre + c (cur-pre) + b h   loads cur, pre       stores tmp, end
 //   THIRD (stage 2): tmp = pre + a h                                   loads cur, pre       stores tmp
 //   LAST  (stage 3): end = end + c (cur-pre) + b h                     loads cur, pre, end  stores end
-// with c = b_prev / a_prev, because cur = pre + a_prev h_prev. PML auxiliary variables and visco-elastic memory variables
-// keep the plain three-kind update (FIRST / MID / LAST; THIRD behaves like MID there).
+// with c = b_prev / a_prev, because cur = pre + a_prev h_prev. The PML auxiliary variables and the visco-elastic memory
+// variables advance the same way.
 enum { KIND_FIRST = 0, KIND_MID = 1, KIND_LAST = 2, KIND_THIRD = 3 };
-__host__ __device__ constexpr int aux_kind(int kind) { return kind == KIND_THIRD ? KIND_MID : kind; }
 
 constexpr int MAX_MEDIA = 24;
 constexpr int MAX_MAXWELL = 8;

@@ -70,8 +70,11 @@ struct TmaCtx {
   uint64_t pol_keep, pol_stream;   // L2 eviction policies (thread 0 only)
 };
 
+// Loads of one plane into ring slot s, in two parts: A = the tiles nothing is stored from (wavefield with halo, metric,
+// media; also arms the barrier with the byte count of the whole plane), B = the w_pre / w_end tiles, which double as the
+// sources of the TMA stores of the plane that used the slot before and can only be refilled once those have been read.
 template <int DX, int DY, int KIND, int MED>
-__device__ __forceinline__ void tma_issue(const StageArgs &P, const TmaMaps &M, const TmaCtx &C, int kk, int s)
+__device__ __forceinline__ void tma_issue_a(const StageArgs &P, const TmaMaps &M, const TmaCtx &C, int kk, int s)
 {
   constexpr int YL = Ofs<DY>::left;
   unsigned char *b = C.ring + s * Lay<MED>::STAGE_BYTES;
@@ -81,8 +84,20 @@ __device__ __forceinline__ void tma_issue(const StageArgs &P, const TmaMaps &M, 
   tma_load_4d_hint(b + OFF_CUR, &M.cur, bar, C.i0 - HX + P.shift, C.j0 - YL, kk, 0, C.pol_keep);
   tma_load_4d_hint(b + OFF_MET, &M.met, bar, C.i0 + P.shift, C.j0, kk, 0, C.pol_stream);
   tma_load_4d_hint(b + OFF_MED, &M.med, bar, C.i0 + P.shift, C.j0, kk, 0, C.pol_stream);
+}
+template <int DX, int DY, int KIND, int MED>
+__device__ __forceinline__ void tma_issue_b(const StageArgs &P, const TmaMaps &M, const TmaCtx &C, int kk, int s)
+{
+  unsigned char *b = C.ring + s * Lay<MED>::STAGE_BYTES;
+  uint64_t *bar = C.full + s;
   if (KIND != KIND_FIRST) tma_load_4d_hint(b + OFF_PRE, &M.pre, bar, C.i0 + P.shift, C.j0, kk, 0, C.pol_stream);
   if (KIND == KIND_LAST) tma_load_4d_hint(b + OFF_END, &M.end, bar, C.i0 + P.shift, C.j0, kk, 0, C.pol_stream);
+}
+template <int DX, int DY, int KIND, int MED>
+__device__ __forceinline__ void tma_issue(const StageArgs &P, const TmaMaps &M, const TmaCtx &C, int kk, int s)
+{
+  tma_issue_a<DX, DY, KIND, MED>(P, M, C, kk, s);
+  tma_issue_b<DX, DY, KIND, MED>(P, M, C, kk, s);
 }
 
 // One plane. The march along z runs TOWARDS the short side of the one-sided zeta operator (upwards for
@@ -136,8 +151,8 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
                   : cz[0] * q4[c] + cz[1] * q3[c] + cz[2] * q2[c] + cz[3] * q1[c] + cz[4] * q0[c];
     }
     hooke<MED>(d, m, md, h);
-    if (PML) pml_all<aux_kind(KIND), 0, MED>(P, C.i, C.j, k, d, m, md, h);
-    if constexpr (MED == MED_VIS) atten_update<aux_kind(KIND)>(P, (size_t)k * P.siz_slice + C.pij, md.lam, md.mu, h);
+    if (PML) pml_all<KIND, 0, MED>(P, C.i, C.j, k, d, m, md, h);
+    if constexpr (MED == MED_VIS) atten_update<KIND>(P, (size_t)k * P.siz_slice + C.pij, md.lam, md.mu, h);
 #pragma unroll
     for (int c = 3; c < 9; c++) rk_smem<KIND>(sp + c * NT, se + c * NT, qz[c], h[c], P.a, P.b, P.c);
     // ---- velocity half: needs the stress derivatives only
@@ -150,7 +165,7 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
                   : cz[0] * q4[c] + cz[1] * q3[c] + cz[2] * q2[c] + cz[3] * q1[c] + cz[4] * q0[c];
     }
     momentum(d, m, slw, h);
-    if (PML) pml_all<aux_kind(KIND), 1, MED>(P, C.i, C.j, k, d, m, md, h);
+    if (PML) pml_all<KIND, 1, MED>(P, C.i, C.j, k, d, m, md, h);
 #pragma unroll
     for (int c = 0; c < 3; c++) rk_smem<KIND>(sp + c * NT, se + c * NT, qz[c], h[c], P.a, P.b, P.c);
     fence_proxy_async_smem();   // the results written above are read by the TMA store below
@@ -158,13 +173,17 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
   __syncthreads();   // every thread is done with ring slot s; its PRE / END tiles now hold w_tmp / w_end of this plane
   if (C.t == 0) {
     const int tx0 = C.i0 - P.ni1, ty0 = C.j0 - P.nj1;
+    const bool refill = it + NST < nplanes;
+    if (refill) tma_issue_a<DX, DY, KIND, MED>(P, M, C, k + NST * DIR, s);   // most of the next plane's bytes: requested at once
     if (KIND != KIND_LAST) tma_store_4d_hint(&M.out_tmp, b + OFF_PRE, tx0, ty0, k, 0, C.pol_stream);
     if (KIND == KIND_MID || KIND == KIND_LAST) tma_store_4d_hint(&M.out_end, b + OFF_END, tx0, ty0, k, 0, C.pol_stream);
     tma_store_commit();
     if (P.l2mode & 8) tma_store_wait_all();   // debugging switch: synchronous stores
-    if (it + NST < nplanes) {
-      tma_store_wait_read();   // the slot may be refilled once the stores have read it
-      tma_issue<DX, DY, KIND, MED>(P, M, C, k + NST * DIR, s);
+    if (refill) {
+      // the w_pre / w_end tiles may be refilled -- or, two planes on, overwritten by the threads -- once the stores have read
+      // them: thread 0 passes this wait before it joins the next __syncthreads
+      tma_store_wait_read();
+      tma_issue_b<DX, DY, KIND, MED>(P, M, C, k + NST * DIR, s);
     }
   }
 }
@@ -244,8 +263,9 @@ __global__ void __launch_bounds__(TX *TY, Lay<MED>::BLOCKS) k_main_tma(const Sta
 template <int DX, int DY, int DZ, int KIND, int MED>
 __global__ void __launch_bounds__(128, 3) k_top(const StageArgs P)
 {
-  const int i = P.ni1 + blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = P.nj1 + blockIdx.y;
+  // 32 x 4 points per block: the eta neighbours of a row are mostly rows of the same block (L1 hits)
+  const int i = P.ni1 + blockIdx.x * 32 + threadIdx.x;
+  const int j = P.nj1 + blockIdx.y * 4 + threadIdx.y;
   const int k = P.kbeg + blockIdx.z;
   if (i > P.ni2 || j > P.nj2 || k > P.kend) return;
   const size_t L = P.siz_line, S = P.siz_slice, V = P.siz_vol;
@@ -384,9 +404,9 @@ __global__ void __launch_bounds__(128, 3) k_top(const StageArgs P)
     }
   }
 
-  pml_all<aux_kind(KIND), 0, MED>(P, i, j, k, d, m, md, h);
-  pml_all<aux_kind(KIND), 1, MED>(P, i, j, k, d, m, md, h);
-  if constexpr (MED == MED_VIS) atten_update<aux_kind(KIND)>(P, p, md.lam, md.mu, h);
+  pml_all<KIND, 0, MED>(P, i, j, k, d, m, md, h);
+  pml_all<KIND, 1, MED>(P, i, j, k, d, m, md, h);
+  if constexpr (MED == MED_VIS) atten_update<KIND>(P, p, md.lam, md.mu, h);
 #pragma unroll
   for (int c = 0; c < 9; c++) rk_wave<KIND>(P.tmp, P.end, c * V + p, cur[c], pv[c], ev[c], h[c], P.a, P.b, P.c);
 }
@@ -429,7 +449,7 @@ static void launch_top_t(const StageArgs &P0, cudaStream_t st, int *nlaunch)
   const int ni = P.ni2 - P.ni1 + 1, nj = P.nj2 - P.nj1 + 1;
   const int ktop = P.nk2 - 3;
   P.kbeg = (ktop < P.nk1) ? P.nk1 : ktop; P.kend = P.nk2;
-  dim3 block(128), grid((ni + 127) / 128, nj, P.kend - P.kbeg + 1);
+  dim3 block(32, 4), grid((ni + 31) / 32, (nj + 3) / 4, P.kend - P.kbeg + 1);
   k_top<DX, DY, DZ, KIND, MED><<<grid, block, 0, st>>>(P);
   (*nlaunch)++;
 }

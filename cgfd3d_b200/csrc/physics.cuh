@@ -55,27 +55,6 @@ __device__ __forceinline__ void hooke_iso(const Deriv &d, const Met &m, float la
   h[TYZ] = mu * (m.xiz * d.x[VY] + m.xiy * d.x[VZ] + m.etz * d.y[VY] + m.ety * d.y[VZ] + m.ztz * d.z[VY] + m.zty * d.z[VZ]);
 }
 
-// Runge-Kutta stage update fused into the RHS epilogue (forward/drv_rk_curv_col.c:292-446):
-//   first : tmp = pre + a*rhs ; end  = pre + b*rhs      (w_cur == w_pre, its value is `cur_c`)
-//   mid   : tmp = pre + a*rhs ; end += b*rhs
-//   last  :                     end += b*rhs
-// pre_v / end_v are the values of w_pre / w_end at this point, fetched by the caller ahead of time
-// (first: both unused; last: pre_v unused).
-template <int KIND>
-__device__ __forceinline__ void rk_store(float *__restrict__ tmp, float *__restrict__ end, size_t off, float cur_c,
-                                         float pre_v, float end_v, float rhs, float a, float b)
-{
-  if (KIND == KIND_FIRST) {
-    tmp[off] = cur_c + a * rhs;
-    end[off] = cur_c + b * rhs;
-  } else if (KIND == KIND_MID) {
-    tmp[off] = pre_v + a * rhs;
-    end[off] = end_v + b * rhs;
-  } else {
-    end[off] = end_v + b * rhs;
-  }
-}
-
 // Wavefield update of the four RK stages with the reconstructed w_end (kinds in cgfd_dev.cuh). The reference accumulates
 // w_end += b_s dt h_s in every stage (forward/drv_rk_curv_col.c:298-300, 330-332, 354-356, 386-388, 409-411); here the
 // contributions of stages 0 and 2 are recovered one stage later from w_tmp - w_pre = a dt h, which removes one w_end write
@@ -248,8 +227,8 @@ __device__ __forceinline__ void pml_face(const StageArgs &P, const PmlFaceDev &F
   for (int c = C0; c < C1; c++) {
     const size_t o = c * F.siz + pa;
     au[c] = __ldg(F.aux_cur + o);
-    if (KIND == KIND_MID) pv[c] = __ldg(F.aux_pre + o);
-    if (KIND != KIND_FIRST) ev[c] = F.aux_end[o];
+    if (KIND != KIND_FIRST) pv[c] = __ldg(F.aux_pre + o);
+    if (KIND == KIND_LAST) ev[c] = F.aux_end[o];
   }
   float r[9];
   if (PART) {
@@ -288,19 +267,9 @@ __device__ __forceinline__ void pml_face(const StageArgs &P, const PmlFaceDev &F
       ar[c] += cD * q[c];
     }
   }
+  // the auxiliary variables advance with the same four-kind update as the wavefield (rk_wave)
 #pragma unroll
-  for (int c = C0; c < C1; c++) {
-    const size_t o = c * F.siz + pa;
-    if (KIND == KIND_FIRST) {
-      F.aux_tmp[o] = au[c] + P.a * ar[c];
-      F.aux_end[o] = au[c] + P.b * ar[c];
-    } else if (KIND == KIND_MID) {
-      F.aux_tmp[o] = pv[c] + P.a * ar[c];
-      F.aux_end[o] = ev[c] + P.b * ar[c];
-    } else {
-      F.aux_end[o] = ev[c] + P.b * ar[c];
-    }
-  }
+  for (int c = C0; c < C1; c++) rk_wave<KIND>(F.aux_tmp, F.aux_end, c * F.siz + pa, au[c], pv[c], ev[c], ar[c], P.a, P.b, P.c);
 }
 
 // all PML faces a point belongs to, in the reference's face order x1,x2,y1,y2,z1,z2
@@ -353,9 +322,9 @@ __device__ __forceinline__ void atten_update(const StageArgs &P, size_t p, float
       sum[q] += ymu * J[q];
       const float hJ = wl * (EV[q] - J[q]);
       const size_t o = (size_t)(9 + 6 * n + q) * P.siz_vol + p;
-      const float pv = (KIND == KIND_MID) ? __ldg(P.pre + o) : 0.0f;
-      const float ev = (KIND != KIND_FIRST) ? P.end[o] : 0.0f;
-      rk_store<KIND>(P.tmp, P.end, o, J[q], pv, ev, hJ, P.a, P.b);
+      const float pv = (KIND != KIND_FIRST) ? __ldg(P.pre + o) : 0.0f;
+      const float ev = (KIND == KIND_LAST) ? P.end[o] : 0.0f;
+      rk_wave<KIND>(P.tmp, P.end, o, J[q], pv, ev, hJ, P.a, P.b, P.c);
     }
   }
   h[TXX] -= lam * sum_tr + 2.0f * mu * sum[0];
