@@ -486,7 +486,7 @@ extern "C" int cgfd_b200_create(const cgfd_problem_t *p, int device, cgfd_b200_c
     if (2 * (f.nlay + 1) > ext) { cgfd_b200_destroy(c); return fail("cgfd_b200_create: PML slabs of opposite faces overlap"); }
     h.siz = (size_t)(r[1] - r[0] + 1) * (r[3] - r[2] + 1) * (r[5] - r[4] + 1);
     rc |= upload(c, &h.A, f.A, f.nlay + 1); rc |= upload(c, &h.B, f.B, f.nlay + 1); rc |= upload(c, &h.D, f.D, f.nlay + 1);
-    for (int l = 0; l < 4; l++) rc |= upload(c, &h.aux[l], (const float *)nullptr, h.siz * 9);
+    for (int l = 0; l < 4; l++) rc |= upload(c, &h.aux[l], (const float *)nullptr, h.siz * AUX_REC);
   }
   if (c->free_top) {
     if (!p->matVx2Vz || !p->matVy2Vz || !p->matF2Vz) { cgfd_b200_destroy(c); return fail("cgfd_b200_create: free surface needs matVx2Vz/matVy2Vz/matF2Vz"); }
@@ -542,34 +542,46 @@ extern "C" int cgfd_b200_get_wavefield(cgfd_b200_ctx *c, float *w)
   return 0;
 }
 extern "C" size_t cgfd_b200_pml_aux_size(cgfd_b200_ctx *c, int idim, int is) { return c->pml[idim][is].on ? c->pml[idim][is].siz * 9 : 0; }
+// host [9][slab] (the reference's bdrypml_auxvar_t order, forward/bdry_t.c:300-306) <-> device [slab][AUX_REC] records
+static int aux_to_device(cgfd_b200_ctx *c, PmlFaceHost &h, float *dev, const float *host)
+{
+  std::vector<float> rec(h.siz * AUX_REC, 0.0f);
+  for (int cmp = 0; cmp < 9; cmp++)
+    for (size_t n = 0; n < h.siz; n++) rec[n * AUX_REC + aux_slot(cmp)] = host[(size_t)cmp * h.siz + n];
+  CK(cudaMemcpyAsync(dev, rec.data(), rec.size() * sizeof(float), cudaMemcpyHostToDevice, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  return 0;
+}
+static int aux_to_host(cgfd_b200_ctx *c, PmlFaceHost &h, float *host, const float *dev)
+{
+  std::vector<float> rec(h.siz * AUX_REC);
+  CK(cudaStreamSynchronize(c->st));
+  CK(cudaMemcpyAsync(rec.data(), dev, rec.size() * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  for (int cmp = 0; cmp < 9; cmp++)
+    for (size_t n = 0; n < h.siz; n++) host[(size_t)cmp * h.siz + n] = rec[n * AUX_REC + aux_slot(cmp)];
+  return 0;
+}
 extern "C" int cgfd_b200_set_pml_aux(cgfd_b200_ctx *c, int idim, int is, const float *aux)
 {
   PmlFaceHost &h = c->pml[idim][is];
   if (!h.on) return fail("set_pml_aux: face has no PML");
   CK(cudaSetDevice(c->device));
-  CK(cudaMemcpyAsync(h.aux[c->ipre], aux, h.siz * 9 * sizeof(float), cudaMemcpyHostToDevice, c->st));
-  CK(cudaStreamSynchronize(c->st));
-  return 0;
+  return aux_to_device(c, h, h.aux[c->ipre], aux);
 }
 extern "C" int cgfd_b200_get_pml_aux(cgfd_b200_ctx *c, int idim, int is, float *aux)
 {
   PmlFaceHost &h = c->pml[idim][is];
   if (!h.on) return fail("get_pml_aux: face has no PML");
   CK(cudaSetDevice(c->device));
-  CK(cudaStreamSynchronize(c->st));
-  CK(cudaMemcpyAsync(aux, h.aux[c->ipre], h.siz * 9 * sizeof(float), cudaMemcpyDeviceToHost, c->st));
-  CK(cudaStreamSynchronize(c->st));
-  return 0;
+  return aux_to_host(c, h, aux, h.aux[c->ipre]);
 }
 extern "C" int cgfd_b200_get_pml_aux_rhs(cgfd_b200_ctx *c, int idim, int is, float *aux)
 {
   PmlFaceHost &h = c->pml[idim][is];
   if (!h.on) return fail("get_pml_aux_rhs: face has no PML");
   CK(cudaSetDevice(c->device));
-  CK(cudaStreamSynchronize(c->st));
-  CK(cudaMemcpyAsync(aux, h.aux[c->ib], h.siz * 9 * sizeof(float), cudaMemcpyDeviceToHost, c->st));
-  CK(cudaStreamSynchronize(c->st));
-  return 0;
+  return aux_to_host(c, h, aux, h.aux[c->ib]);
 }
 
 // ---- one RK stage -----------------------------------------------------------------------------
@@ -781,8 +793,8 @@ extern "C" int cgfd_b200_onestage(cgfd_b200_ctx *c, int it, int ipair, int istag
   for (int idim = 0; idim < 3; idim++) for (int is = 0; is < 2; is++) {
     PmlFaceHost &h = c->pml[idim][is];
     if (!h.on) continue;
-    const size_t ab = h.siz * 9 * sizeof(float);
-    if (!h.zero) { if (upload(c, &h.zero, (const float *)nullptr, h.siz * 9)) return 1; }
+    const size_t ab = h.siz * AUX_REC * sizeof(float);
+    if (!h.zero) { if (upload(c, &h.zero, (const float *)nullptr, h.siz * AUX_REC)) return 1; }
     CK(cudaMemcpyAsync(h.aux[icur], h.aux[c->ipre], ab, cudaMemcpyDeviceToDevice, c->st));
     CK(cudaMemsetAsync(h.aux[iout], 0, ab, c->st));
     CK(cudaMemsetAsync(h.aux[izero], 0, ab, c->st));

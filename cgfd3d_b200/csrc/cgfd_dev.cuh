@@ -34,13 +34,20 @@ struct FdConst {
 };
 extern __constant__ FdConst c_fd;
 
+// PML auxiliary variables live as one record of AUX_REC floats per slab point and level:
+//   [Txx Tyy Tzz Tyz Txz Txy | Vx Vy Vz | pad]   (the stress part first: it is read first)
+// so that a point's variables come with three 8-byte loads + one 8-byte and one 4-byte load instead of nine scalar
+// loads from nine different cache lines. aux_slot(c) = position of wavefield component c inside the record.
+constexpr int AUX_REC = 10;
+__host__ __device__ constexpr int aux_slot(int c) { return c >= 3 ? c - 3 : 6 + c; }
+
 struct PmlFaceDev {
   int on;
   int i1, i2, j1, j2, k1, k2;   // slab range, inclusive (forward/bdry_t.c:161-186)
   int sni, snj;                 // slab extents in i and j
-  size_t siz;                   // slab points per component
+  size_t siz;                   // slab points
   const float *A, *B, *D;       // [nlay+1] device
-  const float *aux_cur;         // level read by this stage
+  const float *aux_cur;         // level read by this stage; every level is [slab point][AUX_REC]
   const float *aux_pre;         // level n
   float *aux_tmp;               // level written for the next stage
   float *aux_end;               // accumulating level n+1
@@ -99,6 +106,13 @@ void med_launch_main(const StageArgs &P, const TmaMaps *maps, int dx, int dy, in
                      cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1, int *nlaunch);
 // the four free-surface rows, whole x-y range (no-op without a free top)
 template <int MED> void med_launch_top(const StageArgs &P, int dx, int dy, int dz, int kind, cudaStream_t st, int *nlaunch);
-constexpr int TILE_X = 32, TILE_Y = 8, HALO_X = 4;
+// tile of the interior kernel (one thread per column); overridable at build time for tile-shape experiments
+#ifndef CGFD_TILE_X
+#define CGFD_TILE_X 32
+#endif
+#ifndef CGFD_TILE_Y
+#define CGFD_TILE_Y 8
+#endif
+constexpr int TILE_X = CGFD_TILE_X, TILE_Y = CGFD_TILE_Y, HALO_X = 4;
 
 }  // namespace cgfd

@@ -52,7 +52,9 @@ template <int MED> struct Lay {   // the media tiles come last: their number dep
   static constexpr int STAGE_BYTES = OFF_MED + NMT * CEN_BYTES;
   static constexpr int SMEM_BYTES = NST * STAGE_BYTES + 128 /*alignment slack*/ + 64 /*barriers*/;
   // blocks per SM the shared memory allows (227 KB usable, 1 KB reserved per block)
-  static constexpr int BLOCKS = (2 * (SMEM_BYTES + 1024) <= 233472) ? 2 : 1;
+  static constexpr int BY_SMEM = 233472 / (SMEM_BYTES + 1024);
+  static constexpr int BY_REGS = 65536 / (TILE_X * TILE_Y * 128);   // 128 registers per thread
+  static constexpr int BLOCKS = BY_SMEM < BY_REGS ? (BY_SMEM < 1 ? 1 : BY_SMEM) : BY_REGS;
 };
 
 template <int KIND, int MED> __device__ __forceinline__ constexpr uint32_t stage_tx_bytes()
@@ -123,6 +125,7 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
 #pragma unroll
     for (int c = 0; c < 9; c++) qn[c] = __ldg(w + c * P.siz_vol);
   }
+  if (PML && C.active && it + 1 < nplanes) pml_prefetch<KIND>(P, C.i, C.j, k + DIR);
   unsigned char *b = C.ring + s * Lay<MED>::STAGE_BYTES;
   mbar_wait(C.full + s, parity);
   if (C.active) {

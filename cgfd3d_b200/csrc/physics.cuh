@@ -209,11 +209,31 @@ __device__ __forceinline__ void stress_one_axis(const float *D_, float e1, float
 // PART 0 handles the 6 stress components (needs the velocity derivatives along the normal),
 // PART 1 the 3 velocity components (needs the stress derivatives), so that a caller can finish one
 // half of the RHS before it forms the other.
+// n consecutive floats of an aux record (8-byte aligned: n = 6 -> three float2, n = 3 -> float2 + float)
+template <int N> __device__ __forceinline__ void aux_load(const float *p, float *v)
+{
+  if (N == 6) {
+    const float2 a = __ldg((const float2 *)p), b = __ldg((const float2 *)p + 1), c = __ldg((const float2 *)p + 2);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y;
+  } else {
+    const float2 a = __ldg((const float2 *)p);
+    v[0] = a.x; v[1] = a.y; v[2] = __ldg(p + 2);
+  }
+}
+template <int N> __device__ __forceinline__ void aux_store(float *p, const float *v)
+{
+  if (N == 6) {
+    ((float2 *)p)[0] = make_float2(v[0], v[1]); ((float2 *)p)[1] = make_float2(v[2], v[3]); ((float2 *)p)[2] = make_float2(v[4], v[5]);
+  } else {
+    ((float2 *)p)[0] = make_float2(v[0], v[1]); p[2] = v[2];
+  }
+}
+
 template <int AXIS, int KIND, int PART, int MED>
 __device__ __forceinline__ void pml_face(const StageArgs &P, const PmlFaceDev &F, int i, int j, int k,
                                          const Deriv &d, const Met &m, const Med<MED> &M, float *h)
 {
-  constexpr int C0 = PART ? 0 : 3, C1 = PART ? 3 : 9;
+  constexpr int C0 = PART ? 0 : 3, N = PART ? 3 : 6;   // wavefield components C0 .. C0+N-1 = record slots aux_slot(C0) ..
   const int ia = (AXIS == 0) ? (i - F.i1) : (AXIS == 1) ? (j - F.j1) : (k - F.k1);
   const float cA = __ldg(F.A + ia), cB = __ldg(F.B + ia), cD = __ldg(F.D + ia);
   const float cB1 = cB - 1.0f;
@@ -221,15 +241,11 @@ __device__ __forceinline__ void pml_face(const StageArgs &P, const PmlFaceDev &F
   const float e1 = (AXIS == 0) ? m.xix : (AXIS == 1) ? m.etx : m.ztx;
   const float e2 = (AXIS == 0) ? m.xiy : (AXIS == 1) ? m.ety : m.zty;
   const float e3 = (AXIS == 0) ? m.xiz : (AXIS == 1) ? m.etz : m.ztz;
-  const size_t pa = ((size_t)(k - F.k1) * F.snj + (size_t)(j - F.j1)) * F.sni + (size_t)(i - F.i1);
-  float au[9], pv[9], ev[9];
-#pragma unroll
-  for (int c = C0; c < C1; c++) {
-    const size_t o = c * F.siz + pa;
-    au[c] = __ldg(F.aux_cur + o);
-    if (KIND != KIND_FIRST) pv[c] = __ldg(F.aux_pre + o);
-    if (KIND == KIND_LAST) ev[c] = F.aux_end[o];
-  }
+  const size_t pa = (((size_t)(k - F.k1) * F.snj + (size_t)(j - F.j1)) * F.sni + (size_t)(i - F.i1)) * AUX_REC + aux_slot(C0);
+  float au[N], pv[N], ev[N];
+  aux_load<N>(F.aux_cur + pa, au);
+  if (KIND != KIND_FIRST) aux_load<N>(F.aux_pre + pa, pv);
+  if (KIND == KIND_LAST) aux_load<N>(F.aux_end + pa, ev);
   float r[9];
   if (PART) {
     r[VX] = M.slw * (e1 * D_[TXX] + e2 * D_[TXY] + e3 * D_[TXZ]);
@@ -238,11 +254,11 @@ __device__ __forceinline__ void pml_face(const StageArgs &P, const PmlFaceDev &F
   } else {
     stress_one_axis<MED>(D_, e1, e2, e3, M, r);
   }
-  float ar[9];
+  float ar[N];
 #pragma unroll
-  for (int c = C0; c < C1; c++) {
-    h[c] += cB1 * r[c] - cB * au[c];
-    ar[c] = cD * r[c] - cA * au[c];
+  for (int n = 0; n < N; n++) {
+    h[C0 + n] += cB1 * r[C0 + n] - cB * au[n];
+    ar[n] = cD * r[C0 + n] - cA * au[n];
   }
   if (PART == 0 && AXIS < 2 && P.free_top && k == P.nk2) {
     const float *Mt = ((AXIS == 0) ? P.matVx2Vz : P.matVy2Vz) + ((size_t)j * P.nx + i) * 9;
@@ -261,15 +277,43 @@ __device__ __forceinline__ void pml_face(const StageArgs &P, const PmlFaceDev &F
     } else {
       stress_one_axis<MED>(z, m.ztx, m.zty, m.ztz, M, q);
     }
+    if (PART == 0) {
 #pragma unroll
-    for (int c = 3; c < 9; c++) {
-      h[c] += cB1 * q[c];
-      ar[c] += cD * q[c];
+      for (int n = 0; n < N; n++) {
+        h[C0 + n] += cB1 * q[C0 + n];
+        ar[n] += cD * q[C0 + n];
+      }
     }
   }
   // the auxiliary variables advance with the same four-kind update as the wavefield (rk_wave)
+  float vt[N], ve[N];
 #pragma unroll
-  for (int c = C0; c < C1; c++) rk_wave<KIND>(F.aux_tmp, F.aux_end, c * F.siz + pa, au[c], pv[c], ev[c], ar[c], P.a, P.b, P.c);
+  for (int n = 0; n < N; n++) {
+    if (KIND == KIND_FIRST) vt[n] = au[n] + P.a * ar[n];
+    else if (KIND == KIND_MID) { vt[n] = pv[n] + P.a * ar[n]; ve[n] = (pv[n] + P.c * (au[n] - pv[n])) + P.b * ar[n]; }
+    else if (KIND == KIND_THIRD) vt[n] = pv[n] + P.a * ar[n];
+    else ve[n] = (ev[n] + P.c * (au[n] - pv[n])) + P.b * ar[n];
+  }
+  if (KIND != KIND_LAST) aux_store<N>(F.aux_tmp + pa, vt);
+  if (KIND == KIND_MID || KIND == KIND_LAST) aux_store<N>(F.aux_end + pa, ve);
+}
+
+// the aux records plane k of the march will read, requested into L2 one plane ahead (no registers held; the loads of
+// pml_face then see L2 latency instead of DRAM latency)
+template <int KIND> __device__ __forceinline__ void pml_prefetch(const StageArgs &P, int i, int j, int k)
+{
+#pragma unroll
+  for (int ax = 0; ax < 3; ax++) {
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+      const PmlFaceDev &F = P.pml[ax][s];
+      if (!F.on || i < F.i1 || i > F.i2 || j < F.j1 || j > F.j2 || k < F.k1 || k > F.k2) continue;
+      const size_t pa = (((size_t)(k - F.k1) * F.snj + (size_t)(j - F.j1)) * F.sni + (size_t)(i - F.i1)) * AUX_REC;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(F.aux_cur + pa));
+      if (KIND != KIND_FIRST) asm volatile("prefetch.global.L2 [%0];" ::"l"(F.aux_pre + pa));
+      if (KIND == KIND_LAST) asm volatile("prefetch.global.L2 [%0];" ::"l"(F.aux_end + pa));
+    }
+  }
 }
 
 // all PML faces a point belongs to, in the reference's face order x1,x2,y1,y2,z1,z2

@@ -14,7 +14,8 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcgfd3d_b200.so")
+# CGFD_LIB selects another in-tree build of the same library (tile-shape experiments, scripts/gpu_tiles.sh)
+LIB_PATH = os.environ.get("CGFD_LIB") or os.path.join(_HERE, "libcgfd3d_b200.so")
 
 SYMBOLS = [
     "cgfd_b200_last_error", "cgfd_b200_abi_version", "cgfd_b200_sizeof_problem", "cgfd_b200_device_count", "cgfd_b200_create", "cgfd_b200_destroy",
