@@ -27,6 +27,8 @@ NUM_STAGES = 4
 NUM_METRIC = 10
 
 VX, VY, VZ, TXX, TYY, TZZ, TYZ, TXZ, TXY = range(9)
+# metric array order of cgfd_problem_t.metric (forward/gd_t.c:101-180)
+M_JAC, M_XIX, M_XIY, M_XIZ, M_ETX, M_ETY, M_ETZ, M_ZTX, M_ZTY, M_ZTZ = range(10)
 CMP_NAMES = ["Vx", "Vy", "Vz", "Txx", "Tyy", "Tzz", "Tyz", "Txz", "Txy"]
 JAC, XI_X, XI_Y, XI_Z, ET_X, ET_Y, ET_Z, ZT_X, ZT_Y, ZT_Z = range(10)
 

@@ -42,10 +42,10 @@ static int kernels_init(int med)
 #undef CALL
   return rc;
 }
-static void launch_main(int med, const StageArgs &P, const TmaMaps *maps, const int *dir, int kind, int zchunk, const int rect[4],
+static void launch_main(int med, const StageArgs &P, const TmaMaps *maps, const int *dir, int kind, int gz, int zchunk, const int rect[4],
                         cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, int *nl)
 {
-#define CALL(M) med_launch_main<M>(P, maps, dir[0], dir[1], dir[2], kind, zchunk, rect, st, e0, e1, nl)
+#define CALL(M) med_launch_main<M>(P, maps, dir[0], dir[1], dir[2], kind, gz, zchunk, rect, st, e0, e1, nl)
   MED_SWITCH(med, CALL)
 #undef CALL
 }
@@ -73,6 +73,19 @@ struct PmlFaceHost {
   float *zero = nullptr;
 };
 
+// one snapshot / slice output (iosnap_t / ioslice_t, forward/io_funcs.c:640-760): a strided sub-box of a few components,
+// packed on the device every `tinv` steps from step `it1` on and copied to the caller's host buffer on the I/O stream
+constexpr int SNAP_RING = 4;
+struct SnapTap {
+  int ncmp = 0; int cmps[32];
+  int box[9];                    // i1, ni, di, j1, nj, dj, k1, nk, dk (local indices incl. ghosts)
+  int it1 = 0, tinv = 1, max_frames = 0, nframes = 0;
+  size_t cmp_elems = 0;          // ni*nj*nk
+  float *host = nullptr;         // [max_frames][ncmp][nk][nj][ni]
+  float *ring[SNAP_RING];
+  cudaEvent_t packed[SNAP_RING], copied[SNAP_RING];
+};
+
 struct cgfd_b200_ctx {
   int device = 0;
   cudaStream_t st = nullptr;        // compute stream
@@ -93,7 +106,8 @@ struct cgfd_b200_ctx {
   size_t hV = 0, hslice = 0;        // host (unpadded) volume / slice
   float *lev[4] = {nullptr, nullptr, nullptr, nullptr};   // bases (unshifted)
   float *metric_blk = nullptr, *media_blk = nullptr;
-  CUtensorMap map_halo[4], map_cen[4], map_out[4], map_met, map_med;
+  CUtensorMap map_halo[4], map_cen[4], map_out[4], map_met, map_met5, map_med;
+  int gz = 0;                       // xi_y = xi_z = eta_x = eta_z == 0 at every physical point: GZ kernels (cgfd_dev.cuh)
   bool have_maps = false;
   int zchunk = 0;
   int ipre = 0, ia = 1, ib = 2, iend = 3;   // roles of the four level buffers
@@ -112,6 +126,11 @@ struct cgfd_b200_ctx {
   int nrec = 0, rec_max_nt = 0, rec_count = 0; int64_t *rec_iptr = nullptr; float *rec = nullptr;
   float *PG = nullptr, *Dis = nullptr;
   float *boxbuf = nullptr; size_t boxcap = 0;
+  // host <-> device traffic that must not stall the stage pipeline runs on its own stream
+  cudaStream_t st_io = nullptr;
+  float *stage[2] = {nullptr, nullptr};            // one unpadded component each (set / get_wavefield)
+  cudaEvent_t stage_full[2] = {nullptr, nullptr}, stage_free[2] = {nullptr, nullptr};
+  std::vector<struct SnapTap *> snaps;
   // measurement
   int profiling = 0;
   std::vector<cudaEvent_t> ev;   // pairs around the main kernel
@@ -429,6 +448,11 @@ extern "C" int cgfd_b200_create(const cgfd_problem_t *p, int device, cgfd_b200_c
     CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     CK(cudaStreamCreateWithPriority(&c->st, cudaStreamNonBlocking, lo));
     CK(cudaStreamCreateWithPriority(&c->st2, cudaStreamNonBlocking, hi));
+    CK(cudaStreamCreateWithFlags(&c->st_io, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; b++) {
+      CK(cudaEventCreateWithFlags(&c->stage_full[b], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&c->stage_free[b], cudaEventDisableTiming));
+    }
     CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   }
@@ -449,9 +473,10 @@ extern "C" int cgfd_b200_create(const cgfd_problem_t *p, int device, cgfd_b200_c
   rc |= upload(c, &c->metric_blk, (const float *)nullptr, c->V * NMETRIC);
   rc |= upload(c, &c->media_blk, (const float *)nullptr, c->V * p->nmedia);
   if (rc) { cgfd_b200_destroy(c); return 1; }
-  for (int m = 0; m < NMETRIC; m++) {
-    c->metric[m] = c->metric_blk + (size_t)m * c->V + c->shift;
-    rc |= copy_in3d(c, c->metric_blk + (size_t)m * c->V, p->metric[m], 1, c->st);
+  for (int m = 0; m < NMETRIC; m++) {   // device order: metric_dev_slot (cgfd_dev.cuh)
+    float *base = c->metric_blk + (size_t)metric_dev_slot(m) * c->V;
+    c->metric[m] = base + c->shift;
+    rc |= copy_in3d(c, base, p->metric[m], 1, c->st);
   }
   for (int m = 0; m < p->nmedia; m++) {
     c->media[m] = c->media_blk + (size_t)m * c->V + c->shift;
@@ -459,6 +484,22 @@ extern "C" int cgfd_b200_create(const cgfd_problem_t *p, int device, cgfd_b200_c
   }
   CK(cudaStreamSynchronize(c->st));
   if (rc) { cgfd_b200_destroy(c); return 1; }
+  // grid class: do the four metric arrays that vanish on a vertically deformed grid vanish here? (physical points only:
+  // the interior kernel uses the metric point-wise; the free-surface kernel stays general)
+  {
+    int *flag = nullptr;
+    if (upload(c, &flag, (const int *)nullptr, 1)) { cgfd_b200_destroy(c); return 1; }
+    const int zero_arrays[4] = {M_XIY, M_XIZ, M_ETX, M_ETZ};
+    for (int n = 0; n < 4; n++) {
+      dim3 blk(128), grd((g.ni2 - g.ni1 + 128) / 128, g.nj2 - g.nj1 + 1, g.nk2 - g.nk1 + 1);
+      k_any_nonzero<<<grd, blk, 0, c->st>>>(c->metric[zero_arrays[n]], c->PX, g.ny, g.ni1, g.ni2, g.nj1, g.nk1, flag);
+    }
+    int hflag = 1;
+    CK(cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    c->gz = (hflag == 0);
+    if (const char *e = getenv("CGFD_GZ")) { if (atoi(e) == 0) c->gz = 0; }
+  }
   // tensor maps of the TMA kernel
   {
     int mrc = 0;
@@ -468,6 +509,7 @@ extern "C" int cgfd_b200_create(const cgfd_problem_t *p, int device, cgfd_b200_c
       mrc |= make_map(c, &c->map_out[l], c->lev[l], c->ncmp, TILE_X, TILE_Y, 9, true);
     }
     if (!mrc) mrc |= make_map(c, &c->map_met, c->metric_blk + c->V /* skip jac */, 9, TILE_X, TILE_Y, 9);
+    if (!mrc) mrc |= make_map(c, &c->map_met5, c->metric_blk + c->V, 9, TILE_X, TILE_Y, 5);
     const int ntile = (med == MED_ISO || med == MED_VIS) ? 3 : p->nmedia;   // media arrays staged per plane (Med<MED>::NTILE)
     if (!mrc) mrc |= make_map(c, &c->map_med, c->media_blk, p->nmedia, TILE_X, TILE_Y, ntile);
     c->have_maps = (mrc == 0);
@@ -522,23 +564,71 @@ extern "C" void cgfd_b200_destroy(cgfd_b200_ctx *c)
   if (c->run1) cudaEventDestroy(c->run1);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
+  for (SnapTap *t : c->snaps) {
+    for (int r = 0; r < SNAP_RING; r++) { cudaFree(t->ring[r]); cudaEventDestroy(t->packed[r]); cudaEventDestroy(t->copied[r]); }
+    delete t;
+  }
+  for (int b = 0; b < 2; b++) {
+    if (c->stage[b]) cudaFree(c->stage[b]);
+    if (c->stage_full[b]) cudaEventDestroy(c->stage_full[b]);
+    if (c->stage_free[b]) cudaEventDestroy(c->stage_free[b]);
+  }
+  if (c->st_io) cudaStreamDestroy(c->st_io);
   if (c->st2) cudaStreamDestroy(c->st2);
   if (c->st) cudaStreamDestroy(c->st);
   delete c;
 }
 
+// Whole-wavefield transfers go component by component through two contiguous staging buffers: one 1-D copy per component
+// on the I/O stream (full PCIe rate from pinned memory; a pitched 2-D copy of 1.6 KB rows is several times slower) and a
+// re-pitch kernel on the compute stream, double-buffered so that the copy of component c+1 overlaps the kernel of c.
+static int stage_alloc(cgfd_b200_ctx *c)
+{
+  for (int b = 0; b < 2; b++)
+    if (!c->stage[b]) CK(cudaMalloc((void **)&c->stage[b], c->hV * sizeof(float)));
+  return 0;
+}
+static void repitch(cgfd_b200_ctx *c, float *dev_base, float *flat, int to_padded)
+{
+  const size_t rows = (size_t)c->g.ny * c->g.nz;
+  dim3 blk(128), grd((c->g.nx + 127) / 128, (unsigned)(rows < 16384 ? rows : 16384));
+  k_repitch<<<grd, blk, 0, c->st>>>(dev_base + c->shift, flat, c->g.nx, c->PX, rows, to_padded);
+}
 extern "C" int cgfd_b200_set_wavefield(cgfd_b200_ctx *c, const float *w)
 {
   CK(cudaSetDevice(c->device));
-  if (copy_in3d(c, c->lev[c->ipre], w, c->ncmp, c->st)) return 1;
+  if (stage_alloc(c)) return 1;
   CK(cudaStreamSynchronize(c->st));
+  for (int m = 0; m < c->ncmp; m++) {
+    const int b = m & 1;
+    if (m >= 2) CK(cudaStreamWaitEvent(c->st_io, c->stage_free[b], 0));
+    CK(cudaMemcpyAsync(c->stage[b], w + (size_t)m * c->hV, c->hV * sizeof(float), cudaMemcpyHostToDevice, c->st_io));
+    CK(cudaEventRecord(c->stage_full[b], c->st_io));
+    CK(cudaStreamWaitEvent(c->st, c->stage_full[b], 0));
+    repitch(c, c->lev[c->ipre] + (size_t)m * c->V, c->stage[b], 1);
+    CK(cudaEventRecord(c->stage_free[b], c->st));
+  }
+  CK(cudaStreamSynchronize(c->st));
+  CK(cudaGetLastError());
   return 0;
 }
 extern "C" int cgfd_b200_get_wavefield(cgfd_b200_ctx *c, float *w)
 {
   CK(cudaSetDevice(c->device));
-  if (copy_out3d(c, w, c->lev[c->ipre], c->ncmp, c->st)) return 1;
+  if (stage_alloc(c)) return 1;
+  CK(cudaStreamSynchronize(c->st_io));
+  for (int m = 0; m < c->ncmp; m++) {
+    const int b = m & 1;
+    if (m >= 2) CK(cudaStreamWaitEvent(c->st, c->stage_free[b], 0));
+    repitch(c, c->lev[c->ipre] + (size_t)m * c->V, c->stage[b], 0);
+    CK(cudaEventRecord(c->stage_full[b], c->st));
+    CK(cudaStreamWaitEvent(c->st_io, c->stage_full[b], 0));
+    CK(cudaMemcpyAsync(w + (size_t)m * c->hV, c->stage[b], c->hV * sizeof(float), cudaMemcpyDeviceToHost, c->st_io));
+    CK(cudaEventRecord(c->stage_free[b], c->st_io));
+  }
+  CK(cudaStreamSynchronize(c->st_io));
   CK(cudaStreamSynchronize(c->st));
+  CK(cudaGetLastError());
   return 0;
 }
 extern "C" size_t cgfd_b200_pml_aux_size(cgfd_b200_ctx *c, int idim, int is) { return c->pml[idim][is].on ? c->pml[idim][is].siz * 9 : 0; }
@@ -644,7 +734,7 @@ static int run_stage(cgfd_b200_ctx *c, StageArgs &P, int it, int ipair, int ista
   TmaMaps maps;
   if (c->have_maps) {
     maps.cur = c->map_halo[icur]; maps.pre = c->map_cen[ipre]; maps.end = c->map_cen[iend];
-    maps.met = c->map_met; maps.med = c->map_med;
+    maps.met = c->map_met; maps.met5 = c->map_met5; maps.med = c->map_med;
     maps.out_tmp = c->map_out[itmp]; maps.out_end = c->map_out[iend];
   }
   const TmaMaps *mp = c->have_maps ? &maps : nullptr;
@@ -676,7 +766,7 @@ static int run_stage(cgfd_b200_ctx *c, StageArgs &P, int it, int ipair, int ista
   if (two) { CK(cudaEventRecord(c->ev_fork, c->st)); CK(cudaStreamWaitEvent(c->st2, c->ev_fork, 0)); }
   // ---- boundary phase
   launch_top(c->med, P, dir, kind, sb, &nl);
-  for (int n = 0; n < nb; n++) launch_main(c->med, P, mp, dir, kind, c->zchunk, bnd[n], sb, nullptr, nullptr, &nl);
+  for (int n = 0; n < nb; n++) launch_main(c->med, P, mp, dir, kind, c->gz, c->zchunk, bnd[n], sb, nullptr, nullptr, &nl);
   if (c->has_src && c->src_nb > 0) {
     k_src_inject<<<(c->src_nb + 127) / 128, 128, 0, sb>>>(c->src, 0, c->src_nb, it, istage, c->lev[itmp] + sh, c->lev[iend] + sh, a, b, c->V, kind);
     nl++;
@@ -687,7 +777,7 @@ static int run_stage(cgfd_b200_ctx *c, StageArgs &P, int it, int ipair, int ista
   }
   if (two) CK(cudaEventRecord(c->ev_join, c->st2));
   // ---- interior phase
-  launch_main(c->med, P, mp, dir, kind, c->zchunk, inner, c->st, e0, e1, &nl);
+  launch_main(c->med, P, mp, dir, kind, c->gz, c->zchunk, inner, c->st, e0, e1, &nl);
   if (c->has_src && c->src.npts > c->src_nb) {
     const int cnt = c->src.npts - c->src_nb;
     k_src_inject<<<(cnt + 127) / 128, 128, 0, c->st>>>(c->src, c->src_nb, cnt, it, istage, c->lev[itmp] + sh, c->lev[iend] + sh, a, b, c->V, kind);
@@ -764,12 +854,31 @@ extern "C" int cgfd_b200_run(cgfd_b200_ctx *c, int it0, int nsteps)
                                                    c->rec + (size_t)c->rec_count * c->ncmp * c->nrec);
       c->rec_count++; c->total_launches++;
     }
+    for (SnapTap *t : c->snaps) {
+      // io_snap_nc_put / io_slice_nc_put (forward/io_funcs.c:991-1268): frame of w_end every tinv steps from it1 on
+      if (it < t->it1 || (it - t->it1) % t->tinv != 0 || t->nframes >= t->max_frames) continue;
+      const int r = t->nframes % SNAP_RING;
+      if (t->nframes >= SNAP_RING) CK(cudaEventSynchronize(t->copied[r]));   // the slot's previous frame has left the device
+      const size_t tot = t->cmp_elems;
+      for (int m = 0; m < t->ncmp; m++)
+        k_pack_box<<<(unsigned)((tot + 255) / 256), 256, 0, c->st>>>(wnew + (size_t)t->cmps[m] * c->V, c->PX, g.ny, t->box[0], t->box[1], t->box[2],
+                                                                    t->box[3], t->box[4], t->box[5], t->box[6], t->box[7], t->box[8],
+                                                                    t->ring[r] + (size_t)m * tot);
+      c->total_launches += t->ncmp;
+      CK(cudaEventRecord(t->packed[r], c->st));
+      CK(cudaStreamWaitEvent(c->st_io, t->packed[r], 0));
+      CK(cudaMemcpyAsync(t->host + (size_t)t->nframes * t->ncmp * tot, t->ring[r], (size_t)t->ncmp * tot * sizeof(float),
+                         cudaMemcpyDeviceToHost, c->st_io));
+      CK(cudaEventRecord(t->copied[r], c->st_io));
+      t->nframes++;
+    }
     // swap levels n <-> n+1 (forward/drv_rk_curv_col.c:530-542)
     int t = c->ipre; c->ipre = c->iend; c->iend = t;
     if (c->profiling && c->ev_used > 4096) { if (drain_profile(c)) return 1; }
   }
   CK(cudaEventRecord(c->run1, c->st));
   CK(cudaStreamSynchronize(c->st));
+  if (!c->snaps.empty()) CK(cudaStreamSynchronize(c->st_io));   // every frame of these steps is in host memory on return
   CK(cudaGetLastError());
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, c->run0, c->run1));
@@ -805,7 +914,7 @@ extern "C" int cgfd_b200_onestage(cgfd_b200_ctx *c, int it, int ipair, int istag
   TmaMaps maps;
   if (c->have_maps) {
     maps.cur = c->map_halo[icur]; maps.pre = c->map_cen[iz2]; maps.end = c->map_cen[izero];
-    maps.met = c->map_met; maps.med = c->map_med;
+    maps.met = c->map_met; maps.met5 = c->map_met5; maps.med = c->map_med;
     maps.out_tmp = c->map_out[iout]; maps.out_end = c->map_out[izero];
   }
   // aux: cur = copy of level n, pre = zeros, tmp = out, end = scratch
@@ -827,7 +936,7 @@ extern "C" int cgfd_b200_onestage(cgfd_b200_ctx *c, int it, int ipair, int istag
   const int *dir = c->fd.dir[ipair][istage];
   const int whole[4] = {0, c->ntx, 0, c->nty};
   launch_top(c->med, P, dir, KIND_THIRD, c->st, &nl);
-  launch_main(c->med, P, &maps, dir, KIND_THIRD, c->zchunk, whole, c->st, nullptr, nullptr, &nl);
+  launch_main(c->med, P, &maps, dir, KIND_THIRD, c->gz, c->zchunk, whole, c->st, nullptr, nullptr, &nl);
   if (c->has_src)
     k_src_inject<<<(c->src.npts + 127) / 128, 128, 0, c->st>>>(c->src, 0, c->src.npts, it, istage, c->lev[iout] + sh, c->lev[izero] + sh, 1.0f, 0.0f, c->V, KIND_THIRD);
   CK(cudaGetLastError());
@@ -884,6 +993,34 @@ extern "C" int cgfd_b200_get_box(cgfd_b200_ctx *c, int icmp, int i1, int ni, int
   CK(cudaStreamSynchronize(c->st));
   return 0;
 }
+extern "C" int cgfd_b200_add_snapshot(cgfd_b200_ctx *c, int ncmps, const int *cmps, const int box[9], int it1, int tinv, int max_frames,
+                                      float *host_out)
+{
+  CK(cudaSetDevice(c->device));
+  const cgfd_grid_t &g = c->g;
+  if (ncmps <= 0 || ncmps > 32 || !cmps || !host_out || tinv <= 0 || max_frames <= 0) { fail("add_snapshot: bad arguments"); return -1; }
+  for (int m = 0; m < ncmps; m++) if (cmps[m] < 0 || cmps[m] >= c->ncmp) { fail("add_snapshot: component out of range"); return -1; }
+  const int i1 = box[0], ni = box[1], di = box[2], j1 = box[3], nj = box[4], dj = box[5], k1 = box[6], nk = box[7], dk = box[8];
+  if (ni <= 0 || nj <= 0 || nk <= 0 || di <= 0 || dj <= 0 || dk <= 0 || i1 < 0 || j1 < 0 || k1 < 0 || i1 + (ni - 1) * di >= g.nx ||
+      j1 + (nj - 1) * dj >= g.ny || k1 + (nk - 1) * dk >= g.nz) { fail("add_snapshot: box outside the array"); return -1; }
+  SnapTap *t = new SnapTap();
+  t->ncmp = ncmps; memcpy(t->cmps, cmps, ncmps * sizeof(int)); memcpy(t->box, box, 9 * sizeof(int));
+  t->it1 = it1; t->tinv = tinv; t->max_frames = max_frames; t->host = host_out;
+  t->cmp_elems = (size_t)ni * nj * nk;
+  for (int r = 0; r < SNAP_RING; r++) {
+    t->ring[r] = nullptr;
+    if (cudaMalloc((void **)&t->ring[r], t->cmp_elems * ncmps * sizeof(float)) != cudaSuccess ||
+        cudaEventCreateWithFlags(&t->packed[r], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&t->copied[r], cudaEventDisableTiming) != cudaSuccess) { fail("add_snapshot: out of device memory"); return -1; }
+  }
+  c->snaps.push_back(t);
+  return (int)c->snaps.size() - 1;
+}
+extern "C" int cgfd_b200_snapshot_frames(cgfd_b200_ctx *c, int id)
+{
+  if (id < 0 || id >= (int)c->snaps.size()) { fail("snapshot_frames: unknown snapshot"); return -1; }
+  return c->snaps[id]->nframes;
+}
 extern "C" int cgfd_b200_get_pg(cgfd_b200_ctx *c, float *pg)
 {
   if (!c->PG) return fail("get_pg: no free surface");
@@ -931,6 +1068,7 @@ extern "C" int cgfd_b200_get_profile(cgfd_b200_ctx *c, double *ms, int64_t *nmai
   if (ntot) *ntot = c->total_launches;
   return 0;
 }
+extern "C" int cgfd_b200_grid_class(cgfd_b200_ctx *c) { return c->gz; }
 extern "C" int cgfd_b200_last_run_ms(cgfd_b200_ctx *c, double *ms) { *ms = c->last_run_ms; return 0; }
 extern "C" int cgfd_b200_set_variant(cgfd_b200_ctx *c, const char *name)
 {

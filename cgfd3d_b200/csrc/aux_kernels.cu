@@ -80,6 +80,17 @@ __global__ void k_pack_box(const float *w, int nx, int ny, int i1, int ni, int d
   out[n] = w[((size_t)(k1 + kk * dk) * ny + (j1 + jj * dj)) * nx + (i1 + ii * di)];
 }
 
+// rows of nx floats between the unpadded host order and the padded device rows (pitch PX; `pad` is already shifted)
+__global__ void k_repitch(float *pad, float *flat, int nx, int pitch, size_t rows, int to_padded)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nx) return;
+  for (size_t r = blockIdx.y; r < rows; r += gridDim.y) {
+    if (to_padded) pad[r * pitch + i] = flat[r * nx + i];
+    else flat[r * nx + i] = pad[r * pitch + i];
+  }
+}
+
 // PGV / PGA / PGD maps on the free surface (PG_calcu, forward/wav_t.c:379-455)
 __global__ void k_pg(const float *w_new, const float *w_old, size_t V, int pitch, int nx, int ny, int ni1, int ni2, int nj1,
                      int nj2, int nk2, float dt, float *PG, float *Dis)
@@ -154,6 +165,15 @@ __global__ void k_ablexp(float *w, size_t V, int ncmp, int nx, int ny, int i1, i
 // halo strips <-> contiguous message buffers, layout [ivar][k][j][i] per side as
 // blk_macdrp_pack_mesg / unpack_mesg (forward/blk_t.c:576-808): only j in [nj1,nj2], k in [nk1,nk2]
 // for x messages and i in [ni1,ni2] for y messages (no edges / corners).
+// *flag = 1 when a[k][j][i] != 0 anywhere in i1..i2 x (j1 + blockIdx.y) x (k1 + blockIdx.z); a is a shifted, padded array
+__global__ void k_any_nonzero(const float *a, int pitch, int ny, int i1, int i2, int j1, int k1, int *flag)
+{
+  const int i = i1 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > i2) return;
+  const size_t p = ((size_t)(k1 + blockIdx.z) * ny + (j1 + blockIdx.y)) * pitch + i;
+  if (a[p] != 0.0f) *flag = 1;
+}
+
 __global__ void k_halo_copy(float *w, float *buf, size_t V, int ncmp, int nx, int ny, int i1, int ni, int j1, int nj, int k1,
                             int nk, int unpack)
 {

@@ -21,6 +21,16 @@ enum { M_JAC = 0, M_XIX, M_XIY, M_XIZ, M_ETX, M_ETY, M_ETZ, M_ZTX, M_ZTY, M_ZTZ,
 // variables advance the same way.
 enum { KIND_FIRST = 0, KIND_MID = 1, KIND_LAST = 2, KIND_THIRD = 3 };
 
+// Device order of the metric arrays: the five that differ from zero on a grid whose x-y lines stay Cartesian (only the
+// vertical coordinate is deformed: topography on a regular horizontal mesh) come first, so that the kernels specialised for
+// such grids (GZ: xi_y = xi_z = eta_x = eta_z == 0 everywhere) fetch them with one 5-component TMA box.
+//   block:  jac | xi_x eta_y zeta_x zeta_y zeta_z | xi_y xi_z eta_x eta_z
+__host__ __device__ constexpr int metric_dev_slot(int m)
+{
+  return m == M_JAC ? 0 : m == M_XIX ? 1 : m == M_ETY ? 2 : m == M_ZTX ? 3 : m == M_ZTY ? 4 : m == M_ZTZ ? 5
+       : m == M_XIY ? 6 : m == M_XIZ ? 7 : m == M_ETX ? 8 : 9;
+}
+
 constexpr int MAX_MEDIA = 24;
 constexpr int MAX_MAXWELL = 8;
 
@@ -67,6 +77,7 @@ struct StageArgs {
   int bx0, by0;                 // first tile of this launch along x / y (main kernel)
   int l2mode;                   // bit 0: wavefield tiles evict_last, bit 1: touch-once operands and results evict_first;
                                 // bit 2: no PML-free fast path (every block-plane runs the PML copy of the loop body)
+                                // bits 5-6: L2 prefetch distance of the interior kernel, planes beyond the ring (0 = off)
   size_t siz_line, siz_slice, siz_vol;   // padded pitch, pitch*ny, pitch*ny*nz
   const float *cur;             // w_cur  [ncmp][nz][ny][nx]
   const float *pre;             // w_pre
@@ -88,7 +99,8 @@ struct StageArgs {
 // tensor maps of one stage launch (TMA variant of the interior kernel)
 struct TmaMaps {
   CUtensorMap cur;   // w_cur, box (TX+2*HALO_X, TY+4, 1, 9)
-  CUtensorMap met;   // xi_x..zeta_z, box (TX, TY, 1, 9)
+  CUtensorMap met;   // the 9 metric arrays in device order (metric_dev_slot), box (TX, TY, 1, 9)
+  CUtensorMap met5;  // the same tensor, box (TX, TY, 1, 5): the arrays a vertically deformed grid needs (GZ kernels)
   CUtensorMap med;   // media, box (TX, TY, 1, nmedia)
   CUtensorMap pre;   // w_pre, box (TX, TY, 1, 9)
   CUtensorMap end;   // w_end, box (TX, TY, 1, 9)
@@ -101,8 +113,9 @@ struct TmaMaps {
 // this stage's operator; MED = MED_* of physics.cuh
 template <int MED> int med_kernels_init();   // one-time function attributes (dynamic shared memory)
 // interior rows of the tile rectangle rect = {bx0, bx1, by0, by1} (tiles of TILE_X x TILE_Y points from (ni1, nj1))
+// gz = 1: the grid has xi_y = xi_z = eta_x = eta_z == 0 (checked by the caller): kernels that never read those arrays
 template <int MED>
-void med_launch_main(const StageArgs &P, const TmaMaps *maps, int dx, int dy, int dz, int kind, int zchunk, const int rect[4],
+void med_launch_main(const StageArgs &P, const TmaMaps *maps, int dx, int dy, int dz, int kind, int gz, int zchunk, const int rect[4],
                      cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1, int *nlaunch);
 // the four free-surface rows, whole x-y range (no-op without a free top)
 template <int MED> void med_launch_top(const StageArgs &P, int dx, int dy, int dz, int kind, cudaStream_t st, int *nlaunch);

@@ -57,15 +57,16 @@ template <int MED> struct Lay {   // the media tiles come last: their number dep
   static constexpr int BLOCKS = BY_SMEM < BY_REGS ? (BY_SMEM < 1 ? 1 : BY_SMEM) : BY_REGS;
 };
 
-template <int KIND, int MED> __device__ __forceinline__ constexpr uint32_t stage_tx_bytes()
+template <int KIND, int MED, bool GZ> __device__ __forceinline__ constexpr uint32_t stage_tx_bytes()
 {
-  return CUR_BYTES + (9 + Lay<MED>::NMT) * CEN_BYTES + (KIND != KIND_FIRST ? 9 * CEN_BYTES : 0) + (KIND == KIND_LAST ? 9 * CEN_BYTES : 0);
+  return CUR_BYTES + ((GZ ? 5 : 9) + Lay<MED>::NMT) * CEN_BYTES + (KIND != KIND_FIRST ? 9 * CEN_BYTES : 0) + (KIND == KIND_LAST ? 9 * CEN_BYTES : 0);
 }
 
 struct TmaCtx {
   unsigned char *ring;
   uint64_t *full;
   int tx, ty, t, i, j, i0, j0, k1;
+  int pf;              // L2 prefetch distance in planes beyond the ring (0 = off)
   bool active, inarr;
   size_t pij;
   const float *qptr;   // w_cur + pij: this thread's column of component 0
@@ -75,16 +76,16 @@ struct TmaCtx {
 // Loads of one plane into ring slot s, in two parts: A = the tiles nothing is stored from (wavefield with halo, metric,
 // media; also arms the barrier with the byte count of the whole plane), B = the w_pre / w_end tiles, which double as the
 // sources of the TMA stores of the plane that used the slot before and can only be refilled once those have been read.
-template <int DX, int DY, int KIND, int MED>
+template <int DX, int DY, int KIND, int MED, bool GZ>
 __device__ __forceinline__ void tma_issue_a(const StageArgs &P, const TmaMaps &M, const TmaCtx &C, int kk, int s)
 {
   constexpr int YL = Ofs<DY>::left;
   unsigned char *b = C.ring + s * Lay<MED>::STAGE_BYTES;
   uint64_t *bar = C.full + s;
-  mbar_expect_tx(bar, stage_tx_bytes<KIND, MED>());
+  mbar_expect_tx(bar, stage_tx_bytes<KIND, MED, GZ>());
   // the wavefield tiles overlap their neighbours' (x-y halo): keep them in L2; everything else is touched once per stage
   tma_load_4d_hint(b + OFF_CUR, &M.cur, bar, C.i0 - HX + P.shift, C.j0 - YL, kk, 0, C.pol_keep);
-  tma_load_4d_hint(b + OFF_MET, &M.met, bar, C.i0 + P.shift, C.j0, kk, 0, C.pol_stream);
+  tma_load_4d_hint(b + OFF_MET, GZ ? &M.met5 : &M.met, bar, C.i0 + P.shift, C.j0, kk, 0, C.pol_stream);
   tma_load_4d_hint(b + OFF_MED, &M.med, bar, C.i0 + P.shift, C.j0, kk, 0, C.pol_stream);
 }
 template <int DX, int DY, int KIND, int MED>
@@ -95,10 +96,22 @@ __device__ __forceinline__ void tma_issue_b(const StageArgs &P, const TmaMaps &M
   if (KIND != KIND_FIRST) tma_load_4d_hint(b + OFF_PRE, &M.pre, bar, C.i0 + P.shift, C.j0, kk, 0, C.pol_stream);
   if (KIND == KIND_LAST) tma_load_4d_hint(b + OFF_END, &M.end, bar, C.i0 + P.shift, C.j0, kk, 0, C.pol_stream);
 }
-template <int DX, int DY, int KIND, int MED>
+// every operand of plane kk into L2 (thread 0, PF planes ahead of the ring refill): the ring holds only NST planes per block,
+// too few bytes in flight to cover DRAM latency; the L2 has room for several more
+template <int DX, int DY, int KIND, int MED, bool GZ>
+__device__ __forceinline__ void tma_prefetch_plane(const StageArgs &P, const TmaMaps &M, const TmaCtx &C, int kk)
+{
+  constexpr int YL = Ofs<DY>::left;
+  tma_prefetch_4d(&M.cur, C.i0 - HX + P.shift, C.j0 - YL, kk, 0);
+  tma_prefetch_4d(GZ ? &M.met5 : &M.met, C.i0 + P.shift, C.j0, kk, 0);
+  tma_prefetch_4d(&M.med, C.i0 + P.shift, C.j0, kk, 0);
+  if (KIND != KIND_FIRST) tma_prefetch_4d(&M.pre, C.i0 + P.shift, C.j0, kk, 0);
+  if (KIND == KIND_LAST) tma_prefetch_4d(&M.end, C.i0 + P.shift, C.j0, kk, 0);
+}
+template <int DX, int DY, int KIND, int MED, bool GZ>
 __device__ __forceinline__ void tma_issue(const StageArgs &P, const TmaMaps &M, const TmaCtx &C, int kk, int s)
 {
-  tma_issue_a<DX, DY, KIND, MED>(P, M, C, kk, s);
+  tma_issue_a<DX, DY, KIND, MED, GZ>(P, M, C, kk, s);
   tma_issue_b<DX, DY, KIND, MED>(P, M, C, kk, s);
 }
 
@@ -106,7 +119,7 @@ __device__ __forceinline__ void tma_issue(const StageArgs &P, const TmaMaps &M, 
 // offsets {-3..1}, downwards for {-1..3}), so that three of its neighbours are planes already visited and only one
 // lies ahead: q0,q1,q2 = planes k-3d, k-2d, k-d (d = march direction), q3 = plane k, q4 receives plane k+d, which was
 // requested one iteration earlier (qn) -- at the same time as the TMA of that plane, so it is one DRAM read.
-template <int DX, int DY, int DZ, int KIND, int MED, bool PML>
+template <int DX, int DY, int DZ, int KIND, int MED, bool GZ, bool PML>
 __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, const TmaCtx &C, int k, int it, int nplanes,
                                           const float (&q0)[9], const float (&q1)[9], const float (&q2)[9],
                                           const float (&q3)[9], float (&q4)[9], float (&qn)[9])
@@ -135,10 +148,10 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
     float *sp = (float *)(b + OFF_PRE) + C.t;   // w_pre in, w_tmp out
     float *se = (float *)(b + OFF_END) + C.t;   // w_end in, w_end out
     const float(&qz)[9] = q3;   // centre plane of the queue
-    Met m;
-    m.xix = sm[0 * NT]; m.xiy = sm[1 * NT]; m.xiz = sm[2 * NT];
-    m.etx = sm[3 * NT]; m.ety = sm[4 * NT]; m.etz = sm[5 * NT];
-    m.ztx = sm[6 * NT]; m.zty = sm[7 * NT]; m.ztz = sm[8 * NT];
+    Met m;   // tiles in device order (metric_dev_slot)
+    m.xix = sm[0 * NT]; m.ety = sm[1 * NT]; m.ztx = sm[2 * NT]; m.zty = sm[3 * NT]; m.ztz = sm[4 * NT];
+    if (GZ) { m.xiy = 0.0f; m.xiz = 0.0f; m.etx = 0.0f; m.etz = 0.0f; }
+    else { m.xiy = sm[5 * NT]; m.xiz = sm[6 * NT]; m.etx = sm[7 * NT]; m.etz = sm[8 * NT]; }
     Med<MED> md;
     md.load([&](int n) { return sd[n * NT]; });
     const float slw = md.slw;
@@ -153,7 +166,7 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
       d.z[c] = DZ ? cz[0] * q0[c] + cz[1] * q1[c] + cz[2] * q2[c] + cz[3] * q3[c] + cz[4] * q4[c]
                   : cz[0] * q4[c] + cz[1] * q3[c] + cz[2] * q2[c] + cz[3] * q1[c] + cz[4] * q0[c];
     }
-    hooke<MED>(d, m, md, h);
+    hooke<MED, GZ>(d, m, md, h);
     if (PML) pml_all<KIND, 0, MED>(P, C.i, C.j, k, d, m, md, h);
     if constexpr (MED == MED_VIS) atten_update<KIND>(P, (size_t)k * P.siz_slice + C.pij, md.lam, md.mu, h);
 #pragma unroll
@@ -167,7 +180,7 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
       d.z[c] = DZ ? cz[0] * q0[c] + cz[1] * q1[c] + cz[2] * q2[c] + cz[3] * q3[c] + cz[4] * q4[c]
                   : cz[0] * q4[c] + cz[1] * q3[c] + cz[2] * q2[c] + cz[3] * q1[c] + cz[4] * q0[c];
     }
-    momentum(d, m, slw, h);
+    if (GZ) momentum_gz(d, m, slw, h); else momentum(d, m, slw, h);
     if (PML) pml_all<KIND, 1, MED>(P, C.i, C.j, k, d, m, md, h);
 #pragma unroll
     for (int c = 0; c < 3; c++) rk_smem<KIND>(sp + c * NT, se + c * NT, qz[c], h[c], P.a, P.b, P.c);
@@ -177,7 +190,8 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
   if (C.t == 0) {
     const int tx0 = C.i0 - P.ni1, ty0 = C.j0 - P.nj1;
     const bool refill = it + NST < nplanes;
-    if (refill) tma_issue_a<DX, DY, KIND, MED>(P, M, C, k + NST * DIR, s);   // most of the next plane's bytes: requested at once
+    if (refill) tma_issue_a<DX, DY, KIND, MED, GZ>(P, M, C, k + NST * DIR, s);   // most of the next plane's bytes: requested at once
+    if (C.pf > 0 && it + NST + C.pf < nplanes) tma_prefetch_plane<DX, DY, KIND, MED, GZ>(P, M, C, k + (NST + C.pf) * DIR);
     if (KIND != KIND_LAST) tma_store_4d_hint(&M.out_tmp, b + OFF_PRE, tx0, ty0, k, 0, C.pol_stream);
     if (KIND == KIND_MID || KIND == KIND_LAST) tma_store_4d_hint(&M.out_end, b + OFF_END, tx0, ty0, k, 0, C.pol_stream);
     tma_store_commit();
@@ -191,7 +205,7 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
   }
 }
 
-template <int DX, int DY, int DZ, int KIND, int MED>
+template <int DX, int DY, int DZ, int KIND, int MED, bool GZ>
 __global__ void __launch_bounds__(TX *TY, Lay<MED>::BLOCKS) k_main_tma(const StageArgs P, const __grid_constant__ TmaMaps M)
 {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -219,10 +233,13 @@ __global__ void __launch_bounds__(TX *TY, Lay<MED>::BLOCKS) k_main_tma(const Sta
   constexpr int DIR = DZ ? 1 : -1;
   const int nplanes = C.k1 - k0 + 1;
   const int kf = DZ ? k0 : C.k1;   // first plane of the march
+  C.pf = (P.l2mode >> 5) & 3;
   if (C.t == 0) {
 #pragma unroll
     for (int s = 0; s < NST; s++)
-      if (s < nplanes) tma_issue<DX, DY, KIND, MED>(P, M, C, kf + s * DIR, s);
+      if (s < nplanes) tma_issue<DX, DY, KIND, MED, GZ>(P, M, C, kf + s * DIR, s);
+    for (int s = NST; s < NST + C.pf; s++)
+      if (s < nplanes) tma_prefetch_plane<DX, DY, KIND, MED, GZ>(P, M, C, kf + s * DIR);
   }
   // does this tile meet the slab of an x or y PML face? (block-uniform; the z faces are tested per plane)
   bool pml_xy = false;
@@ -249,8 +266,8 @@ __global__ void __launch_bounds__(TX *TY, Lay<MED>::BLOCKS) k_main_tma(const Sta
   }
   for (int it = 0; it < nplanes; it++) {
     const int k = kf + it * DIR;
-    if (pml_xy || k <= zk1 || k >= zk2 || (P.l2mode & 4)) tma_plane<DX, DY, DZ, KIND, MED, true>(P, M, C, k, it, nplanes, q0, q1, q2, q3, q4, qn);
-    else tma_plane<DX, DY, DZ, KIND, MED, false>(P, M, C, k, it, nplanes, q0, q1, q2, q3, q4, qn);
+    if (pml_xy || k <= zk1 || k >= zk2 || (P.l2mode & 4)) tma_plane<DX, DY, DZ, KIND, MED, GZ, true>(P, M, C, k, it, nplanes, q0, q1, q2, q3, q4, qn);
+    else tma_plane<DX, DY, DZ, KIND, MED, GZ, false>(P, M, C, k, it, nplanes, q0, q1, q2, q3, q4, qn);
     // rotate the zeta queue (register moves; unrolling by 5 instead makes the loop body outgrow the
     // instruction cache and the kernel instruction-fetch bound -- profiles/r1d_summary.txt)
 #pragma unroll
@@ -416,7 +433,7 @@ __global__ void __launch_bounds__(128, 3) k_top(const StageArgs P)
 
 // =============================================================================================
 // interior rows of the tile rectangle [bx0,bx1) x [by0,by1) (tiles of TX x TY points counted from (ni1,nj1))
-template <int DX, int DY, int DZ, int KIND, int MED>
+template <int DX, int DY, int DZ, int KIND, int MED, bool GZ>
 static void launch_main_t(const StageArgs &P0, const TmaMaps *maps, int zchunk, const int rect[4], cudaStream_t st,
                           cudaEvent_t ev0, cudaEvent_t ev1, int *nlaunch)
 {
@@ -438,7 +455,7 @@ static void launch_main_t(const StageArgs &P0, const TmaMaps *maps, int zchunk, 
   nzc = (nk + P.zchunk - 1) / P.zchunk;
   dim3 grid(bx, by, nzc), block(TX, TY);
   if (ev0) cudaEventRecord(ev0, st);
-  k_main_tma<DX, DY, DZ, KIND, MED><<<grid, block, Lay<MED>::SMEM_BYTES, st>>>(P, *maps);
+  k_main_tma<DX, DY, DZ, KIND, MED, GZ><<<grid, block, Lay<MED>::SMEM_BYTES, st>>>(P, *maps);
   if (ev1) cudaEventRecord(ev1, st);
   (*nlaunch)++;
 }
@@ -457,12 +474,16 @@ static void launch_top_t(const StageArgs &P0, cudaStream_t st, int *nlaunch)
   (*nlaunch)++;
 }
 
+template <int DX, int DY, int DZ, int KIND, int MED, bool GZ> static int set_attr_g()
+{
+  cudaError_t e = cudaFuncSetAttribute(k_main_tma<DX, DY, DZ, KIND, MED, GZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<MED>::SMEM_BYTES);
+  if (e != cudaSuccess) return 1;
+  e = cudaFuncSetAttribute(k_main_tma<DX, DY, DZ, KIND, MED, GZ>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  return e != cudaSuccess;
+}
 template <int DX, int DY, int DZ, int KIND, int MED> static int set_attr_t()
 {
-  cudaError_t e = cudaFuncSetAttribute(k_main_tma<DX, DY, DZ, KIND, MED>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<MED>::SMEM_BYTES);
-  if (e != cudaSuccess) return 1;
-  e = cudaFuncSetAttribute(k_main_tma<DX, DY, DZ, KIND, MED>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  return e != cudaSuccess;
+  return set_attr_g<DX, DY, DZ, KIND, MED, false>() | set_attr_g<DX, DY, DZ, KIND, MED, true>();
 }
 template <int KIND, int MED> static int set_attr_k()
 {
@@ -482,10 +503,14 @@ template <int MED> int med_kernels_init()
   }
 
 template <int KIND, int MED>
-static void launch_main_k(const StageArgs &P, const TmaMaps *maps, int dx, int dy, int dz, int zchunk,
+static void launch_main_k(const StageArgs &P, const TmaMaps *maps, int dx, int dy, int dz, int gz, int zchunk,
                           const int rect[4], cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, int *n)
 {
-#define CALL(a, b, c) launch_main_t<a, b, c, KIND, MED>(P, maps, zchunk, rect, st, e0, e1, n)
+#define CALL(a, b, c)                                                                 \
+  do {                                                                                \
+    if (gz) launch_main_t<a, b, c, KIND, MED, true>(P, maps, zchunk, rect, st, e0, e1, n);  \
+    else launch_main_t<a, b, c, KIND, MED, false>(P, maps, zchunk, rect, st, e0, e1, n);    \
+  } while (0)
   CGFD_DISPATCH_DIR(CALL)
 #undef CALL
 }
@@ -497,13 +522,13 @@ template <int KIND, int MED> static void launch_top_k(const StageArgs &P, int dx
 }
 
 template <int MED>
-void med_launch_main(const StageArgs &P, const TmaMaps *maps, int dx, int dy, int dz, int kind, int zchunk, const int rect[4],
+void med_launch_main(const StageArgs &P, const TmaMaps *maps, int dx, int dy, int dz, int kind, int gz, int zchunk, const int rect[4],
                      cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1, int *nlaunch)
 {
-  if (kind == KIND_FIRST) launch_main_k<KIND_FIRST, MED>(P, maps, dx, dy, dz, zchunk, rect, st, ev0, ev1, nlaunch);
-  else if (kind == KIND_MID) launch_main_k<KIND_MID, MED>(P, maps, dx, dy, dz, zchunk, rect, st, ev0, ev1, nlaunch);
-  else if (kind == KIND_THIRD) launch_main_k<KIND_THIRD, MED>(P, maps, dx, dy, dz, zchunk, rect, st, ev0, ev1, nlaunch);
-  else launch_main_k<KIND_LAST, MED>(P, maps, dx, dy, dz, zchunk, rect, st, ev0, ev1, nlaunch);
+  if (kind == KIND_FIRST) launch_main_k<KIND_FIRST, MED>(P, maps, dx, dy, dz, gz, zchunk, rect, st, ev0, ev1, nlaunch);
+  else if (kind == KIND_MID) launch_main_k<KIND_MID, MED>(P, maps, dx, dy, dz, gz, zchunk, rect, st, ev0, ev1, nlaunch);
+  else if (kind == KIND_THIRD) launch_main_k<KIND_THIRD, MED>(P, maps, dx, dy, dz, gz, zchunk, rect, st, ev0, ev1, nlaunch);
+  else launch_main_k<KIND_LAST, MED>(P, maps, dx, dy, dz, gz, zchunk, rect, st, ev0, ev1, nlaunch);
 }
 
 template <int MED> void med_launch_top(const StageArgs &P, int dx, int dy, int dz, int kind, cudaStream_t st, int *nlaunch)
@@ -517,7 +542,7 @@ template <int MED> void med_launch_top(const StageArgs &P, int dx, int dy, int d
 // one medium per translation unit
 #define CGFD_INSTANTIATE_MEDIUM(MED)                                                                                  \
   template int med_kernels_init<MED>();                                                                                \
-  template void med_launch_main<MED>(const StageArgs &, const TmaMaps *, int, int, int, int, int, const int[4], cudaStream_t, \
+  template void med_launch_main<MED>(const StageArgs &, const TmaMaps *, int, int, int, int, int, int, const int[4], cudaStream_t, \
                                      cudaEvent_t, cudaEvent_t, int *);                                                 \
   template void med_launch_top<MED>(const StageArgs &, int, int, int, int, cudaStream_t, int *);
 

@@ -23,7 +23,8 @@ SYMBOLS = [
     "cgfd_b200_pml_aux_size", "cgfd_b200_onestage", "cgfd_b200_get_pml_aux_rhs", "cgfd_b200_run",
     "cgfd_b200_set_record_points", "cgfd_b200_get_record", "cgfd_b200_get_box", "cgfd_b200_get_pg",
     "cgfd_b200_comm_unique_id", "cgfd_b200_comm_init", "cgfd_b200_halo_plan", "cgfd_b200_set_profiling", "cgfd_b200_get_profile",
-    "cgfd_b200_last_run_ms", "cgfd_b200_set_variant",
+    "cgfd_b200_last_run_ms", "cgfd_b200_set_variant", "cgfd_b200_grid_class",
+    "cgfd_b200_add_snapshot", "cgfd_b200_snapshot_frames",
 ]
 
 _lib = None
@@ -67,6 +68,9 @@ def load_library():
     L.cgfd_b200_get_profile.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.cgfd_b200_last_run_ms.argtypes = [vp, C.POINTER(C.c_double)]
     L.cgfd_b200_set_variant.argtypes = [vp, C.c_char_p]
+    L.cgfd_b200_grid_class.argtypes = [vp]
+    L.cgfd_b200_add_snapshot.argtypes = [vp, ci, C.POINTER(ci), C.POINTER(ci * 9), ci, ci, ci, fp]
+    L.cgfd_b200_snapshot_frames.argtypes = [vp, ci]
     _lib = L
     return L
 
@@ -165,6 +169,24 @@ class Solver:
         self._chk(self.L.cgfd_b200_get_box(self.h, icmp, i1, ni, di, j1, nj, dj, k1, nk, dk, _f(o)))
         return o
 
+    def add_snapshot(self, cmps, box, max_frames, it1=0, tinv=1, out=None):
+        """Stream frames of the strided sub-box `box` = (i1, ni, di, j1, nj, dj, k1, nk, dk) of components `cmps` to host
+        memory while run() advances (include/cgfd3d_b200.h). Returns (id, out) with out[frame][cmp][nk][nj][ni]."""
+        ni, nj, nk = box[1], box[4], box[7]
+        if out is None:
+            out = np.zeros((max_frames, len(cmps), nk, nj, ni), np.float32)
+        assert out.dtype == np.float32 and out.flags["C_CONTIGUOUS"] and out.size == max_frames * len(cmps) * nk * nj * ni
+        cm = (C.c_int * len(cmps))(*cmps)
+        bx = (C.c_int * 9)(*box)
+        sid = self.L.cgfd_b200_add_snapshot(self.h, len(cmps), cm, C.byref(bx), it1, tinv, max_frames, _f(out))
+        if sid < 0:
+            raise CgfdError(self.L.cgfd_b200_last_error().decode())
+        self._snap_keep = getattr(self, "_snap_keep", []) + [out]   # the library writes into it during run()
+        return sid, out
+
+    def snapshot_frames(self, sid):
+        return int(self.L.cgfd_b200_snapshot_frames(self.h, sid))
+
     def get_pg(self):
         out = np.empty((15, self.prob.ny, self.prob.nx), np.float32)
         self._chk(self.L.cgfd_b200_get_pg(self.h, _f(out)))
@@ -187,6 +209,10 @@ class Solver:
         ms = C.c_double()
         self._chk(self.L.cgfd_b200_last_run_ms(self.h, C.byref(ms)))
         return ms.value
+
+    def grid_class(self) -> int:
+        """1: kernels specialised for vertically deformed grids (four metric arrays identically zero) are in use."""
+        return int(self.L.cgfd_b200_grid_class(self.h))
 
     def set_variant(self, name: str):
         self._chk(self.L.cgfd_b200_set_variant(self.h, name.encode()))

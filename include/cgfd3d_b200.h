@@ -202,6 +202,18 @@ int  cgfd_b200_comm_init(cgfd_b200_ctx *ctx, const char id[128], int rank, int n
  * indices including ghosts. Mirrors blk_macdrp_pack_mesg / unpack_mesg (forward/blk_t.c:576-808). */
 int  cgfd_b200_halo_plan(const cgfd_grid_t *grid, int dirx, int diry, int side, int send_box[6], int recv_box[6]);
 
+/* ---- streaming outputs ------------------------------------------------------------------------- */
+/* Snapshot / slice output without stalling the time loop (replaces the per-step io_snap_nc_put / io_slice_nc_put gathers,
+ * forward/io_funcs.c:991-1268, called at forward/drv_rk_curv_col.c:498-512). A snapshot is the strided sub-box
+ * box = {i1, ni, di, j1, nj, dj, k1, nk, dk} (local indices including ghosts) of `ncmps` wavefield components; during
+ * cgfd_b200_run a frame of the new wavefield is packed on the device after every step it >= it1 with (it - it1) % tinv == 0
+ * and copied asynchronously to host_out[frame][cmp][nk][nj][ni] (pinned memory gives a true asynchronous copy). When
+ * cgfd_b200_run returns, every frame of the steps it covered is complete. Returns the snapshot id (>= 0) or -1. */
+int  cgfd_b200_add_snapshot(cgfd_b200_ctx *ctx, int ncmps, const int *cmps, const int box[9], int it1, int tinv, int max_frames,
+                            float *host_out);
+/* frames written so far for snapshot `id` (-1: unknown id) */
+int  cgfd_b200_snapshot_frames(cgfd_b200_ctx *ctx, int id);
+
 /* ---- measurement ----------------------------------------------------------------------------- */
 /* When enabled, every launch of the dominant (interior RHS + RK) kernel is bracketed by CUDA
  * events on its own stream; get_profile returns the accumulated milliseconds and launch counts. */
@@ -210,6 +222,9 @@ int  cgfd_b200_get_profile(cgfd_b200_ctx *ctx, double *main_kernel_ms, int64_t *
                            int64_t *total_launches);
 /* time (ms, CUDA events on the compute stream) of the last cgfd_b200_run call */
 int  cgfd_b200_last_run_ms(cgfd_b200_ctx *ctx, double *ms);
+/* 1 when the context runs the kernels specialised for vertically deformed grids (xi_y = xi_z = eta_x = eta_z == 0 at every
+ * physical point, detected at create time; CGFD_GZ=0 in the environment keeps the general kernels), else 0 */
+int  cgfd_b200_grid_class(cgfd_b200_ctx *ctx);
 /* choose a kernel variant by name; NULL/"" = default */
 int  cgfd_b200_set_variant(cgfd_b200_ctx *ctx, const char *name);
 

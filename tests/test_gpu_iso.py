@@ -165,3 +165,75 @@ def test_interior_tiles_without_pml(medium):
     assert np.isfinite(wg).all() and float(np.abs(wr[0]).max()) > 0
     bad = [(util.CMP[c], util.rel_l2(wg[c], wr[c])) for c in range(9) if not util.rel_l2(wg[c], wr[c]) <= TOL_RUN]
     assert not bad, bad
+
+
+@pytest.mark.parametrize("medium", ["iso", "vti"])
+def test_vertically_deformed_grid_kernels(medium, monkeypatch):
+    """Grids whose xi_y, xi_z, eta_x, eta_z vanish identically run kernels that never read those arrays (GZ, cgfd_dev.cuh).
+    They must agree with the general kernels to float32 round-off (same terms, the zero ones dropped; only the compiler's FMA
+    contraction differs: rel L2 <= 2e-6 after the run) and match the reference."""
+    _need()
+    nt = 24
+    prob = util.small_problem(ni=70, nj=30, nk=28, pml_layers=5, nt_total=nt, seed=11, medium=medium)
+    for m in (abi.M_XIY, abi.M_XIZ, abi.M_ETX, abi.M_ETZ):
+        prob.metric[m][...] = 0.0
+    if medium == "iso":
+        from cgfd3d_b200 import hostsetup as hs
+        mvx, mvy, mf = hs.dvh2dvz_iso(prob.metric, prob.media[0], prob.media[1], prob.grid)
+        prob.mats = dict(matVx2Vz=mvx, matVy2Vz=mvy, matF2Vz=mf, matD=np.zeros_like(mf))
+    R = ref_flat.RefSolver(prob)
+    util.fill_surface_matrices(prob, R)
+    wr, _, _ = R.run(nt)
+    out = {}
+    for gz in ("1", "0"):
+        monkeypatch.setenv("CGFD_GZ", gz)
+        G = solver.Solver(prob)
+        assert G.grid_class() == int(gz)
+        G.run(nt)
+        out[gz] = G.get_wavefield()
+        G.close()
+    assert float(np.abs(wr[0]).max()) > 0
+    bad = [(util.CMP[c], util.rel_l2(out["1"][c], out["0"][c])) for c in range(9) if not util.rel_l2(out["1"][c], out["0"][c]) <= 2e-6]
+    assert not bad, bad
+    for gz in ("1", "0"):
+        bad = [(gz, util.CMP[c], util.rel_l2(out[gz][c], wr[c])) for c in range(9) if not util.rel_l2(out[gz][c], wr[c]) <= TOL_RUN]
+        assert not bad, bad
+    # the test grids built from coordinates carry round-off in those four arrays, like the reference's own: general kernels
+    monkeypatch.delenv("CGFD_GZ")
+    G = solver.Solver(util.small_problem(seed=1))
+    assert G.grid_class() == 0
+    G.close()
+
+
+def test_streaming_snapshot_and_staged_wavefield_copies():
+    """add_snapshot frames written while run() advances equal per-step get_box gathers; set/get_wavefield (staged,
+    re-pitched on the device) round-trip bit-exactly, ghosts included."""
+    _need()
+    nt = 12
+    prob = util.small_problem(ni=45, nj=28, nk=24, pml_layers=5, nt_total=nt)
+    rng = np.random.default_rng(5)
+    G = solver.Solver(prob)
+    w0 = rng.uniform(-1, 1, G.shape).astype(np.float32)
+    G.set_wavefield(w0)
+    np.testing.assert_array_equal(G.get_wavefield(), w0)
+    G.close()
+    # reference sequence: one step at a time, synchronous gathers
+    box_a = (3, prob.ni, 1, 3, prob.nj, 1, prob.nz - 4, 1, 1)      # surface, every point
+    box_b = (4, 10, 3, 5, 6, 2, 6, 4, 3)                            # strided volume
+    G = solver.Solver(prob)
+    fa, fb = [], []
+    for it in range(nt):
+        G.run(1, it0=it)
+        fa.append(np.stack([G.get_box(c, *box_a) for c in (0, 1, 2)]))
+        if it >= 2 and (it - 2) % 3 == 0:
+            fb.append(np.stack([G.get_box(c, *box_b) for c in (2, 5)]))
+    G.close()
+    G = solver.Solver(prob)
+    ia, oa = G.add_snapshot((0, 1, 2), box_a, max_frames=nt)
+    ib, ob = G.add_snapshot((2, 5), box_b, max_frames=3, it1=2, tinv=3)   # fewer frames allowed than due: extra ones are dropped
+    G.run(nt)
+    assert G.snapshot_frames(ia) == nt and G.snapshot_frames(ib) == 3
+    np.testing.assert_array_equal(oa, np.stack(fa))
+    np.testing.assert_array_equal(ob, np.stack(fb[:3]))
+    assert float(np.abs(oa).max()) > 0
+    G.close()
