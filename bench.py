@@ -62,7 +62,39 @@ class ClockSampler:
         self.stop = False
         self.t = None
 
+    def _loop_nvml(self, nv, h):
+        # NVML in-process: a sample every ~5 ms (an nvidia-smi call takes > 100 ms, too coarse for a sub-second region)
+        R = nv.nvmlClocksThrottleReasonHwSlowdown, nv.nvmlClocksThrottleReasonHwThermalSlowdown, \
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown, nv.nvmlClocksThrottleReasonSwPowerCap
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        while not self.stop:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append([str(sm), str(mx), "%.2f" % pw] + ["Active" if rs & r else "Not Active" for r in R])
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _loop(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            uuid = None
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:   # NVML enumerates physical devices
+                tok = vis.split(",")[self.index].strip()
+                if tok.isdigit():
+                    idx = int(tok)
+                else:
+                    uuid = tok
+            h = nv.nvmlDeviceGetHandleByUUID(uuid) if uuid else nv.nvmlDeviceGetHandleByIndex(idx)
+            self.how = "nvml"
+            return self._loop_nvml(nv, h)
+        except Exception:
+            self.how = "nvidia-smi"
         while not self.stop:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
@@ -91,7 +123,7 @@ class ClockSampler:
         reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
         pw = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "power_w_max": max(pw) if pw else None, "samples": len(self.rows)}
+                "power_w_max": max(pw) if pw else None, "samples": len(self.rows), "how": getattr(self, "how", None)}
 
 
 def build_rank_problem(size, rank, nranks, device=None, medium="iso"):

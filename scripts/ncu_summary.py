@@ -41,10 +41,18 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio"]
+def raw_rows(path_rep=None, path_csv=None):
+    if path_csv:
+        return list(csv.reader(open(path_csv)))
+    p = subprocess.run(["ncu", "-i", path_rep, "--page", "raw", "--csv"], capture_output=True, text=True)
+    return list(csv.reader(p.stdout.splitlines()))
+
+
+traffic = []
 for f in sorted(os.listdir(src)):
-    if f.endswith(".ncu-rep"):
-        p = subprocess.run(["ncu", "-i", os.path.join(src, f), "--page", "raw", "--csv"], capture_output=True, text=True)
-        rows = list(csv.reader(p.stdout.splitlines()))
+    # the reports are exported to CSV on the GPU box (scripts/gpu_ncu.sh): a .ncu-rep with sources is too large to travel
+    if f.endswith(".ncu-rep") or f.endswith("_raw.csv"):
+        rows = raw_rows(path_rep=os.path.join(src, f)) if f.endswith(".ncu-rep") else raw_rows(path_csv=os.path.join(src, f))
         if len(rows) < 3:
             continue
         hdr, units = rows[0], rows[1]
@@ -55,6 +63,15 @@ for f in sorted(os.listdir(src)):
             for w in want:
                 if w in d:
                     out.append("    %-90s %s %s" % (w, d[w], units[hdr.index(w)]))
+            if "k_main_tma" in d["Kernel Name"]:
+                def gb(k):
+                    v = float(d[k]); u = units[hdr.index(k)]
+                    return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
+                traffic.append((d["Kernel Name"], gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum")))
+if traffic:
+    out.append("\n# DRAM traffic (read + write) per captured launch of the dominant kernel")
+    for k, b in traffic:
+        out.append("%-70s %.3f GB" % (k[:70], b / 1e9))
 bj = os.path.join(src, "bench.json")
 if os.path.isfile(bj):
     out.append("\n# bench.py line of the same session")
