@@ -5,6 +5,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <array>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -49,6 +51,14 @@ static void launch_main(int med, const StageArgs &P, const TmaMaps *maps, const 
   MED_SWITCH(med, CALL)
 #undef CALL
 }
+static int blocks_per_sm(int med)
+{
+  int n = 1;
+#define CALL(M) n = med_blocks_per_sm<M>()
+  MED_SWITCH(med, CALL)
+#undef CALL
+  return n;
+}
 static void launch_top(int med, const StageArgs &P, const int *dir, int kind, cudaStream_t st, int *nl)
 {
 #define CALL(M) med_launch_top<M>(P, dir[0], dir[1], dir[2], kind, st, nl)
@@ -86,6 +96,12 @@ struct SnapTap {
   cudaEvent_t packed[SNAP_RING], copied[SNAP_RING];
 };
 
+// how one tile rectangle of the interior kernel is launched: rows per z chunk and the block order (device table)
+struct LaunchPlan {
+  int zchunk = 0;
+  int *order = nullptr;
+};
+
 struct cgfd_b200_ctx {
   int device = 0;
   cudaStream_t st = nullptr;        // compute stream
@@ -109,7 +125,9 @@ struct cgfd_b200_ctx {
   CUtensorMap map_halo[4], map_cen[4], map_out[4], map_met, map_met5, map_med;
   int gz = 0;                       // xi_y = xi_z = eta_x = eta_z == 0 at every physical point: GZ kernels (cgfd_dev.cuh)
   bool have_maps = false;
-  int zchunk = 0;
+  int zchunk = 0;                   // explicit rows per z chunk (CGFD_ZCHUNK), 0 = chosen by plan_for()
+  int plan_waves = 16, plan_minchunk = 16, plan_lpt = 1;   // measured at 400x400x200: chunks of 14..28 rows within 0.5 %, 49 rows 2 % slower
+  std::map<std::array<int, 4>, struct LaunchPlan> plans;
   int ipre = 0, ia = 1, ib = 2, iend = 3;   // roles of the four level buffers
   float *metric[NMETRIC];           // shifted pointers into metric_blk
   float *media[MAX_MEDIA];
@@ -209,7 +227,9 @@ static int make_map(cgfd_b200_ctx *c, CUtensorMap *m, float *base, int ncomp, in
 {
   encode_tiled_fn enc = get_encode();
   if (!enc) return fail("cuTensorMapEncodeTiled is not available from this driver");
-  cuuint64_t dim[4] = {(cuuint64_t)c->PX, (cuuint64_t)c->g.ny, (cuuint64_t)c->g.nz, (cuuint64_t)ncomp};
+  // x extent = the logical row (shift + nx), not the padded pitch: the part of the last tile's box that hangs over the row is
+  // zero-filled by the TMA unit instead of being fetched from the pad columns (4 % of every operand at 400 points per row)
+  cuuint64_t dim[4] = {(cuuint64_t)(c->shift + c->g.nx), (cuuint64_t)c->g.ny, (cuuint64_t)c->g.nz, (cuuint64_t)ncomp};
   if (phys) {
     dim[0] = (cuuint64_t)(c->g.ni2 - c->g.ni1 + 1); dim[1] = (cuuint64_t)(c->g.nj2 - c->g.nj1 + 1);
     base += c->shift + c->g.ni1 + (size_t)c->g.nj1 * c->PX;
@@ -217,8 +237,13 @@ static int make_map(cgfd_b200_ctx *c, CUtensorMap *m, float *base, int ncomp, in
   cuuint64_t str[3] = {(cuuint64_t)c->PX * 4, (cuuint64_t)c->slice * 4, (cuuint64_t)c->V * 4};
   cuuint32_t box[4] = {(cuuint32_t)bx, (cuuint32_t)by, 1, (cuuint32_t)bc};
   cuuint32_t es[4] = {1, 1, 1, 1};
+  // L2 promotion = granularity of the DRAM fetch behind a box row (CGFD_L2PROMO: 0 none, 1 64 B, 2 128 B, 3 256 B)
+  static const CUtensorMapL2promotion promo_tab[4] = {CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_64B,
+                                                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B};
+  int promo = 2;
+  if (const char *e = getenv("CGFD_L2PROMO")) promo = atoi(e) & 3;
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dim, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_SWIZZLE_NONE, promo_tab[promo], CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
   return 0;
 }
@@ -440,6 +465,9 @@ extern "C" int cgfd_b200_create(const cgfd_problem_t *p, int device, cgfd_b200_c
   c->hslice = (size_t)g.nx * g.ny; c->hV = c->hslice * g.nz;
   c->slice = (size_t)c->PX * g.ny; c->V = c->slice * g.nz;
   if (const char *e = getenv("CGFD_ZCHUNK")) c->zchunk = atoi(e);
+  if (const char *e = getenv("CGFD_WAVES")) c->plan_waves = atoi(e);
+  if (const char *e = getenv("CGFD_MINCHUNK")) c->plan_minchunk = atoi(e);
+  if (const char *e = getenv("CGFD_LPT")) c->plan_lpt = atoi(e);
   if (const char *e = getenv("CGFD_VARIANT")) c->variant = atoi(e);
   if (const char *e = getenv("CGFD_OVERLAP")) c->overlap = atoi(e);
   if (const char *e = getenv("CGFD_L2MODE")) c->l2mode = atoi(e);
@@ -718,6 +746,46 @@ static int split_tiles(const cgfd_b200_ctx *c, bool split, int bnd[4][4], int in
   return n;
 }
 
+// Launch plan of a tile rectangle (cached): z chunks so that the launch has at least `plan_waves` waves of resident blocks
+// with chunks no shorter than `plan_minchunk` rows, and the longest-job-first block order: blocks whose tile meets an x / y
+// PML slab run the PML copy of the loop body on every plane (~3x the time of a plain block-plane), so they go first.
+static const LaunchPlan *plan_for(cgfd_b200_ctx *c, const int rect[4])
+{
+  std::array<int, 4> key = {rect[0], rect[1], rect[2], rect[3]};
+  auto it = c->plans.find(key);
+  if (it != c->plans.end()) return &it->second;
+  LaunchPlan pl;
+  const cgfd_grid_t &g = c->g;
+  const int bx = rect[1] - rect[0], by = rect[3] - rect[2];
+  const int nk = (c->free_top ? g.nk2 - 4 : g.nk2) - g.nk1 + 1;
+  if (bx > 0 && by > 0 && nk > 0) {
+    int nzc = 1;
+    if (c->zchunk > 0) nzc = (nk + c->zchunk - 1) / c->zchunk;
+    else
+      while (nzc < nk && (long)bx * by * nzc < 148L * blocks_per_sm(c->med) * c->plan_waves && nk / (nzc + 1) >= c->plan_minchunk) nzc++;
+    pl.zchunk = (nk + nzc - 1) / nzc;
+    nzc = (nk + pl.zchunk - 1) / pl.zchunk;
+    if (c->plan_lpt) {
+      std::vector<int> slow, fast;
+      for (int z = 0; z < nzc; z++)
+        for (int y = 0; y < by; y++)
+          for (int x = 0; x < bx; x++) {
+            const int i0 = g.ni1 + (rect[0] + x) * TILE_X, j0 = g.nj1 + (rect[2] + y) * TILE_Y;
+            bool pml = false;
+            for (int sd = 0; sd < 2; sd++) {
+              const PmlFaceHost &fx = c->pml[0][sd], &fy = c->pml[1][sd];
+              pml |= fx.on && i0 <= fx.r[1] && i0 + TILE_X - 1 >= fx.r[0];
+              pml |= fy.on && j0 <= fy.r[3] && j0 + TILE_Y - 1 >= fy.r[2];
+            }
+            (pml ? slow : fast).push_back((z * by + y) * bx + x);
+          }
+      slow.insert(slow.end(), fast.begin(), fast.end());
+      if (upload(c, &pl.order, slow.data(), slow.size())) return nullptr;
+    }
+  }
+  return &(c->plans[key] = pl);
+}
+
 // Launch everything of stage `istage` of step `it`; level roles: icur -> (itmp, iend), ipre.
 // Two phases on two streams:
 //   boundary phase (st2, high priority): the free-surface rows, the tiles next to inter-rank faces, the source points
@@ -766,7 +834,12 @@ static int run_stage(cgfd_b200_ctx *c, StageArgs &P, int it, int ipair, int ista
   if (two) { CK(cudaEventRecord(c->ev_fork, c->st)); CK(cudaStreamWaitEvent(c->st2, c->ev_fork, 0)); }
   // ---- boundary phase
   launch_top(c->med, P, dir, kind, sb, &nl);
-  for (int n = 0; n < nb; n++) launch_main(c->med, P, mp, dir, kind, c->gz, c->zchunk, bnd[n], sb, nullptr, nullptr, &nl);
+  for (int n = 0; n < nb; n++) {
+    const LaunchPlan *pl = plan_for(c, bnd[n]);
+    if (!pl) return 1;
+    P.order = pl->order;
+    launch_main(c->med, P, mp, dir, kind, c->gz, pl->zchunk, bnd[n], sb, nullptr, nullptr, &nl);
+  }
   if (c->has_src && c->src_nb > 0) {
     k_src_inject<<<(c->src_nb + 127) / 128, 128, 0, sb>>>(c->src, 0, c->src_nb, it, istage, c->lev[itmp] + sh, c->lev[iend] + sh, a, b, c->V, kind);
     nl++;
@@ -777,7 +850,12 @@ static int run_stage(cgfd_b200_ctx *c, StageArgs &P, int it, int ipair, int ista
   }
   if (two) CK(cudaEventRecord(c->ev_join, c->st2));
   // ---- interior phase
-  launch_main(c->med, P, mp, dir, kind, c->gz, c->zchunk, inner, c->st, e0, e1, &nl);
+  {
+    const LaunchPlan *pl = plan_for(c, inner);
+    if (!pl) return 1;
+    P.order = pl->order;
+    launch_main(c->med, P, mp, dir, kind, c->gz, pl->zchunk, inner, c->st, e0, e1, &nl);
+  }
   if (c->has_src && c->src.npts > c->src_nb) {
     const int cnt = c->src.npts - c->src_nb;
     k_src_inject<<<(cnt + 127) / 128, 128, 0, c->st>>>(c->src, c->src_nb, cnt, it, istage, c->lev[itmp] + sh, c->lev[iend] + sh, a, b, c->V, kind);
@@ -936,7 +1014,12 @@ extern "C" int cgfd_b200_onestage(cgfd_b200_ctx *c, int it, int ipair, int istag
   const int *dir = c->fd.dir[ipair][istage];
   const int whole[4] = {0, c->ntx, 0, c->nty};
   launch_top(c->med, P, dir, KIND_THIRD, c->st, &nl);
-  launch_main(c->med, P, &maps, dir, KIND_THIRD, c->gz, c->zchunk, whole, c->st, nullptr, nullptr, &nl);
+  {
+    const LaunchPlan *pl = plan_for(c, whole);
+    if (!pl) return 1;
+    P.order = pl->order;
+    launch_main(c->med, P, &maps, dir, KIND_THIRD, c->gz, pl->zchunk, whole, c->st, nullptr, nullptr, &nl);
+  }
   if (c->has_src)
     k_src_inject<<<(c->src.npts + 127) / 128, 128, 0, c->st>>>(c->src, 0, c->src.npts, it, istage, c->lev[iout] + sh, c->lev[izero] + sh, 1.0f, 0.0f, c->V, KIND_THIRD);
   CK(cudaGetLastError());

@@ -75,6 +75,8 @@ struct StageArgs {
   int kbeg, kend;               // rows handled by this launch, inclusive
   int zchunk;                   // rows per block along z (main kernel)
   int bx0, by0;                 // first tile of this launch along x / y (main kernel)
+  int nbx, nby;                 // tiles of this launch along x / y: block b works on tile (b % nbx, b / nbx % nby), chunk b / (nbx nby)
+  const int *order;             // optional permutation of the block indices: the slow (PML) tiles first (longest job first)
   int l2mode;                   // bit 0: wavefield tiles evict_last, bit 1: touch-once operands and results evict_first;
                                 // bit 2: no PML-free fast path (every block-plane runs the PML copy of the loop body)
                                 // bits 5-6: L2 prefetch distance of the interior kernel, planes beyond the ring (0 = off)
@@ -112,6 +114,7 @@ struct TmaMaps {
 // launchers, one explicit instantiation per medium (kernels_{iso,vti,aniso,vis}.cu); dir = direction index per axis of
 // this stage's operator; MED = MED_* of physics.cuh
 template <int MED> int med_kernels_init();   // one-time function attributes (dynamic shared memory)
+template <int MED> int med_blocks_per_sm();  // resident blocks of the interior kernel per SM
 // interior rows of the tile rectangle rect = {bx0, bx1, by0, by1} (tiles of TILE_X x TILE_Y points from (ni1, nj1))
 // gz = 1: the grid has xi_y = xi_z = eta_x = eta_z == 0 (checked by the caller): kernels that never read those arrays
 template <int MED>

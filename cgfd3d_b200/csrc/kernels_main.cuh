@@ -213,9 +213,13 @@ __global__ void __launch_bounds__(TX *TY, Lay<MED>::BLOCKS) k_main_tma(const Sta
   C.ring = smem_raw;
   C.full = (uint64_t *)(C.ring + NST * Lay<MED>::STAGE_BYTES);
   C.tx = threadIdx.x; C.ty = threadIdx.y; C.t = C.ty * TX + C.tx;
-  C.i0 = P.ni1 + (P.bx0 + blockIdx.x) * TX; C.j0 = P.nj1 + (P.by0 + blockIdx.y) * TY;
+  // 1-D grid; the optional order table puts the tiles that meet an x / y PML slab first: they take ~3x as long per plane,
+  // and started last they would be the tail of the launch
+  const int bid = P.order ? __ldg(P.order + blockIdx.x) : (int)blockIdx.x;
+  const int bxi = bid % P.nbx, byi = (bid / P.nbx) % P.nby, bzi = bid / (P.nbx * P.nby);
+  C.i0 = P.ni1 + (P.bx0 + bxi) * TX; C.j0 = P.nj1 + (P.by0 + byi) * TY;
   C.i = C.i0 + C.tx; C.j = C.j0 + C.ty;
-  const int k0 = P.kbeg + blockIdx.z * P.zchunk;
+  const int k0 = P.kbeg + bzi * P.zchunk;
   C.k1 = min(k0 + P.zchunk - 1, P.kend);
   C.inarr = (C.i < P.nx) && (C.j < P.ny);
   C.active = (C.i <= P.ni2) && (C.j <= P.nj2);
@@ -453,7 +457,8 @@ static void launch_main_t(const StageArgs &P0, const TmaMaps *maps, int zchunk, 
   }
   P.zchunk = (nk + nzc - 1) / nzc;
   nzc = (nk + P.zchunk - 1) / P.zchunk;
-  dim3 grid(bx, by, nzc), block(TX, TY);
+  P.nbx = bx; P.nby = by;
+  dim3 grid(bx * by * nzc), block(TX, TY);
   if (ev0) cudaEventRecord(ev0, st);
   k_main_tma<DX, DY, DZ, KIND, MED, GZ><<<grid, block, Lay<MED>::SMEM_BYTES, st>>>(P, *maps);
   if (ev1) cudaEventRecord(ev1, st);
@@ -490,6 +495,7 @@ template <int KIND, int MED> static int set_attr_k()
   return set_attr_t<0, 0, 0, KIND, MED>() | set_attr_t<0, 0, 1, KIND, MED>() | set_attr_t<0, 1, 0, KIND, MED>() | set_attr_t<0, 1, 1, KIND, MED>() |
          set_attr_t<1, 0, 0, KIND, MED>() | set_attr_t<1, 0, 1, KIND, MED>() | set_attr_t<1, 1, 0, KIND, MED>() | set_attr_t<1, 1, 1, KIND, MED>();
 }
+template <int MED> int med_blocks_per_sm() { return Lay<MED>::BLOCKS; }
 template <int MED> int med_kernels_init()
 {
   return set_attr_k<KIND_FIRST, MED>() | set_attr_k<KIND_MID, MED>() | set_attr_k<KIND_THIRD, MED>() | set_attr_k<KIND_LAST, MED>();
@@ -542,6 +548,7 @@ template <int MED> void med_launch_top(const StageArgs &P, int dx, int dy, int d
 // one medium per translation unit
 #define CGFD_INSTANTIATE_MEDIUM(MED)                                                                                  \
   template int med_kernels_init<MED>();                                                                                \
+  template int med_blocks_per_sm<MED>();                                                                               \
   template void med_launch_main<MED>(const StageArgs &, const TmaMaps *, int, int, int, int, int, int, const int[4], cudaStream_t, \
                                      cudaEvent_t, cudaEvent_t, int *);                                                 \
   template void med_launch_top<MED>(const StageArgs &, int, int, int, int, cudaStream_t, int *);
