@@ -185,6 +185,18 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
 #pragma unroll
     for (int c = 0; c < 3; c++) rk_smem<KIND>(sp + c * NT, se + c * NT, qz[c], h[c], P.a, P.b, P.c);
     fence_proxy_async_smem();   // the results written above are read by the TMA store below
+  } else {
+    // Columns / rows of the tile beyond the physical range. The TMA store clips at the tensor extent, but in units of 16 bytes:
+    // when ni is not a multiple of 4 the last granule carries up to 3 ghost columns along (measured: ni = 70 -> columns 70, 71
+    // written). Ghost values of the result must be zero here (physical face) or are overwritten by the halo exchange that
+    // follows (inter-rank face), so these threads clear their tile entries instead of leaving stale shared memory in them.
+    float *sp = (float *)(b + OFF_PRE) + C.t, *se = (float *)(b + OFF_END) + C.t;
+#pragma unroll
+    for (int c = 0; c < 9; c++) {
+      if (KIND != KIND_LAST) sp[c * NT] = 0.0f;
+      if (KIND == KIND_MID || KIND == KIND_LAST) se[c * NT] = 0.0f;
+    }
+    fence_proxy_async_smem();
   }
   __syncthreads();   // every thread is done with ring slot s; its PRE / END tiles now hold w_tmp / w_end of this plane
   if (C.t == 0) {

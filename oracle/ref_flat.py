@@ -49,8 +49,8 @@ def _f(a):
     return a.ctypes.data_as(fptr)
 
 
-class RefSolver:
-    """The reference CPU implementation behind the same calls as cgfd3d_b200.solver.Solver."""
+class _RefSolverImpl:
+    """The reference CPU implementation behind the same calls as cgfd3d_b200.solver.Solver (in-process)."""
 
     def __init__(self, prob):
         self.prob = prob
@@ -112,3 +112,93 @@ class RefSolver:
         if tmp is not None:
             tmp.cleanup()
         return w, (rec if nrec else rec[:, :, :0]), secs.value
+
+
+def _serve(conn, prob):
+    """child process: one reference instance, commands over a pipe"""
+    try:
+        R = _RefSolverImpl(prob)
+        conn.send(("ok", (R.ncmp, R.shape)))
+    except Exception as e:   # pragma: no cover
+        conn.send(("err", repr(e)))
+        return
+    while True:
+        try:
+            name, args, kw = conn.recv()
+        except EOFError:
+            return
+        if name == "__close__":
+            return
+        try:
+            conn.send(("ok", getattr(R, name)(*args, **kw)))
+        except Exception as e:
+            conn.send(("err", repr(e)))
+
+
+class RefSolver:
+    """Proxy of _RefSolverImpl living in a forked child process, one per instance.
+
+    The reference keeps process-wide state and is known to touch memory it does not own (SURVEY.md 8c hazards); run inside
+    the test process, an earlier instance can change what a later one -- or the arrays of the problem under test -- sees
+    (observed: a VTI case wrong only when an isotropic case ran before it in the same pytest process). A child forked per
+    instance starts from the pristine library image and a copy-on-write view of `prob`, so nothing leaks either way."""
+
+    def __init__(self, prob):
+        import multiprocessing as mp
+        lib()   # dlopen before the fork, the child inherits the mapping
+        ctx = mp.get_context("fork")
+        self._conn, child = ctx.Pipe()
+        self._p = ctx.Process(target=_serve, args=(child, prob), daemon=True)
+        import warnings
+        with warnings.catch_warnings():
+            # the child runs only the C reference and numpy; the parent's CUDA / BLAS threads are never touched there
+            warnings.simplefilter("ignore", DeprecationWarning)
+            self._p.start()
+        child.close()
+        st, val = self._conn.recv()
+        if st != "ok":
+            raise RuntimeError("reference instance failed: %s" % val)
+        self.prob = prob
+        self.ncmp, self.shape = val
+
+    def _call(self, name, *args, **kw):
+        self._conn.send((name, args, kw))
+        st, val = self._conn.recv()
+        if st != "ok":
+            raise RuntimeError("reference call %s failed: %s" % (name, val))
+        return val
+
+    def pml_aux_size(self, idim, iside):
+        return self._call("pml_aux_size", idim, iside)
+
+    def set_pml_aux(self, idim, iside, aux):
+        return self._call("set_pml_aux", idim, iside, np.ascontiguousarray(aux, np.float32))
+
+    def get_pml_aux(self, idim, iside, level=0):
+        return self._call("get_pml_aux", idim, iside, level)
+
+    def get_pml_aux_rhs(self, idim, iside):
+        return self._call("get_pml_aux_rhs", idim, iside)
+
+    def dvh2dvz(self):
+        return self._call("dvh2dvz")
+
+    def onestage(self, it, ipair, istage, w_cur):
+        return self._call("onestage", it, ipair, istage, np.ascontiguousarray(w_cur, np.float32))
+
+    def run(self, nsteps, w0=None, rec_iptr=None, outdir=None):
+        return self._call("run", nsteps, w0=w0, rec_iptr=rec_iptr, outdir=outdir)
+
+    def close(self):
+        if getattr(self, "_p", None) is not None:
+            try:
+                self._conn.send(("__close__", (), {}))
+            except Exception:
+                pass
+            self._p.join(timeout=10)
+            if self._p.is_alive():
+                self._p.kill()
+            self._p = None
+
+    def __del__(self):
+        self.close()
