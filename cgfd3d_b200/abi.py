@@ -9,7 +9,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 MEDIUM_ELASTIC_ISO = 2
 MEDIUM_ELASTIC_VTI = 3
@@ -101,6 +101,8 @@ class Problem(C.Structure):
         ("ablexp_Ex", fptr), ("ablexp_Ey", fptr), ("ablexp_Ez", fptr),
         ("src", Src),
         ("neigh", C.c_int32 * 4),
+        ("graves_Qs", fptr),
+        ("graves_Qs_freq", C.c_float),
     ]
 
 

@@ -122,6 +122,7 @@ struct cgfd_b200_ctx {
   size_t hV = 0, hslice = 0;        // host (unpadded) volume / slice
   float *lev[4] = {nullptr, nullptr, nullptr, nullptr};   // bases (unshifted)
   float *metric_blk = nullptr, *media_blk = nullptr;
+  float *qatt = nullptr;            // Graves' attenuation factor per point (padded layout, unshifted base) or nullptr
   CUtensorMap map_halo[4], map_cen[4], map_out[4], map_met, map_met5, map_med;
   int gz = 0;                       // xi_y = xi_z = eta_x = eta_z == 0 at every physical point: GZ kernels (cgfd_dev.cuh)
   bool have_maps = false;
@@ -512,6 +513,14 @@ extern "C" int cgfd_b200_create(const cgfd_problem_t *p, int device, cgfd_b200_c
   }
   CK(cudaStreamSynchronize(c->st));
   if (rc) { cgfd_b200_destroy(c); return 1; }
+  if (p->graves_Qs) {
+    if (med == MED_VIS) { cgfd_b200_destroy(c); return fail("cgfd_b200_create: Graves Qs attenuation applies to the elastic media, not to the GMB visco-elastic one"); }
+    if (upload(c, &c->qatt, (const float *)nullptr, c->V)) { cgfd_b200_destroy(c); return 1; }
+    if (copy_in3d(c, c->qatt, p->graves_Qs, 1, c->st)) { cgfd_b200_destroy(c); return 1; }
+    const float coef = (float)(-M_PI * (double)p->graves_Qs_freq * (double)p->dt);   // float coef = - PI * md->visco_Qs_freq * dt, PI a double literal
+    k_graves_factor<<<(unsigned)((c->V + 255) / 256), 256, 0, c->st>>>(c->qatt, c->V, coef);
+    CK(cudaStreamSynchronize(c->st));
+  }
   // grid class: do the four metric arrays that vanish on a vertically deformed grid vanish here? (physical points only:
   // the interior kernel uses the metric point-wise; the free-surface kernel stays general)
   {
@@ -713,6 +722,7 @@ static void fill_args(cgfd_b200_ctx *c, StageArgs &P)
   for (int m = 0; m < NMETRIC; m++) P.metric[m] = c->metric[m];
   for (int m = 0; m < c->nmedia; m++) P.media[m] = c->media[m];
   P.nmaxwell = c->nmaxwell;
+  P.qatt = c->qatt ? c->qatt + c->shift : nullptr;
   for (int n = 0; n < MAX_MAXWELL; n++) P.wl[n] = c->wl[n];
   P.free_top = c->free_top; P.timg_mode = c->timg_mode; P.l2mode = c->l2mode;
   P.matVx2Vz = c->mats[0]; P.matVy2Vz = c->mats[1]; P.matF2Vz = c->mats[2]; P.matD = c->mats[3];
@@ -841,7 +851,7 @@ static int run_stage(cgfd_b200_ctx *c, StageArgs &P, int it, int ipair, int ista
     launch_main(c->med, P, mp, dir, kind, c->gz, pl->zchunk, bnd[n], sb, nullptr, nullptr, &nl);
   }
   if (c->has_src && c->src_nb > 0) {
-    k_src_inject<<<(c->src_nb + 127) / 128, 128, 0, sb>>>(c->src, 0, c->src_nb, it, istage, c->lev[itmp] + sh, c->lev[iend] + sh, a, b, c->V, kind);
+    k_src_inject<<<(c->src_nb + 127) / 128, 128, 0, sb>>>(c->src, 0, c->src_nb, it, istage, c->lev[itmp] + sh, c->lev[iend] + sh, a, b, c->V, kind, P.qatt);
     nl++;
   }
   if (halo_w) {
@@ -858,7 +868,7 @@ static int run_stage(cgfd_b200_ctx *c, StageArgs &P, int it, int ipair, int ista
   }
   if (c->has_src && c->src.npts > c->src_nb) {
     const int cnt = c->src.npts - c->src_nb;
-    k_src_inject<<<(cnt + 127) / 128, 128, 0, c->st>>>(c->src, c->src_nb, cnt, it, istage, c->lev[itmp] + sh, c->lev[iend] + sh, a, b, c->V, kind);
+    k_src_inject<<<(cnt + 127) / 128, 128, 0, c->st>>>(c->src, c->src_nb, cnt, it, istage, c->lev[itmp] + sh, c->lev[iend] + sh, a, b, c->V, kind, P.qatt);
     nl++;
   }
   if (two) CK(cudaStreamWaitEvent(c->st, c->ev_join, 0));
@@ -1021,7 +1031,7 @@ extern "C" int cgfd_b200_onestage(cgfd_b200_ctx *c, int it, int ipair, int istag
     launch_main(c->med, P, &maps, dir, KIND_THIRD, c->gz, pl->zchunk, whole, c->st, nullptr, nullptr, &nl);
   }
   if (c->has_src)
-    k_src_inject<<<(c->src.npts + 127) / 128, 128, 0, c->st>>>(c->src, 0, c->src.npts, it, istage, c->lev[iout] + sh, c->lev[izero] + sh, 1.0f, 0.0f, c->V, KIND_THIRD);
+    k_src_inject<<<(c->src.npts + 127) / 128, 128, 0, c->st>>>(c->src, 0, c->src.npts, it, istage, c->lev[iout] + sh, c->lev[izero] + sh, 1.0f, 0.0f, c->V, KIND_THIRD, nullptr);
   CK(cudaGetLastError());
   if (copy_out3d(c, rhs, c->lev[iout], c->ncmp, c->st)) return 1;
   CK(cudaStreamSynchronize(c->st));

@@ -8,7 +8,7 @@ namespace cgfd {
 // F*w*slw/J to hV and -M*w/J to hT before the RK axpy (forward/sv_curv_col_el.c:350-476);
 // here the same term is pushed through the axpy: tmp += a*s, end += b*s.
 __global__ void k_src_inject(SrcDev S, int first, int count, int it, int istage, float *tmp, float *end, float a, float b, size_t V,
-                             int kind)
+                             int kind, const float *qatt)
 {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= count) return;
@@ -35,7 +35,8 @@ __global__ void k_src_inject(SrcDev S, int first, int count, int it, int istage,
     if (add[c] != 0.0f) {
       // stages 0 and 2 reach w_end through w_tmp - w_pre one stage later (rk_wave, physics.cuh)
       if (kind != KIND_LAST) atomicAdd(tmp + c * V + p, a * add[c]);
-      if (kind == KIND_MID || kind == KIND_LAST) atomicAdd(end + c * V + p, b * add[c]);
+      // the last stage's w_end has already been multiplied by Graves' factor: so is the source's share of it
+      if (kind == KIND_MID || kind == KIND_LAST) atomicAdd(end + c * V + p, b * add[c] * ((kind == KIND_LAST && qatt) ? qatt[p] : 1.0f));
     }
   }
 }
@@ -78,6 +79,16 @@ __global__ void k_pack_box(const float *w, int nx, int ny, int i1, int ni, int d
   if (n >= tot) return;
   int ii = n % ni, jj = (n / ni) % nj, kk = n / ((size_t)ni * nj);
   out[n] = w[((size_t)(k1 + kk * dk) * ny + (j1 + jj * dj)) * nx + (i1 + ii * di)];
+}
+
+// Qs -> exp(coef / Qs) in place (sv_curv_col_el_graves_Qs, forward/sv_curv_col_el.c:638-666: coef = -pi f0 dt, float division,
+// expf). exp in double rounded to float: the correctly rounded value, which glibc's expf returns too.
+__global__ void k_graves_factor(float *q, size_t n, float coef)
+{
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = coef / q[i];
+  q[i] = (q[i] != 0.0f) ? (float)exp((double)x) : 1.0f;
 }
 
 // rows of nx floats between the unpadded host order and the padded device rows (pitch PX; `pad` is already shifted)

@@ -23,7 +23,8 @@ struct SrcDev {
 
 // footprint points [first, first+count) of the list (the list is sorted: points of the boundary phase first)
 __global__ void k_src_inject(SrcDev S, int first, int count, int it, int istage, float *tmp, float *end, float a, float b, size_t V,
-                             int kind);
+                             int kind, const float *qatt);
+__global__ void k_graves_factor(float *q, size_t n, float coef);
 __global__ void k_src_surface(SrcDev S, int it, int istage, float *Tx, float *Ty, float *Tz, float *Vx, float *Vy, float *Vz);
 __global__ void k_record(const float *w, size_t V, int ncmp, int npts, const int64_t *iptr, float *rec_it);
 __global__ void k_pack_box(const float *w, int nx, int ny, int i1, int ni, int di, int j1, int nj, int dj, int k1, int nk,

@@ -91,6 +91,7 @@ struct StageArgs {
   const float *media[MAX_MEDIA];
   int nmaxwell;
   float wl[MAX_MAXWELL];
+  const float *qatt;            // Graves' attenuation factor exp(-pi f0 dt / Qs) per point, applied to w_end by the last stage; or nullptr
   PmlFaceDev pml[3][2];
   int free_top;
   int timg_mode;

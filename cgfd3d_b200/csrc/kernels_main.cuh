@@ -139,6 +139,9 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
     for (int c = 0; c < 9; c++) qn[c] = __ldg(w + c * P.siz_vol);
   }
   if (PML && C.active && it + 1 < nplanes) pml_prefetch<KIND>(P, C.i, C.j, k + DIR);
+  // Graves' attenuation factor of this point (last stage only; requested before the wait below so that it is there in time)
+  float qatt = 1.0f;
+  if (KIND == KIND_LAST && P.qatt && C.active) qatt = __ldg(P.qatt + (size_t)k * P.siz_slice + C.pij);
   unsigned char *b = C.ring + s * Lay<MED>::STAGE_BYTES;
   mbar_wait(C.full + s, parity);
   if (C.active) {
@@ -170,7 +173,7 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
     if (PML) pml_all<KIND, 0, MED>(P, C.i, C.j, k, d, m, md, h);
     if constexpr (MED == MED_VIS) atten_update<KIND>(P, (size_t)k * P.siz_slice + C.pij, md.lam, md.mu, h);
 #pragma unroll
-    for (int c = 3; c < 9; c++) rk_smem<KIND>(sp + c * NT, se + c * NT, qz[c], h[c], P.a, P.b, P.c);
+    for (int c = 3; c < 9; c++) rk_smem<KIND>(sp + c * NT, se + c * NT, qz[c], h[c], P.a, P.b, P.c, qatt);
     // ---- velocity half: needs the stress derivatives only
 #pragma unroll
     for (int c = 3; c < 9; c++) {
@@ -183,7 +186,7 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
     if (GZ) momentum_gz(d, m, slw, h); else momentum(d, m, slw, h);
     if (PML) pml_all<KIND, 1, MED>(P, C.i, C.j, k, d, m, md, h);
 #pragma unroll
-    for (int c = 0; c < 3; c++) rk_smem<KIND>(sp + c * NT, se + c * NT, qz[c], h[c], P.a, P.b, P.c);
+    for (int c = 0; c < 3; c++) rk_smem<KIND>(sp + c * NT, se + c * NT, qz[c], h[c], P.a, P.b, P.c, qatt);
     fence_proxy_async_smem();   // the results written above are read by the TMA store below
   } else {
     // Columns / rows of the tile beyond the physical range. The TMA store clips at the tensor extent, but in units of 16 bytes:
@@ -444,7 +447,8 @@ __global__ void __launch_bounds__(128, 3) k_top(const StageArgs P)
   pml_all<KIND, 1, MED>(P, i, j, k, d, m, md, h);
   if constexpr (MED == MED_VIS) atten_update<KIND>(P, p, md.lam, md.mu, h);
 #pragma unroll
-  for (int c = 0; c < 9; c++) rk_wave<KIND>(P.tmp, P.end, c * V + p, cur[c], pv[c], ev[c], h[c], P.a, P.b, P.c);
+  const float qatt = (KIND == KIND_LAST && P.qatt) ? __ldg(P.qatt + p) : 1.0f;
+  for (int c = 0; c < 9; c++) rk_wave<KIND>(P.tmp, P.end, c * V + p, cur[c], pv[c], ev[c], h[c], P.a, P.b, P.c, qatt);
 }
 
 // =============================================================================================

@@ -79,8 +79,9 @@ __device__ __forceinline__ void hooke_iso_gz(const Deriv &d, const Met &m, float
 // contributions of stages 0 and 2 are recovered one stage later from w_tmp - w_pre = a dt h, which removes one w_end write
 // and two w_end reads per point and step (27 of 192 floats). Same value up to float32 round-off of the field itself.
 template <int KIND>
+// q = Graves' attenuation factor of the point, applied to the finished w_end (forward/drv_rk_curv_col.c:409-416); 1 otherwise
 __device__ __forceinline__ void rk_wave(float *__restrict__ tmp, float *__restrict__ end, size_t off, float cur_c, float pre_v,
-                                        float end_v, float rhs, float a, float b, float c)
+                                        float end_v, float rhs, float a, float b, float c, float q = 1.0f)
 {
   if (KIND == KIND_FIRST) {
     tmp[off] = cur_c + a * rhs;
@@ -90,14 +91,14 @@ __device__ __forceinline__ void rk_wave(float *__restrict__ tmp, float *__restri
   } else if (KIND == KIND_THIRD) {
     tmp[off] = pre_v + a * rhs;
   } else {
-    end[off] = (end_v + c * (cur_c - pre_v)) + b * rhs;
+    end[off] = ((end_v + c * (cur_c - pre_v)) + b * rhs) * q;
   }
 }
 
 // the same update done in place in shared memory: sp holds w_pre (all kinds but FIRST) and receives w_tmp, se holds w_end
 // (LAST) and receives the new w_end (MID, LAST); the tiles are then written out by one TMA store each
 template <int KIND>
-__device__ __forceinline__ void rk_smem(float *sp, float *se, float cur_c, float rhs, float a, float b, float c)
+__device__ __forceinline__ void rk_smem(float *sp, float *se, float cur_c, float rhs, float a, float b, float c, float q = 1.0f)
 {
   if (KIND == KIND_FIRST) {
     *sp = cur_c + a * rhs;
@@ -108,7 +109,7 @@ __device__ __forceinline__ void rk_smem(float *sp, float *se, float cur_c, float
   } else if (KIND == KIND_THIRD) {
     *sp = *sp + a * rhs;
   } else {
-    *se = (*se + c * (cur_c - *sp)) + b * rhs;
+    *se = ((*se + c * (cur_c - *sp)) + b * rhs) * q;
   }
 }
 

@@ -319,6 +319,8 @@ class HostProblem:
     src: dict = field(default_factory=dict)
     neigh: tuple = (-1, -1, -1, -1)
     coords: tuple | None = None
+    graves_Qs: np.ndarray | None = None   # Qs [nz][ny][nx]: Graves' attenuation of an elastic medium (None = off)
+    graves_Qs_freq: float = 1.0
     _keep: list = field(default_factory=list, repr=False)
 
     @property
@@ -409,6 +411,8 @@ class HostProblem:
             p.src.max_stage = 4
         for n in range(4):
             p.neigh[n] = self.neigh[n]
+        p.graves_Qs = abi.as_f(self.graves_Qs)
+        p.graves_Qs_freq = float(self.graves_Qs_freq)
         keep.append(p)
         return p
 

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define CGFD_ABI_VERSION 1
+#define CGFD_ABI_VERSION 2
 
 /* medium types: values of forward/constants.h:21-26 */
 #define CGFD_MEDIUM_ELASTIC_ISO      2
@@ -137,6 +137,12 @@ typedef struct {
   cgfd_src_t src;
   /* x-y neighbours (rank ids, -1 = physical boundary): x1, x2, y1, y2 (forward/mympi_t.c:32-49) */
   int32_t neigh[4];
+  /* Graves' constant-Q attenuation of the elastic media (md->visco_type == CONST_VISCO_GRAVES_QS): after the last RK stage
+   * every component of the new wavefield is multiplied by exp(-pi f0 dt / Qs) at every physical point
+   * (sv_curv_col_el_graves_Qs, forward/sv_curv_col_el.c:638-666, called at forward/drv_rk_curv_col.c:413-416).
+   * graves_Qs = md->Qs [nz][ny][nx] (host or device pointer), graves_Qs_freq = md->visco_Qs_freq; NULL = off. */
+  const float *graves_Qs;
+  float   graves_Qs_freq;
 } cgfd_problem_t;
 
 typedef struct cgfd_b200_ctx cgfd_b200_ctx;

@@ -154,7 +154,7 @@ drv_rk_curv_col_allstep(
     if (md->nmaxwell > CGFD_MAX_MAXWELL) DIE("too many Maxwell bodies");
     for (int n = 0; n < md->nmaxwell; n++) { P.media[3 + n] = md->Ylam[n]; P.media[3 + md->nmaxwell + n] = md->Ymu[n]; P.visco_wl[n] = md->wl[n]; }
   } else DIE("medium_type=%d is not supported", md->medium_type);
-  if (md->visco_type == CONST_VISCO_GRAVES_QS) DIE("Graves Qs attenuation is not available on the GPU path yet");
+  if (md->visco_type == CONST_VISCO_GRAVES_QS) { P.graves_Qs = md->Qs; P.graves_Qs_freq = md->visco_Qs_freq; }
   P.free_top = bdry->is_sides_free[CONST_NDIM - 1][1];
   P.timg_mode = getenv("CGFD_TIMG_MIRROR") ? CGFD_TIMG_MIRROR : CGFD_TIMG_ZERO;
   for (int d = 0; d < 3; d++) for (int s = 0; s < 2; s++) {

@@ -105,8 +105,12 @@ void *cgfd_ref_create(const cgfd_problem_t *p)
     for (int m = 0; m < 10; m++) memcpy(dst[m], p->metric[m], r->nvol * sizeof(float));
   }
 
-  int visco_type = (p->medium_type == CONST_MEDIUM_VISCOELASTIC_ISO) ? CONST_VISCO_GMB : 0;
+  int visco_type = (p->medium_type == CONST_MEDIUM_VISCOELASTIC_ISO) ? CONST_VISCO_GMB : (p->graves_Qs ? CONST_VISCO_GRAVES_QS : 0);
   md_init(gd, &r->md, p->medium_type, visco_type, p->nmaxwell);
+  if (p->graves_Qs) {   /* md_init allocated md->Qs (forward/md_t.c:47-50) */
+    memcpy(r->md.Qs, p->graves_Qs, (size_t)g->nx * g->ny * g->nz * sizeof(float));
+    r->md.visco_Qs_freq = p->graves_Qs_freq;
+  }
   {
     md_t *md = &r->md;
     size_t nb = r->nvol * sizeof(float);
