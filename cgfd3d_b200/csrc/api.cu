@@ -150,6 +150,15 @@ struct cgfd_b200_ctx {
   float *stage[2] = {nullptr, nullptr};            // one unpadded component each (set / get_wavefield)
   cudaEvent_t stage_full[2] = {nullptr, nullptr}, stage_free[2] = {nullptr, nullptr};
   std::vector<struct SnapTap *> snaps;
+  // distributed (finite-fault) sources: points once, time-function blocks double-buffered
+  struct {
+    int n = 0, vi_on = 0, mij_on = 0, max_stage = 0, nt_block = 0;
+    int64_t *iptr = nullptr; float *wV = nullptr, *rjac = nullptr;
+    float *vi[2] = {nullptr, nullptr}, *mij[2] = {nullptr, nullptr};
+    int it_first[2] = {-1, -1}, nt[2] = {0, 0};
+    int next = 0;                                  // buffer the next block goes to
+    cudaEvent_t loaded[2] = {nullptr, nullptr}, used[2] = {nullptr, nullptr};
+  } dd;
   // measurement
   int profiling = 0;
   std::vector<cudaEvent_t> ev;   // pairs around the main kernel
@@ -606,6 +615,8 @@ extern "C" void cgfd_b200_destroy(cgfd_b200_ctx *c)
     delete t;
   }
   for (int b = 0; b < 2; b++) {
+    if (c->dd.loaded[b]) cudaEventDestroy(c->dd.loaded[b]);
+    if (c->dd.used[b]) cudaEventDestroy(c->dd.used[b]);
     if (c->stage[b]) cudaFree(c->stage[b]);
     if (c->stage_full[b]) cudaEventDestroy(c->stage_full[b]);
     if (c->stage_free[b]) cudaEventDestroy(c->stage_free[b]);
@@ -871,6 +882,21 @@ static int run_stage(cgfd_b200_ctx *c, StageArgs &P, int it, int ipair, int ista
     k_src_inject<<<(cnt + 127) / 128, 128, 0, c->st>>>(c->src, c->src_nb, cnt, it, istage, c->lev[itmp] + sh, c->lev[iend] + sh, a, b, c->V, kind, P.qatt);
     nl++;
   }
+  if (c->dd.n > 0) {
+    // the time block that holds step `it` (srcdd is skipped outside every loaded block, like dd_is_valid = 0 past dd_max_nt)
+    for (int bf = 0; bf < 2; bf++) {
+      if (c->dd.it_first[bf] < 0 || it < c->dd.it_first[bf] || it >= c->dd.it_first[bf] + c->dd.nt[bf]) continue;
+      const size_t row = ((size_t)(it - c->dd.it_first[bf]) * c->dd.max_stage + istage) * c->dd.n;
+      if (two) CK(cudaStreamWaitEvent(c->st, c->ev_join, 0));   // dd points may lie in boundary-phase tiles
+      CK(cudaStreamWaitEvent(c->st, c->dd.loaded[bf], 0));
+      k_srcdd_inject<<<(c->dd.n + 127) / 128, 128, 0, c->st>>>(c->dd.n, c->dd.iptr, c->dd.wV, c->dd.rjac,
+          c->dd.vi_on ? c->dd.vi[bf] + row * 3 : nullptr, c->dd.mij_on ? c->dd.mij[bf] + row * 6 : nullptr,
+          c->lev[itmp] + sh, c->lev[iend] + sh, a, b, c->V, kind, P.qatt);
+      CK(cudaEventRecord(c->dd.used[bf], c->st));
+      nl++;
+      break;
+    }
+  }
   if (two) CK(cudaStreamWaitEvent(c->st, c->ev_join, 0));
   c->total_launches += nl;
   CK(cudaGetLastError());
@@ -1084,6 +1110,62 @@ extern "C" int cgfd_b200_get_box(cgfd_b200_ctx *c, int icmp, int i1, int ni, int
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, c->boxbuf, tot * sizeof(float), cudaMemcpyDeviceToHost, c->st));
   CK(cudaStreamSynchronize(c->st));
+  return 0;
+}
+extern "C" int cgfd_b200_dd_set_points(cgfd_b200_ctx *c, int n, const int64_t *indx, int vi_actived, int mij_actived, int max_stage,
+                                       int nt_per_block)
+{
+  CK(cudaSetDevice(c->device));
+  if (c->dd.n > 0) return fail("dd_set_points: already set");
+  if (n <= 0 || !indx || max_stage <= 0 || nt_per_block <= 0 || (!vi_actived && !mij_actived)) return fail("dd_set_points: bad arguments");
+  if (c->halo && c->overlap) {
+    // with the two-phase schedule the ghosts of w_tmp leave before the interior-phase sources are added: points inside the
+    // strips next to an inter-rank face would reach the neighbour one stage late
+    const cgfd_grid_t &g = c->g;
+    for (int q = 0; q < n; q++) {
+      const int64_t i = indx[q] % g.nx, j = (indx[q] / g.nx) % g.ny;
+      if ((c->neigh[0] >= 0 && i < g.ni1 + TILE_X) || (c->neigh[1] >= 0 && i > g.ni2 - TILE_X) || (c->neigh[2] >= 0 && j < g.nj1 + TILE_Y) ||
+          (c->neigh[3] >= 0 && j > g.nj2 - TILE_Y))
+        return fail("dd_set_points: a dd point lies in a boundary-phase tile of an inter-rank face; run this rank with CGFD_OVERLAP=0");
+    }
+  }
+  std::vector<int64_t> dv(n);
+  for (int q = 0; q < n; q++) {
+    if (indx[q] < 0 || (size_t)indx[q] >= c->hV) return fail("dd_set_points: index out of range");
+    dv[q] = dev_index(c, indx[q]);
+  }
+  if (upload(c, &c->dd.iptr, dv.data(), n)) return 1;
+  if (upload(c, &c->dd.wV, (const float *)nullptr, n) || upload(c, &c->dd.rjac, (const float *)nullptr, n)) return 1;
+  const size_t rows = (size_t)nt_per_block * max_stage * n;
+  for (int b = 0; b < 2; b++) {
+    if (vi_actived && upload(c, &c->dd.vi[b], (const float *)nullptr, rows * 3)) return 1;
+    if (mij_actived && upload(c, &c->dd.mij[b], (const float *)nullptr, rows * 6)) return 1;
+    CK(cudaEventCreateWithFlags(&c->dd.loaded[b], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->dd.used[b], cudaEventDisableTiming));
+  }
+  // 1/rho is the last media array of every medium but the visco-elastic one, where it is the third (cgfd3d_b200.h)
+  const float *slw = (c->med == MED_VIS || c->med == MED_ISO) ? c->media[2] : c->media[c->nmedia - 1];
+  k_srcdd_weights<<<(n + 127) / 128, 128, 0, c->st>>>(n, c->dd.iptr, slw, c->metric[M_JAC], c->dd.wV, c->dd.rjac);
+  CK(cudaStreamSynchronize(c->st));
+  c->dd.n = n; c->dd.vi_on = vi_actived; c->dd.mij_on = mij_actived; c->dd.max_stage = max_stage; c->dd.nt_block = nt_per_block;
+  return 0;
+}
+extern "C" int cgfd_b200_dd_load_block(cgfd_b200_ctx *c, int it_first, int nt, const float *vi, const float *mij)
+{
+  CK(cudaSetDevice(c->device));
+  if (c->dd.n <= 0) return fail("dd_load_block: no dd points set");
+  if (nt <= 0 || nt > c->dd.nt_block || it_first < 0) return fail("dd_load_block: bad block");
+  if ((c->dd.vi_on && !vi) || (c->dd.mij_on && !mij)) return fail("dd_load_block: missing table");
+  const int b = c->dd.next;
+  const size_t rows = (size_t)nt * c->dd.max_stage * c->dd.n;
+  // the buffer may still be read by launches of the block it held before
+  if (c->dd.it_first[b] >= 0) CK(cudaStreamWaitEvent(c->st_io, c->dd.used[b], 0));
+  if (c->dd.vi_on) CK(cudaMemcpyAsync(c->dd.vi[b], vi, rows * 3 * sizeof(float), cudaMemcpyHostToDevice, c->st_io));
+  if (c->dd.mij_on) CK(cudaMemcpyAsync(c->dd.mij[b], mij, rows * 6 * sizeof(float), cudaMemcpyHostToDevice, c->st_io));
+  CK(cudaEventRecord(c->dd.loaded[b], c->st_io));
+  CK(cudaEventRecord(c->dd.used[b], c->st));   // defined even if no step of this block ever runs
+  c->dd.it_first[b] = it_first; c->dd.nt[b] = nt;
+  c->dd.next = 1 - b;
   return 0;
 }
 extern "C" int cgfd_b200_add_snapshot(cgfd_b200_ctx *c, int ncmps, const int *cmps, const int box[9], int it1, int tinv, int max_frames,

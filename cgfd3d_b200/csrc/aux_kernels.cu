@@ -41,6 +41,47 @@ __global__ void k_src_inject(SrcDev S, int first, int count, int it, int istage,
   }
 }
 
+// Distributed (finite-fault) sources, sv_curv_col_el_rhs_srcdd (forward/sv_curv_col_el.c:486-632, add-at-point branch):
+// hV += vi * slw/J, hT -= mij / J at every dd point, pushed through the RK axpy like k_src_inject. vi / mij point at the rows of
+// this step and stage inside the resident time block: [n][3] and [n][6] (component order xx yy zz yz xz xy = TXX..TXY).
+__global__ void k_srcdd_inject(int n, const int64_t *iptr, const float *wV, const float *rjac, const float *vi, const float *mij,
+                               float *tmp, float *end, float a, float b, size_t V, int kind, const float *qatt)
+{
+  const int is = blockIdx.x * blockDim.x + threadIdx.x;
+  if (is >= n) return;
+  const size_t p = iptr[is];
+  float add[9];
+#pragma unroll
+  for (int c = 0; c < 9; c++) add[c] = 0.0f;
+  if (vi) {
+    const float w = wV[is];
+#pragma unroll
+    for (int c = 0; c < 3; c++) add[c] = vi[is * 3 + c] * w;
+  }
+  if (mij) {
+    const float w = rjac[is];
+#pragma unroll
+    for (int c = 0; c < 6; c++) add[3 + c] = -(mij[is * 6 + c] * w);
+  }
+  const float q = (kind == KIND_LAST && qatt) ? qatt[p] : 1.0f;
+#pragma unroll
+  for (int c = 0; c < 9; c++) {
+    if (add[c] != 0.0f) {
+      if (kind != KIND_LAST) atomicAdd(tmp + c * V + p, a * add[c]);
+      if (kind == KIND_MID || kind == KIND_LAST) atomicAdd(end + c * V + p, b * add[c] * q);
+    }
+  }
+}
+// weights of the dd points: slw / J (float division, like the reference) and (float)(1.0 / J)
+__global__ void k_srcdd_weights(int n, const int64_t *iptr, const float *slw, const float *jac, float *wV, float *rjac)
+{
+  const int is = blockIdx.x * blockDim.x + threadIdx.x;
+  if (is >= n) return;
+  const size_t p = iptr[is];
+  wV[is] = slw[p] / jac[p];
+  rjac[is] = (float)(1.0 / (double)jac[p]);
+}
+
 // surface force slices TxSrc.. / VxSrc.. of one stage (forward/src_t.c:153-314); slices are
 // zeroed by a memset before this kernel.
 __global__ void k_src_surface(SrcDev S, int it, int istage, float *Tx, float *Ty, float *Tz, float *Vx, float *Vy, float *Vz)

@@ -24,7 +24,7 @@ SYMBOLS = [
     "cgfd_b200_set_record_points", "cgfd_b200_get_record", "cgfd_b200_get_box", "cgfd_b200_get_pg",
     "cgfd_b200_comm_unique_id", "cgfd_b200_comm_init", "cgfd_b200_halo_plan", "cgfd_b200_set_profiling", "cgfd_b200_get_profile",
     "cgfd_b200_last_run_ms", "cgfd_b200_set_variant", "cgfd_b200_grid_class",
-    "cgfd_b200_add_snapshot", "cgfd_b200_snapshot_frames",
+    "cgfd_b200_add_snapshot", "cgfd_b200_snapshot_frames", "cgfd_b200_dd_set_points", "cgfd_b200_dd_load_block",
 ]
 
 _lib = None
@@ -71,6 +71,8 @@ def load_library():
     L.cgfd_b200_grid_class.argtypes = [vp]
     L.cgfd_b200_add_snapshot.argtypes = [vp, ci, C.POINTER(ci), C.POINTER(ci * 9), ci, ci, ci, fp]
     L.cgfd_b200_snapshot_frames.argtypes = [vp, ci]
+    L.cgfd_b200_dd_set_points.argtypes = [vp, ci, C.POINTER(C.c_int64), ci, ci, ci, ci]
+    L.cgfd_b200_dd_load_block.argtypes = [vp, ci, ci, fp, fp]
     _lib = L
     return L
 
@@ -168,6 +170,19 @@ class Solver:
         o = np.empty((nk, nj, ni), np.float32) if out is None else out
         self._chk(self.L.cgfd_b200_get_box(self.h, icmp, i1, ni, di, j1, nj, dj, k1, nk, dk, _f(o)))
         return o
+
+    def dd_set_points(self, indx, vi_actived, mij_actived, nt_per_block, max_stage=4):
+        """distributed-source points (flat host indices) and the size of a time-function block (include/cgfd3d_b200.h)"""
+        a = np.ascontiguousarray(indx, np.int64)
+        self._chk(self.L.cgfd_b200_dd_set_points(self.h, len(a), a.ctypes.data_as(C.POINTER(C.c_int64)), int(vi_actived), int(mij_actived),
+                                                 max_stage, nt_per_block))
+
+    def dd_load_block(self, it_first, vi=None, mij=None):
+        """time functions of steps it_first .. it_first+nt-1: vi[nt][stage][n][3], mij[nt][stage][n][6]"""
+        vi = None if vi is None else np.ascontiguousarray(vi, np.float32)
+        mij = None if mij is None else np.ascontiguousarray(mij, np.float32)
+        nt = (vi if vi is not None else mij).shape[0]
+        self._chk(self.L.cgfd_b200_dd_load_block(self.h, it_first, nt, abi.as_f(vi), abi.as_f(mij)))
 
     def add_snapshot(self, cmps, box, max_frames, it1=0, tinv=1, out=None):
         """Stream frames of the strided sub-box `box` = (i1, ni, di, j1, nj, dj, k1, nk, dk) of components `cmps` to host

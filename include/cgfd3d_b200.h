@@ -208,6 +208,19 @@ int  cgfd_b200_comm_init(cgfd_b200_ctx *ctx, const char id[128], int rank, int n
  * indices including ghosts. Mirrors blk_macdrp_pack_mesg / unpack_mesg (forward/blk_t.c:576-808). */
 int  cgfd_b200_halo_plan(const cgfd_grid_t *grid, int dirx, int diry, int side, int send_box[6], int recv_box[6]);
 
+/* ---- distributed (finite-fault) sources ------------------------------------------------------- */
+/* src_t dd_* (forward/src_t.h:94-126): `n` grid points indx[] = src->dd_indx (flat host index i + j*nx + k*nx*ny) that receive a
+ * velocity source vi and / or a moment-rate source mij at every stage of every step, added at the point
+ * (sv_curv_col_el_rhs_srcdd, forward/sv_curv_col_el.c:486-632; the smoothed variant does not exist in the reference either).
+ * The time functions arrive block by block, as the reference reads them from file (src_dd_accit_loadstf,
+ * forward/src_t.c:1929-2006): vi[nt][max_stage][n][3], mij[nt][max_stage][n][6] (xx yy zz yz xz xy) for the steps
+ * it_first .. it_first+nt-1. Two blocks are resident: load block b+1 while the steps of block b run; the copy is asynchronous
+ * (I/O stream) and the host arrays may be reused as soon as the call returns when they are pageable memory.
+ * Steps outside every resident block get no dd source (dd_is_valid = 0 past dd_max_nt in the reference). */
+int  cgfd_b200_dd_set_points(cgfd_b200_ctx *ctx, int n, const int64_t *indx, int vi_actived, int mij_actived, int max_stage,
+                             int nt_per_block);
+int  cgfd_b200_dd_load_block(cgfd_b200_ctx *ctx, int it_first, int nt, const float *vi, const float *mij);
+
 /* ---- streaming outputs ------------------------------------------------------------------------- */
 /* Snapshot / slice output without stalling the time loop (replaces the per-step io_snap_nc_put / io_slice_nc_put gathers,
  * forward/io_funcs.c:991-1268, called at forward/drv_rk_curv_col.c:498-512). A snapshot is the strided sub-box

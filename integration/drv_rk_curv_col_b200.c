@@ -172,7 +172,7 @@ drv_rk_curv_col_allstep(
     }
     P.ablexp_Ex = bdry->ablexp_Ex; P.ablexp_Ey = bdry->ablexp_Ey; P.ablexp_Ez = bdry->ablexp_Ez;
   }
-  if (src->dd_is_valid == 1) DIE("distributed (dd) sources are not available on the GPU path yet");
+  if (src->dd_is_valid == 1 && src->dd_is_add_at_point != 1) DIE("dd sources with spatial smoothing are not implemented (neither are they in the reference, forward/sv_curv_col_el.c:578-582)");
   cgfd_src_t *S = &P.src;
   S->total_number = src->total_number; S->max_nt = src->max_nt; S->max_stage = src->max_stage;
   S->si = src->si; S->sj = src->sj; S->sk = src->sk;
@@ -207,6 +207,16 @@ drv_rk_curv_col_allstep(
     GPU(cgfd_b200_comm_init(ctx, id, myid, nproc));
   }
 
+  /* distributed (finite-fault) sources: points once, the time block src_dd_read2local left in memory first; the following
+   * blocks are read from file by the reference's own src_dd_accit_loadstf inside the loop (forward/drv_rk_curv_col.c:179-181) */
+  if (src->dd_is_valid == 1) {
+    int64_t *dd_indx = (int64_t *)malloc(sizeof(int64_t) * src->dd_total_number);
+    for (int q = 0; q < src->dd_total_number; q++) dd_indx[q] = (int64_t)src->dd_indx[q];
+    GPU(cgfd_b200_dd_set_points(ctx, src->dd_total_number, dd_indx, src->dd_vi_actived, src->dd_mij_actived, src->max_stage, src->dd_nt_per_read));
+    GPU(cgfd_b200_dd_load_block(ctx, 0, src->dd_nt_this_read, src->dd_vi, src->dd_mij));
+    free(dd_indx);
+  }
+
   /* ---- output taps: every grid point io_recv_keep / io_line_keep will read ------------------------- */
   int nrec = iorecv->total_number * CONST_2_NDIM;
   for (int n = 0; n < ioline->num_of_lines; n++) nrec += ioline->line_nr[n];
@@ -228,6 +238,12 @@ drv_rk_curv_col_allstep(
     float t_end = t_cur + dt;
     if (myid == 0 && verbose > 10) fprintf(stdout, "-> it=%d, t=%f\n", it, t_cur);
 
+    if (src->dd_is_valid == 1) {
+      src_dd_accit_loadstf(src, it, myid);
+      /* a new block was read when the counter wrapped to 0 (forward/src_t.c:1952-2003) */
+      if (src->dd_is_valid == 1 && it > 0 && src->dd_it_here == 0)
+        GPU(cgfd_b200_dd_load_block(ctx, it, src->dd_nt_this_read, src->dd_vi, src->dd_mij));
+    }
     GPU(cgfd_b200_run(ctx, it, 1));
 
     /* receivers and lines: device record -> host w_end at the sampled indices -> reference functions */

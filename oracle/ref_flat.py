@@ -38,6 +38,7 @@ def lib():
         L.cgfd_ref_get_pml_aux.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, fptr]
         L.cgfd_ref_dvh2dvz.argtypes = [C.c_void_p, fptr, fptr, fptr, fptr]
         L.cgfd_ref_onestage.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, fptr, fptr]
+        L.cgfd_ref_set_dd.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.c_int, C.c_int, C.c_int, C.c_int, fptr, fptr, C.c_char_p]
         L.cgfd_ref_run.argtypes = [C.c_void_p, C.c_int, fptr, C.c_int, C.POINTER(C.c_int64), fptr, C.c_char_p,
                                    C.POINTER(C.c_double)]
         _lib = L
@@ -82,6 +83,19 @@ class _RefSolverImpl:
 
     def get_pml_aux_rhs(self, idim, iside):
         return self.get_pml_aux(idim, iside, 2)
+
+    def set_dd(self, indx, vi, mij, nt_per_read):
+        """distributed sources: vi [nt][stage][n][3] and / or mij [nt][stage][n][6] (None = not active)"""
+        indx = np.ascontiguousarray(indx, np.int64)
+        nt = (vi if vi is not None else mij).shape[0]
+        vi = None if vi is None else np.ascontiguousarray(vi, np.float32)
+        mij = None if mij is None else np.ascontiguousarray(mij, np.float32)
+        self._ddtmp = tempfile.TemporaryDirectory()
+        null = fptr()
+        rc = lib().cgfd_ref_set_dd(self.h, len(indx), indx.ctypes.data_as(C.POINTER(C.c_int64)), int(vi is not None), int(mij is not None),
+                                   nt, nt_per_read, _f(vi) if vi is not None else null, _f(mij) if mij is not None else null,
+                                   os.path.join(self._ddtmp.name, "dd").encode())
+        assert rc == 0
 
     def dvh2dvz(self):
         n = self.prob.nx * self.prob.ny * 9
@@ -179,6 +193,9 @@ class RefSolver:
 
     def get_pml_aux_rhs(self, idim, iside):
         return self._call("get_pml_aux_rhs", idim, iside)
+
+    def set_dd(self, indx, vi, mij, nt_per_read):
+        return self._call("set_dd", indx, vi, mij, nt_per_read)
 
     def dvh2dvz(self):
         return self._call("dvh2dvz")

@@ -227,6 +227,42 @@ void *cgfd_ref_create(const cgfd_problem_t *p)
 
 int cgfd_ref_ncmp(void *h) { return ((ref_t *)h)->wav.ncmp; }
 
+/* distributed sources the way src_dd_read2local (forward/src_t.c:1181-1927) leaves them behind: points, first time block in
+ * memory, the rest of the time functions in two binary files the driver's src_dd_accit_loadstf keeps reading from.
+ * vi [nt_total][max_stage][n][3], mij [nt_total][max_stage][n][6] */
+int cgfd_ref_set_dd(void *h, int n, const int64_t *indx, int vi_act, int mij_act, int nt_total, int nt_per_read,
+                    const float *vi, const float *mij, const char *prefix)
+{
+  ref_t *r = (ref_t *)h;
+  src_t *s = &r->src;
+  char fn[1024];
+  if (s->max_stage <= 0) s->max_stage = 4;
+  s->dd_is_valid = 1; s->dd_is_add_at_point = 1; s->dd_smo_hlen = 0;
+  s->dd_vi_actived = vi_act; s->dd_mij_actived = mij_act;
+  s->dd_total_number = n; s->dd_max_nt = nt_total; s->dd_nt_per_read = nt_per_read;
+  s->dd_nt_this_read = nt_per_read < nt_total ? nt_per_read : nt_total; s->dd_it_here = 0;
+  s->dd_indx = (size_t *)malloc(sizeof(size_t) * n);
+  for (int q = 0; q < n; q++) s->dd_indx[q] = (size_t)indx[q];
+  size_t per_step3 = (size_t)s->max_stage * n * 3, per_step6 = (size_t)s->max_stage * n * 6;
+  if (vi_act) {
+    snprintf(fn, sizeof(fn), "%s.vi", prefix);
+    FILE *f = fopen(fn, "wb"); if (!f) return 1;
+    fwrite(vi, sizeof(float), per_step3 * nt_total, f); fclose(f);
+    s->fp_vi = fopen(fn, "rb"); if (!s->fp_vi) return 1;
+    s->dd_vi = (float *)calloc(per_step3 * nt_per_read, sizeof(float));
+    if (fread(s->dd_vi, sizeof(float), per_step3 * s->dd_nt_this_read, s->fp_vi) != per_step3 * s->dd_nt_this_read) return 1;
+  }
+  if (mij_act) {
+    snprintf(fn, sizeof(fn), "%s.mij", prefix);
+    FILE *f = fopen(fn, "wb"); if (!f) return 1;
+    fwrite(mij, sizeof(float), per_step6 * nt_total, f); fclose(f);
+    s->fp_mij = fopen(fn, "rb"); if (!s->fp_mij) return 1;
+    s->dd_mij = (float *)calloc(per_step6 * nt_per_read, sizeof(float));
+    if (fread(s->dd_mij, sizeof(float), per_step6 * s->dd_nt_this_read, s->fp_mij) != per_step6 * s->dd_nt_this_read) return 1;
+  }
+  return 0;
+}
+
 /* grid coordinates [nz][ny][nx] (gd->x3d/y3d/z3d, forward/gd_t.c:23-95): only sv_curv_col_vis_iso_dvh2dvz reads them
  * (surface tangents for matD, forward/sv_curv_col_vis_iso.c:375-507); the C ABI problem does not carry coordinates */
 int cgfd_ref_set_coords(void *h, const float *x, const float *y, const float *z)

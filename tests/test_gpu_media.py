@@ -154,3 +154,34 @@ def test_graves_qs_attenuation(medium):
     w0 = G.get_wavefield()
     G.close()
     assert util.rel_l2(wg[2], w0[2]) > 1e-2   # the attenuation is really applied
+
+
+@pytest.mark.parametrize("case", ["mij", "vi+mij"])
+def test_distributed_sources(case):
+    """finite-fault style dd sources (sv_curv_col_el_rhs_srcdd, forward/sv_curv_col_el.c:486-632): 40 points on a dipping plane,
+    time functions delivered in blocks of 7 steps the way src_dd_accit_loadstf reads them; 30 steps against the reference driver
+    fed from files with the same tables. No other source is present."""
+    _need()
+    nt, nb = 30, 7
+    prob = util.small_problem(ni=44, nj=34, nk=30, pml_layers=6, nt_total=nt, src=None, seed=8)
+    rng = np.random.default_rng(3)
+    pts = [(12 + q % 10, 10 + (q // 10) * 3, prob.nk - 6 - (q % 10)) for q in range(40)]
+    indx = np.array([prob.iptr(*p) for p in pts], np.int64)
+    t = (np.arange(nt)[:, None] + np.array([0.0, 0.5, 0.5, 1.0])[None, :]) * prob.dt          # stage times
+    stf = np.exp(-((t - 0.08) / 0.03) ** 2)[:, :, None, None] * (1.0 + 0.3 * rng.uniform(-1, 1, (1, 1, len(pts), 1)))
+    mij = (stf * 1e15 * rng.uniform(-1, 1, (1, 1, len(pts), 6))).astype(np.float32)
+    vi = (stf * 1e9 * rng.uniform(-1, 1, (1, 1, len(pts), 3))).astype(np.float32) if case == "vi+mij" else None
+    R = ref_flat.RefSolver(prob)
+    R.set_dd(indx, vi, mij, nb)
+    wr, _, _ = R.run(nt)
+    G = solver.Solver(prob)
+    G.dd_set_points(indx, vi is not None, True, nb)
+    for it0 in range(0, nt, nb):
+        n = min(nb, nt - it0)
+        G.dd_load_block(it0, None if vi is None else vi[it0:it0 + n], mij[it0:it0 + n])
+        G.run(n, it0=it0)
+    wg = G.get_wavefield()
+    G.close()
+    assert float(np.abs(wr[0]).max()) > 0 and np.isfinite(wg).all()
+    bad = [(util.CMP[c], util.rel_l2(wg[c], wr[c])) for c in range(9) if not util.rel_l2(wg[c], wr[c]) <= TOL_RUN]
+    assert not bad, bad
