@@ -1112,6 +1112,41 @@ extern "C" int cgfd_b200_get_box(cgfd_b200_ctx *c, int icmp, int i1, int ni, int
   CK(cudaStreamSynchronize(c->st));
   return 0;
 }
+// ---- set-up on the device ---------------------------------------------------
+extern "C" int cgfd_b200_metric_from_coords(int device, const cgfd_grid_t *g, const float *x, const float *y, const float *z, int fd_len,
+                                            const int *fd_indx, const float *fd_coef, float *const metric_out[10])
+{
+  if (!g || !x || !y || !z || !fd_indx || !fd_coef || !metric_out || fd_len <= 0 || fd_len > 16) return fail("metric_from_coords: bad arguments");
+  for (int n = 0; n < fd_len; n++)
+    if (abs(fd_indx[n]) > g->ni1 || abs(fd_indx[n]) > g->nj1 || abs(fd_indx[n]) > g->nk1) return fail("metric_from_coords: operator wider than the ghost layers");
+  CK(cudaSetDevice(device));
+  const size_t V = (size_t)g->nx * g->ny * g->nz, nb = V * sizeof(float);
+  float *buf = nullptr; int *dindx = nullptr; float *dcoef = nullptr;
+  CK(cudaMalloc((void **)&buf, 13 * nb));
+  cudaError_t e = cudaMalloc((void **)&dindx, fd_len * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&dcoef, fd_len * sizeof(float));
+  auto done = [&](int rc) { cudaFree(buf); if (dindx) cudaFree(dindx); if (dcoef) cudaFree(dcoef); return rc; };
+  if (e != cudaSuccess) return done(fail("metric_from_coords: out of device memory"));
+  const float *src[3] = {x, y, z};
+  for (int n = 0; n < 3; n++)
+    if (cudaMemcpy(buf + n * V, src[n], nb, cudaMemcpyDefault) != cudaSuccess) return done(fail("metric_from_coords: copy of the coordinates failed"));
+  cudaMemcpy(dindx, fd_indx, fd_len * sizeof(int), cudaMemcpyHostToDevice);
+  cudaMemcpy(dcoef, fd_coef, fd_len * sizeof(float), cudaMemcpyHostToDevice);
+  cudaMemset(buf + 3 * V, 0, 10 * nb);
+  MetricOut out;
+  for (int m = 0; m < 10; m++) out.a[m] = buf + (3 + m) * V;
+  dim3 blk(128), grd((g->ni2 - g->ni1 + 128) / 128, g->nj2 - g->nj1 + 1, g->nk2 - g->nk1 + 1);
+  k_metric_cal<<<grd, blk>>>(buf, buf + V, buf + 2 * V, g->nx, g->ny, g->ni1, g->ni2, g->nj1, g->nk1, fd_len, dindx, dcoef, out);
+  dim3 grm((unsigned)((V + 255) / 256), 1, 10);
+  k_metric_mirror<<<grm, 256>>>(out, 0, g->nx, g->ny, g->nz, g->ni1, g->ni2);
+  k_metric_mirror<<<grm, 256>>>(out, 1, g->nx, g->ny, g->nz, g->nj1, g->nj2);
+  k_metric_mirror<<<grm, 256>>>(out, 2, g->nx, g->ny, g->nz, g->nk1, g->nk2);
+  if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) return done(fail("metric_from_coords: kernel failed"));
+  for (int m = 0; m < 10; m++)
+    if (!metric_out[m] || cudaMemcpy(metric_out[m], out.a[m], nb, cudaMemcpyDefault) != cudaSuccess) return done(fail("metric_from_coords: copy of the result failed"));
+  return done(0);
+}
+
 extern "C" int cgfd_b200_dd_set_points(cgfd_b200_ctx *c, int n, const int64_t *indx, int vi_actived, int mij_actived, int max_stage,
                                        int nt_per_block)
 {

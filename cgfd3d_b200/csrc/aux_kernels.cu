@@ -132,6 +132,60 @@ __global__ void k_graves_factor(float *q, size_t n, float coef)
   q[i] = (q[i] != 0.0f) ? (float)exp((double)x) : 1.0f;
 }
 
+// gd_curv_metric_cal (forward/gd_t.c:190-286): centred differences of the coordinates (M_FD_SHIFT, forward/fd_t.h:11-15: first term
+// assigned, the others added left to right), Jacobian and the nine metric derivatives at one physical point. Every product and
+// sum is rounded separately (__fmul_rn / __fadd_rn: no FMA contraction), like the reference built by gcc for x86-64, so the
+// arrays come out bit-identical. out = 10 unpadded arrays [nz][ny][nx] in the reference's order jac, xi_x .. zeta_z.
+__device__ __forceinline__ float fd_shift(const float *v, size_t p, long stride, int len, const int *indx, const float *coef)
+{
+  float d = __fmul_rn(coef[0], v[p + indx[0] * stride]);
+  for (int n = 1; n < len; n++) d = __fadd_rn(d, __fmul_rn(coef[n], v[p + indx[n] * stride]));
+  return d;
+}
+__device__ __forceinline__ void cross_rn(const float *A, const float *B, float *C)
+{
+  C[0] = __fsub_rn(__fmul_rn(A[1], B[2]), __fmul_rn(A[2], B[1]));
+  C[1] = __fsub_rn(__fmul_rn(A[2], B[0]), __fmul_rn(A[0], B[2]));
+  C[2] = __fsub_rn(__fmul_rn(A[0], B[1]), __fmul_rn(A[1], B[0]));
+}
+__global__ void k_metric_cal(const float *x, const float *y, const float *z, int nx, int ny, int ni1, int ni2, int nj1, int nk1,
+                             int fd_len, const int *fd_indx, const float *fd_coef, MetricOut out)
+{
+  const int i = ni1 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > ni2) return;
+  const long L = nx, S = (long)nx * ny;
+  const size_t p = (size_t)(nk1 + blockIdx.z) * S + (size_t)(nj1 + blockIdx.y) * L + i;
+  float v1[3], v2[3], v3[3], g[3];
+  v1[0] = fd_shift(x, p, 1, fd_len, fd_indx, fd_coef); v1[1] = fd_shift(y, p, 1, fd_len, fd_indx, fd_coef); v1[2] = fd_shift(z, p, 1, fd_len, fd_indx, fd_coef);
+  v2[0] = fd_shift(x, p, L, fd_len, fd_indx, fd_coef); v2[1] = fd_shift(y, p, L, fd_len, fd_indx, fd_coef); v2[2] = fd_shift(z, p, L, fd_len, fd_indx, fd_coef);
+  v3[0] = fd_shift(x, p, S, fd_len, fd_indx, fd_coef); v3[1] = fd_shift(y, p, S, fd_len, fd_indx, fd_coef); v3[2] = fd_shift(z, p, S, fd_len, fd_indx, fd_coef);
+  cross_rn(v1, v2, g);
+  float jac = 0.0f;   // fdlib_math_dot_product (lib/fdlib_math.c:60-69): result = 0; result += A[i] * B[i]
+  for (int n = 0; n < 3; n++) jac = __fadd_rn(jac, __fmul_rn(g[n], v3[n]));
+  out.a[0][p] = jac;
+  cross_rn(v2, v3, g);
+  out.a[1][p] = __fdiv_rn(g[0], jac); out.a[2][p] = __fdiv_rn(g[1], jac); out.a[3][p] = __fdiv_rn(g[2], jac);
+  cross_rn(v3, v1, g);
+  out.a[4][p] = __fdiv_rn(g[0], jac); out.a[5][p] = __fdiv_rn(g[1], jac); out.a[6][p] = __fdiv_rn(g[2], jac);
+  cross_rn(v1, v2, g);
+  out.a[7][p] = __fdiv_rn(g[0], jac); out.a[8][p] = __fdiv_rn(g[1], jac); out.a[9][p] = __fdiv_rn(g[2], jac);
+}
+// ghosts of one axis mirrored about the mid-point between the last physical and the first ghost point, over the full extent of
+// the other two axes (forward/gd_t.c:288-401, applied in the order x, y, z); blockIdx.z = array
+__global__ void k_metric_mirror(MetricOut out, int axis, int nx, int ny, int nz, int n1, int n2)
+{
+  const size_t tot = (size_t)nx * ny * nz;
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= tot) return;
+  const int i = q % nx, j = (q / nx) % ny, k = q / ((size_t)nx * ny);
+  const int c = (axis == 0) ? i : (axis == 1) ? j : k;
+  if (c >= n1 && c <= n2) return;
+  const long stride = (axis == 0) ? 1 : (axis == 1) ? nx : (long)nx * ny;
+  const long off = (c < n1) ? ((long)(n1 - c) * 2 - 1) : -((long)(c - n2) * 2 - 1);
+  float *a = out.a[blockIdx.z];
+  a[q] = a[q + off * stride];
+}
+
 // rows of nx floats between the unpadded host order and the padded device rows (pitch PX; `pad` is already shifted)
 __global__ void k_repitch(float *pad, float *flat, int nx, int pitch, size_t rows, int to_padded)
 {

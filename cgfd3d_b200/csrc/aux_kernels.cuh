@@ -37,6 +37,10 @@ __global__ void k_pg(const float *w_new, const float *w_old, size_t V, int pitch
 __global__ void k_vis_free(float *w, size_t V, int pitch, int nx, int ny, int ni1, int ni2, int nj1, int nj2, int nk2, const float *matD);
 __global__ void k_ablexp(float *w, size_t V, int ncmp, int nx, int ny, int i1, int i2, int j1, int j2, int k1, int k2,
                          const float *Ex, const float *Ey, const float *Ez);
+struct MetricOut { float *a[10]; };
+__global__ void k_metric_cal(const float *x, const float *y, const float *z, int nx, int ny, int ni1, int ni2, int nj1, int nk1,
+                             int fd_len, const int *fd_indx, const float *fd_coef, MetricOut out);
+__global__ void k_metric_mirror(MetricOut out, int axis, int nx, int ny, int nz, int n1, int n2);
 __global__ void k_repitch(float *pad, float *flat, int nx, int pitch, size_t rows, int to_padded);
 __global__ void k_any_nonzero(const float *a, int pitch, int ny, int i1, int i2, int j1, int k1, int *flag);
 __global__ void k_halo_copy(float *w, float *buf, size_t V, int ncmp, int nx, int ny, int i1, int ni, int j1, int nj, int k1,

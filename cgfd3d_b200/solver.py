@@ -25,6 +25,7 @@ SYMBOLS = [
     "cgfd_b200_comm_unique_id", "cgfd_b200_comm_init", "cgfd_b200_halo_plan", "cgfd_b200_set_profiling", "cgfd_b200_get_profile",
     "cgfd_b200_last_run_ms", "cgfd_b200_set_variant", "cgfd_b200_grid_class",
     "cgfd_b200_add_snapshot", "cgfd_b200_snapshot_frames", "cgfd_b200_dd_set_points", "cgfd_b200_dd_load_block",
+    "cgfd_b200_metric_from_coords",
 ]
 
 _lib = None
@@ -73,6 +74,7 @@ def load_library():
     L.cgfd_b200_snapshot_frames.argtypes = [vp, ci]
     L.cgfd_b200_dd_set_points.argtypes = [vp, ci, C.POINTER(C.c_int64), ci, ci, ci, ci]
     L.cgfd_b200_dd_load_block.argtypes = [vp, ci, ci, fp, fp]
+    L.cgfd_b200_metric_from_coords.argtypes = [ci, C.POINTER(abi.Grid), fp, fp, fp, ci, C.POINTER(ci), fp, C.POINTER(fp * 10)]
     _lib = L
     return L
 
@@ -231,6 +233,24 @@ class Solver:
 
     def set_variant(self, name: str):
         self._chk(self.L.cgfd_b200_set_variant(self.h, name.encode()))
+
+
+def metric_from_coords(grid: dict, x, y, z, fd_indx=None, fd_coef=None, device=0):
+    """jac, xi_x .. zeta_z (list of 10 arrays [nz][ny][nx]) from the coordinates, computed on the GPU by the library
+    (gd_curv_metric_cal, forward/gd_t.c:190-402). Default operator: fd->fdc_indx / fdc_coef of fd_set_macdrp (forward/fd_t.c:292-301)."""
+    from . import hostsetup
+    fd_indx = hostsetup.FDC_INDX if fd_indx is None else fd_indx
+    fd_coef = hostsetup.FDC_COEF if fd_coef is None else fd_coef
+    L = load_library()
+    g = abi.Grid(**grid)
+    x, y, z = (np.ascontiguousarray(a, np.float32) for a in (x, y, z))
+    out = [np.empty_like(x) for _ in range(10)]
+    po = (abi.fptr * 10)(*[_f(o) for o in out])
+    ii = (C.c_int * len(fd_indx))(*fd_indx)
+    cc = np.asarray(fd_coef, np.float32)
+    if L.cgfd_b200_metric_from_coords(device, C.byref(g), _f(x), _f(y), _f(z), len(fd_indx), ii, _f(cc), C.byref(po)) != 0:
+        raise CgfdError(L.cgfd_b200_last_error().decode())
+    return out
 
 
 def halo_plan(grid: dict, dirx: int, diry: int, side: int):

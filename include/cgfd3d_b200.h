@@ -208,6 +208,15 @@ int  cgfd_b200_comm_init(cgfd_b200_ctx *ctx, const char id[128], int rank, int n
  * indices including ghosts. Mirrors blk_macdrp_pack_mesg / unpack_mesg (forward/blk_t.c:576-808). */
 int  cgfd_b200_halo_plan(const cgfd_grid_t *grid, int dirx, int diry, int side, int send_box[6], int recv_box[6]);
 
+/* ---- one-shot set-up on the device ----------------------------------------------------------- */
+/* gd_curv_metric_cal (forward/gd_t.c:190-402, called at forward/main_curv_col_el_3d.c:234): Jacobian and the nine metric
+ * derivatives from the coordinate arrays x, y, z [nz][ny][nx] with the centred operator fd->fdc_indx / fdc_coef (fd_len terms),
+ * ghosts mirrored in the order x, y, z. Every array may be a host or a device pointer; metric_out = jac, xi_x, xi_y, xi_z, eta_x,
+ * eta_y, eta_z, zeta_x, zeta_y, zeta_z. Bit-identical to the reference function (no FMA contraction). Ghosts of inter-rank faces
+ * are the caller's gd_curv_metric_exchange (forward/gd_t.c:407-475) as before. */
+int  cgfd_b200_metric_from_coords(int device, const cgfd_grid_t *grid, const float *x, const float *y, const float *z, int fd_len,
+                                  const int *fd_indx, const float *fd_coef, float *const metric_out[10]);
+
 /* ---- distributed (finite-fault) sources ------------------------------------------------------- */
 /* src_t dd_* (forward/src_t.h:94-126): `n` grid points indx[] = src->dd_indx (flat host index i + j*nx + k*nx*ny) that receive a
  * velocity source vi and / or a moment-rate source mij at every stage of every step, added at the point

@@ -38,6 +38,7 @@ def lib():
         L.cgfd_ref_get_pml_aux.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, fptr]
         L.cgfd_ref_dvh2dvz.argtypes = [C.c_void_p, fptr, fptr, fptr, fptr]
         L.cgfd_ref_onestage.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, fptr, fptr]
+        L.cgfd_ref_metric_from_coords.argtypes = [C.c_void_p, fptr, fptr, fptr, fptr]
         L.cgfd_ref_set_dd.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.c_int, C.c_int, C.c_int, C.c_int, fptr, fptr, C.c_char_p]
         L.cgfd_ref_run.argtypes = [C.c_void_p, C.c_int, fptr, C.c_int, C.POINTER(C.c_int64), fptr, C.c_char_p,
                                    C.POINTER(C.c_double)]
@@ -83,6 +84,13 @@ class _RefSolverImpl:
 
     def get_pml_aux_rhs(self, idim, iside):
         return self.get_pml_aux(idim, iside, 2)
+
+    def metric_from_coords(self, x, y, z):
+        """the reference's gd_curv_metric_cal on this grid: array [10][nz][ny][nx]"""
+        x, y, z = (np.ascontiguousarray(a, np.float32) for a in (x, y, z))
+        out = np.zeros((10,) + x.shape, np.float32)
+        assert lib().cgfd_ref_metric_from_coords(self.h, _f(x), _f(y), _f(z), _f(out)) == 0
+        return out
 
     def set_dd(self, indx, vi, mij, nt_per_read):
         """distributed sources: vi [nt][stage][n][3] and / or mij [nt][stage][n][6] (None = not active)"""
@@ -196,6 +204,9 @@ class RefSolver:
 
     def set_dd(self, indx, vi, mij, nt_per_read):
         return self._call("set_dd", indx, vi, mij, nt_per_read)
+
+    def metric_from_coords(self, x, y, z):
+        return self._call("metric_from_coords", x, y, z)
 
     def dvh2dvz(self):
         return self._call("dvh2dvz")

@@ -227,6 +227,21 @@ void *cgfd_ref_create(const cgfd_problem_t *p)
 
 int cgfd_ref_ncmp(void *h) { return ((ref_t *)h)->wav.ncmp; }
 
+/* gd_curv_metric_cal (forward/gd_t.c:190-402) on the instance's own gd_t with the coordinates x, y, z: out = jac, xi_x .. zeta_z */
+int cgfd_ref_metric_from_coords(void *h, const float *x, const float *y, const float *z, float *out)
+{
+  ref_t *r = (ref_t *)h;
+  gd_t gd = r->gd;
+  gdcurv_metric_t M;
+  gd.x3d = dupf(x, r->nvol); gd.y3d = dupf(y, r->nvol); gd.z3d = dupf(z, r->nvol);
+  gd_curv_metric_init(&gd, &M);
+  gd_curv_metric_cal(&gd, &M, r->fd.fdc_len, r->fd.fdc_indx, r->fd.fdc_coef);
+  float *src[10] = { M.jac, M.xi_x, M.xi_y, M.xi_z, M.eta_x, M.eta_y, M.eta_z, M.zeta_x, M.zeta_y, M.zeta_z };
+  for (int m = 0; m < 10; m++) memcpy(out + (size_t)m * r->nvol, src[m], r->nvol * sizeof(float));
+  free(gd.x3d); free(gd.y3d); free(gd.z3d);
+  return 0;
+}
+
 /* distributed sources the way src_dd_read2local (forward/src_t.c:1181-1927) leaves them behind: points, first time block in
  * memory, the rest of the time functions in two binary files the driver's src_dd_accit_loadstf keeps reading from.
  * vi [nt_total][max_stage][n][3], mij [nt_total][max_stage][n][6] */
