@@ -109,6 +109,7 @@ struct cgfd_b200_ctx {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int l2mode = 3;                   // L2 eviction hints of the interior kernel (CGFD_L2MODE)
   int overlap = 1;                  // run the boundary phase concurrently with the interior kernel
+  int toppar = 0;                   // single rank: free-surface kernel on the second stream beside the interior kernel (CGFD_TOPPAR)
   int ntx = 0, nty = 0;             // tiles of the interior kernel along x / y
   int src_nb = 0;                   // source footprint points that belong to the boundary phase (first in the list)
   cgfd_grid_t g;
@@ -481,6 +482,7 @@ extern "C" int cgfd_b200_create(const cgfd_problem_t *p, int device, cgfd_b200_c
   if (const char *e = getenv("CGFD_VARIANT")) c->variant = atoi(e);
   if (const char *e = getenv("CGFD_OVERLAP")) c->overlap = atoi(e);
   if (const char *e = getenv("CGFD_L2MODE")) c->l2mode = atoi(e);
+  if (const char *e = getenv("CGFD_TOPPAR")) c->toppar = atoi(e);
   {
     int lo = 0, hi = 0;
     CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -848,7 +850,8 @@ static int run_stage(cgfd_b200_ctx *c, StageArgs &P, int it, int ipair, int ista
     }
     e0 = c->ev[c->ev_used]; e1 = c->ev[c->ev_used + 1]; c->ev_used += 2;
   }
-  const bool two = c->overlap && halo_w;   // (running only the free-surface rows beside the interior kernel gains nothing: profiles/r1h)
+  // two streams: with a halo exchange to hide, or (toppar) just to run the latency-bound free-surface kernel beside the interior one
+  const bool two = (c->overlap && halo_w) || (c->toppar && c->free_top);
   cudaStream_t sb = two ? c->st2 : c->st;   // stream of the boundary phase
   int bnd[4][4], inner[4];
   const int nb = split_tiles(c, halo_w != nullptr, bnd, inner);
