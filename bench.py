@@ -298,7 +298,7 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        emit(out)
 
 
 def ncu_traffic(size):
@@ -370,10 +370,33 @@ def run_reference(args):
     if cb["value"] is not None:
         npts = SAMPLE[0] * SAMPLE[1] * SAMPLE[2]
         out["ms_per_step"] = round(cores * npts / (cb["value"] * 1e9) * 1e3, 3)
-    print(json.dumps(out), flush=True)
+    emit(out)
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Everything any library prints on fd 1 during the run (NCCL's version banner, ...) goes to stderr; the one JSON line is
+    written to the original stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, line)
+    else:
+        os.write(_REAL_STDOUT, line)
 
 
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=60)

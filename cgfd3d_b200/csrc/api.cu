@@ -769,44 +769,68 @@ static int split_tiles(const cgfd_b200_ctx *c, bool split, int bnd[4][4], int in
   return n;
 }
 
-// Launch plan of a tile rectangle (cached): z chunks so that the launch has at least `plan_waves` waves of resident blocks
-// with chunks no shorter than `plan_minchunk` rows, and the longest-job-first block order: blocks whose tile meets an x / y
-// PML slab run the PML copy of the loop body on every plane (~3x the time of a plain block-plane), so they go first.
+// Launch plan of a tile rectangle: z chunks so that the launch has at least `waves` waves of resident blocks with chunks no
+// shorter than `minchunk` rows, and the longest-job-first block order: blocks whose tile meets an x / y PML slab run the PML copy
+// of the loop body on every plane (~3x the time of a plain block-plane), so they go first. Pure host logic (also exported as
+// cgfd_b200_launch_plan for the CPU tests). pml_r[idim][iside] = {on, first index, last index} of the slab along its axis.
+static void compute_plan(const cgfd_grid_t &g, const int pml_r[2][2][3], int free_top, int blocks_per_sm, int waves, int minchunk,
+                         int zchunk_explicit, int lpt, const int rect[4], int *zchunk, std::vector<int> *order)
+{
+  *zchunk = 0; order->clear();
+  const int bx = rect[1] - rect[0], by = rect[3] - rect[2];
+  const int nk = (free_top ? g.nk2 - 4 : g.nk2) - g.nk1 + 1;
+  if (bx <= 0 || by <= 0 || nk <= 0) return;
+  int nzc = 1;
+  if (zchunk_explicit > 0) nzc = (nk + zchunk_explicit - 1) / zchunk_explicit;
+  else
+    while (nzc < nk && (long)bx * by * nzc < 148L * blocks_per_sm * waves && nk / (nzc + 1) >= minchunk) nzc++;
+  *zchunk = (nk + nzc - 1) / nzc;
+  nzc = (nk + *zchunk - 1) / *zchunk;
+  if (!lpt) return;
+  std::vector<int> fast;
+  for (int z = 0; z < nzc; z++)
+    for (int y = 0; y < by; y++)
+      for (int x = 0; x < bx; x++) {
+        const int i0 = g.ni1 + (rect[0] + x) * TILE_X, j0 = g.nj1 + (rect[2] + y) * TILE_Y;
+        bool pml = false;
+        for (int sd = 0; sd < 2; sd++) {
+          pml |= pml_r[0][sd][0] && i0 <= pml_r[0][sd][2] && i0 + TILE_X - 1 >= pml_r[0][sd][1];
+          pml |= pml_r[1][sd][0] && j0 <= pml_r[1][sd][2] && j0 + TILE_Y - 1 >= pml_r[1][sd][1];
+        }
+        (pml ? *order : fast).push_back((z * by + y) * bx + x);
+      }
+  order->insert(order->end(), fast.begin(), fast.end());
+}
 static const LaunchPlan *plan_for(cgfd_b200_ctx *c, const int rect[4])
 {
   std::array<int, 4> key = {rect[0], rect[1], rect[2], rect[3]};
   auto it = c->plans.find(key);
   if (it != c->plans.end()) return &it->second;
   LaunchPlan pl;
-  const cgfd_grid_t &g = c->g;
-  const int bx = rect[1] - rect[0], by = rect[3] - rect[2];
-  const int nk = (c->free_top ? g.nk2 - 4 : g.nk2) - g.nk1 + 1;
-  if (bx > 0 && by > 0 && nk > 0) {
-    int nzc = 1;
-    if (c->zchunk > 0) nzc = (nk + c->zchunk - 1) / c->zchunk;
-    else
-      while (nzc < nk && (long)bx * by * nzc < 148L * blocks_per_sm(c->med) * c->plan_waves && nk / (nzc + 1) >= c->plan_minchunk) nzc++;
-    pl.zchunk = (nk + nzc - 1) / nzc;
-    nzc = (nk + pl.zchunk - 1) / pl.zchunk;
-    if (c->plan_lpt) {
-      std::vector<int> slow, fast;
-      for (int z = 0; z < nzc; z++)
-        for (int y = 0; y < by; y++)
-          for (int x = 0; x < bx; x++) {
-            const int i0 = g.ni1 + (rect[0] + x) * TILE_X, j0 = g.nj1 + (rect[2] + y) * TILE_Y;
-            bool pml = false;
-            for (int sd = 0; sd < 2; sd++) {
-              const PmlFaceHost &fx = c->pml[0][sd], &fy = c->pml[1][sd];
-              pml |= fx.on && i0 <= fx.r[1] && i0 + TILE_X - 1 >= fx.r[0];
-              pml |= fy.on && j0 <= fy.r[3] && j0 + TILE_Y - 1 >= fy.r[2];
-            }
-            (pml ? slow : fast).push_back((z * by + y) * bx + x);
-          }
-      slow.insert(slow.end(), fast.begin(), fast.end());
-      if (upload(c, &pl.order, slow.data(), slow.size())) return nullptr;
-    }
+  int pml_r[2][2][3];
+  for (int d = 0; d < 2; d++) for (int sd = 0; sd < 2; sd++) {
+    const PmlFaceHost &f = c->pml[d][sd];
+    pml_r[d][sd][0] = f.on; pml_r[d][sd][1] = f.r[2 * d]; pml_r[d][sd][2] = f.r[2 * d + 1];
   }
+  std::vector<int> order;
+  compute_plan(c->g, pml_r, c->free_top, blocks_per_sm(c->med), c->plan_waves, c->plan_minchunk, c->zchunk, c->plan_lpt, rect, &pl.zchunk, &order);
+  if (!order.empty() && upload(c, &pl.order, order.data(), order.size())) return nullptr;
   return &(c->plans[key] = pl);
+}
+extern "C" int cgfd_b200_launch_plan(const cgfd_grid_t *g, const int pml_nlay[3][2], int free_top, int blocks_per_sm, const int rect[4],
+                                     int *zchunk, int *order, int capacity)
+{
+  if (!g || !pml_nlay || !rect || !zchunk) return -1;
+  int pml_r[2][2][3];
+  for (int d = 0; d < 2; d++) for (int sd = 0; sd < 2; sd++) {
+    const int a1 = d == 0 ? g->ni1 : g->nj1, a2 = d == 0 ? g->ni2 : g->nj2, nl = pml_nlay[d][sd];
+    pml_r[d][sd][0] = nl > 0; pml_r[d][sd][1] = sd == 0 ? a1 : a2 - nl; pml_r[d][sd][2] = sd == 0 ? a1 + nl : a2;
+  }
+  cgfd_b200_ctx defaults;
+  std::vector<int> ord;
+  compute_plan(*g, pml_r, free_top, blocks_per_sm, defaults.plan_waves, defaults.plan_minchunk, 0, 1, rect, zchunk, &ord);
+  if (order) for (size_t n = 0; n < ord.size() && (int)n < capacity; n++) order[n] = ord[n];
+  return (int)ord.size();
 }
 
 // Launch everything of stage `istage` of step `it`; level roles: icur -> (itmp, iend), ipre.

@@ -242,6 +242,13 @@ int  cgfd_b200_add_snapshot(cgfd_b200_ctx *ctx, int ncmps, const int *cmps, cons
 /* frames written so far for snapshot `id` (-1: unknown id) */
 int  cgfd_b200_snapshot_frames(cgfd_b200_ctx *ctx, int id);
 
+/* The launch plan of the interior kernel for the tile rectangle rect = {bx0, bx1, by0, by1} (tiles of 32 x 8 points counted from
+ * (ni1, nj1)); pure host logic, no GPU needed. pml_nlay[idim][iside] = layers of the CFS-PML on that face (0 = none). Returns the
+ * number of blocks, *zchunk = rows per z chunk, order[b] = (chunk * ntiles_y + tile_y) * ntiles_x + tile_x of the b-th block:
+ * tiles that meet an x / y PML slab first (longest job first). -1 on bad arguments. */
+int  cgfd_b200_launch_plan(const cgfd_grid_t *grid, const int pml_nlay[3][2], int free_top, int blocks_per_sm, const int rect[4],
+                           int *zchunk, int *order, int capacity);
+
 /* ---- measurement ----------------------------------------------------------------------------- */
 /* When enabled, every launch of the dominant (interior RHS + RK) kernel is bracketed by CUDA
  * events on its own stream; get_profile returns the accumulated milliseconds and launch counts. */

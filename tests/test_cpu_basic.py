@@ -64,3 +64,28 @@ def test_device_setup_matches_host_setup():
             np.testing.assert_array_equal(a.pml[k][q], b.pml[k][q])
     for n in ("matVx2Vz", "matVy2Vz", "matF2Vz"):
         np.testing.assert_allclose(b.mats[n], a.mats[n], rtol=1e-6, atol=1e-30)
+
+
+def test_launch_plan_longest_job_first():
+    """the block order of the interior kernel (pure host logic of the library): a permutation of tiles x z-chunks in which every
+    tile that meets an x / y PML slab comes before every tile that does not; chunks cover the rows below the free-surface rows"""
+    from cgfd3d_b200 import solver
+    ni, nj, nk, nl = 400, 400, 200, 10
+    grid = dict(nx=ni + 6, ny=nj + 6, nz=nk + 6, ni1=3, ni2=ni + 2, nj1=3, nj2=nj + 2, nk1=3, nk2=nk + 2)
+    ntx, nty = (ni + 31) // 32, (nj + 7) // 8
+    zchunk, order = solver.launch_plan(grid, ((nl, nl), (nl, nl), (nl, 0)), 1, (0, ntx, 0, nty))
+    nzc = -(-(nk - 4) // zchunk)
+    assert 16 <= zchunk <= 49 and len(order) == ntx * nty * nzc
+    assert sorted(order) == list(range(ntx * nty * nzc))
+
+    def is_pml(b):
+        x, y = b % ntx, (b // ntx) % nty
+        i0, j0 = 3 + 32 * x, 3 + 8 * y
+        return i0 <= 3 + nl or i0 + 31 >= ni + 2 - nl or j0 <= 3 + nl or j0 + 7 >= nj + 2 - nl
+    flags = [is_pml(b) for b in order]
+    first_fast = flags.index(False)
+    assert all(flags[:first_fast]) and not any(flags[first_fast:])
+    assert 0 < first_fast < len(order)
+    # no PML at all: natural order
+    zc2, order2 = solver.launch_plan(grid, ((0, 0), (0, 0), (0, 0)), 0, (0, ntx, 0, nty))
+    assert order2 == list(range(len(order2)))
