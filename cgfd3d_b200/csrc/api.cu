@@ -128,8 +128,8 @@ struct cgfd_b200_ctx {
   int gz = 0;                       // xi_y = xi_z = eta_x = eta_z == 0 at every physical point: GZ kernels (cgfd_dev.cuh)
   bool have_maps = false;
   int zchunk = 0;                   // explicit rows per z chunk (CGFD_ZCHUNK), 0 = chosen by plan_for()
-  int plan_waves = 16, plan_minchunk = 16, plan_lpt = 1;   // measured at 400x400x200: chunks of 14..28 rows within 0.5 %, 49 rows 2 % slower
-  std::map<std::array<int, 4>, struct LaunchPlan> plans;
+  int plan_waves = 16, plan_minchunk = 16, plan_lpt = 2;   // measured at 400x400x200: chunks of 14..28 rows within 0.5 %, 49 rows 2 % slower
+  std::map<std::array<int, 5>, struct LaunchPlan> plans;
   int ipre = 0, ia = 1, ib = 2, iend = 3;   // roles of the four level buffers
   float *metric[NMETRIC];           // shifted pointers into metric_blk
   float *media[MAX_MEDIA];
@@ -773,8 +773,12 @@ static int split_tiles(const cgfd_b200_ctx *c, bool split, int bnd[4][4], int in
 // shorter than `minchunk` rows, and the longest-job-first block order: blocks whose tile meets an x / y PML slab run the PML copy
 // of the loop body on every plane (~3x the time of a plain block-plane), so they go first. Pure host logic (also exported as
 // cgfd_b200_launch_plan for the CPU tests). pml_r[idim][iside] = {on, first index, last index} of the slab along its axis.
+// lpt = 2 (default): within each class the tiles are taken in bands of one wave (148 x blocks_per_sm tiles); a band runs through
+// its z chunks in the direction the kernel marches (dz = 1 upwards, 0 downwards) before the next band starts, so that the
+// 4 planes a chunk re-reads for its zeta queue are the ones the previous chunk of the same tile has just fetched (L2 hits
+// instead of a second DRAM read). lpt = 1: chunk-major order.
 static void compute_plan(const cgfd_grid_t &g, const int pml_r[2][2][3], int free_top, int blocks_per_sm, int waves, int minchunk,
-                         int zchunk_explicit, int lpt, const int rect[4], int *zchunk, std::vector<int> *order)
+                         int zchunk_explicit, int lpt, int dz, const int rect[4], int *zchunk, std::vector<int> *order)
 {
   *zchunk = 0; order->clear();
   const int bx = rect[1] - rect[0], by = rect[3] - rect[2];
@@ -787,23 +791,30 @@ static void compute_plan(const cgfd_grid_t &g, const int pml_r[2][2][3], int fre
   *zchunk = (nk + nzc - 1) / nzc;
   nzc = (nk + *zchunk - 1) / *zchunk;
   if (!lpt) return;
-  std::vector<int> fast;
-  for (int z = 0; z < nzc; z++)
-    for (int y = 0; y < by; y++)
-      for (int x = 0; x < bx; x++) {
-        const int i0 = g.ni1 + (rect[0] + x) * TILE_X, j0 = g.nj1 + (rect[2] + y) * TILE_Y;
-        bool pml = false;
-        for (int sd = 0; sd < 2; sd++) {
-          pml |= pml_r[0][sd][0] && i0 <= pml_r[0][sd][2] && i0 + TILE_X - 1 >= pml_r[0][sd][1];
-          pml |= pml_r[1][sd][0] && j0 <= pml_r[1][sd][2] && j0 + TILE_Y - 1 >= pml_r[1][sd][1];
-        }
-        (pml ? *order : fast).push_back((z * by + y) * bx + x);
+  std::vector<int> cls[2];   // tiles (y * bx + x): [0] meet an x / y PML slab, [1] do not
+  for (int y = 0; y < by; y++)
+    for (int x = 0; x < bx; x++) {
+      const int i0 = g.ni1 + (rect[0] + x) * TILE_X, j0 = g.nj1 + (rect[2] + y) * TILE_Y;
+      bool pml = false;
+      for (int sd = 0; sd < 2; sd++) {
+        pml |= pml_r[0][sd][0] && i0 <= pml_r[0][sd][2] && i0 + TILE_X - 1 >= pml_r[0][sd][1];
+        pml |= pml_r[1][sd][0] && j0 <= pml_r[1][sd][2] && j0 + TILE_Y - 1 >= pml_r[1][sd][1];
       }
-  order->insert(order->end(), fast.begin(), fast.end());
+      cls[pml ? 0 : 1].push_back(y * bx + x);
+    }
+  for (int cl = 0; cl < 2; cl++) {
+    const size_t nt = cls[cl].size();
+    const size_t band = (lpt >= 2) ? (size_t)148 * blocks_per_sm : (nt ? nt : 1);
+    for (size_t b0 = 0; b0 < nt; b0 += band)
+      for (int zi = 0; zi < nzc; zi++) {
+        const int z = (lpt >= 2 && dz == 0) ? nzc - 1 - zi : zi;
+        for (size_t t = b0; t < nt && t < b0 + band; t++) order->push_back(z * by * bx + cls[cl][t]);
+      }
+  }
 }
-static const LaunchPlan *plan_for(cgfd_b200_ctx *c, const int rect[4])
+static const LaunchPlan *plan_for(cgfd_b200_ctx *c, const int rect[4], int dz)
 {
-  std::array<int, 4> key = {rect[0], rect[1], rect[2], rect[3]};
+  std::array<int, 5> key = {rect[0], rect[1], rect[2], rect[3], dz};
   auto it = c->plans.find(key);
   if (it != c->plans.end()) return &it->second;
   LaunchPlan pl;
@@ -813,11 +824,11 @@ static const LaunchPlan *plan_for(cgfd_b200_ctx *c, const int rect[4])
     pml_r[d][sd][0] = f.on; pml_r[d][sd][1] = f.r[2 * d]; pml_r[d][sd][2] = f.r[2 * d + 1];
   }
   std::vector<int> order;
-  compute_plan(c->g, pml_r, c->free_top, blocks_per_sm(c->med), c->plan_waves, c->plan_minchunk, c->zchunk, c->plan_lpt, rect, &pl.zchunk, &order);
+  compute_plan(c->g, pml_r, c->free_top, blocks_per_sm(c->med), c->plan_waves, c->plan_minchunk, c->zchunk, c->plan_lpt, dz, rect, &pl.zchunk, &order);
   if (!order.empty() && upload(c, &pl.order, order.data(), order.size())) return nullptr;
   return &(c->plans[key] = pl);
 }
-extern "C" int cgfd_b200_launch_plan(const cgfd_grid_t *g, const int pml_nlay[3][2], int free_top, int blocks_per_sm, const int rect[4],
+extern "C" int cgfd_b200_launch_plan(const cgfd_grid_t *g, const int pml_nlay[3][2], int free_top, int blocks_per_sm, int dz, const int rect[4],
                                      int *zchunk, int *order, int capacity)
 {
   if (!g || !pml_nlay || !rect || !zchunk) return -1;
@@ -828,7 +839,7 @@ extern "C" int cgfd_b200_launch_plan(const cgfd_grid_t *g, const int pml_nlay[3]
   }
   cgfd_b200_ctx defaults;
   std::vector<int> ord;
-  compute_plan(*g, pml_r, free_top, blocks_per_sm, defaults.plan_waves, defaults.plan_minchunk, 0, 1, rect, zchunk, &ord);
+  compute_plan(*g, pml_r, free_top, blocks_per_sm, defaults.plan_waves, defaults.plan_minchunk, 0, defaults.plan_lpt, dz, rect, zchunk, &ord);
   if (order) for (size_t n = 0; n < ord.size() && (int)n < capacity; n++) order[n] = ord[n];
   return (int)ord.size();
 }
@@ -883,7 +894,7 @@ static int run_stage(cgfd_b200_ctx *c, StageArgs &P, int it, int ipair, int ista
   // ---- boundary phase
   launch_top(c->med, P, dir, kind, sb, &nl);
   for (int n = 0; n < nb; n++) {
-    const LaunchPlan *pl = plan_for(c, bnd[n]);
+    const LaunchPlan *pl = plan_for(c, bnd[n], dir[2]);
     if (!pl) return 1;
     P.order = pl->order;
     launch_main(c->med, P, mp, dir, kind, c->gz, pl->zchunk, bnd[n], sb, nullptr, nullptr, &nl);
@@ -899,7 +910,7 @@ static int run_stage(cgfd_b200_ctx *c, StageArgs &P, int it, int ipair, int ista
   if (two) CK(cudaEventRecord(c->ev_join, c->st2));
   // ---- interior phase
   {
-    const LaunchPlan *pl = plan_for(c, inner);
+    const LaunchPlan *pl = plan_for(c, inner, dir[2]);
     if (!pl) return 1;
     P.order = pl->order;
     launch_main(c->med, P, mp, dir, kind, c->gz, pl->zchunk, inner, c->st, e0, e1, &nl);
@@ -1078,7 +1089,7 @@ extern "C" int cgfd_b200_onestage(cgfd_b200_ctx *c, int it, int ipair, int istag
   const int whole[4] = {0, c->ntx, 0, c->nty};
   launch_top(c->med, P, dir, KIND_THIRD, c->st, &nl);
   {
-    const LaunchPlan *pl = plan_for(c, whole);
+    const LaunchPlan *pl = plan_for(c, whole, dir[2]);
     if (!pl) return 1;
     P.order = pl->order;
     launch_main(c->med, P, &maps, dir, KIND_THIRD, c->gz, pl->zchunk, whole, c->st, nullptr, nullptr, &nl);

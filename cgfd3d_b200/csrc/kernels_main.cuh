@@ -299,8 +299,11 @@ __global__ void __launch_bounds__(TX *TY, Lay<MED>::BLOCKS) k_main_tma(const Sta
 // =============================================================================================
 // free-surface rows: k in [nk2-3, nk2], one thread per point, neighbours straight from L1/L2
 // =============================================================================================
+#ifndef CGFD_TOP_BLOCKS
+#define CGFD_TOP_BLOCKS 3   // resident blocks per SM the free-surface kernel is compiled for (168 registers at 3)
+#endif
 template <int DX, int DY, int DZ, int KIND, int MED>
-__global__ void __launch_bounds__(128, 3) k_top(const StageArgs P)
+__global__ void __launch_bounds__(128, CGFD_TOP_BLOCKS) k_top(const StageArgs P)
 {
   // 32 x 4 points per block: the eta neighbours of a row are mostly rows of the same block (L1 hits)
   const int i = P.ni1 + blockIdx.x * 32 + threadIdx.x;

@@ -74,7 +74,7 @@ def load_library():
     L.cgfd_b200_snapshot_frames.argtypes = [vp, ci]
     L.cgfd_b200_dd_set_points.argtypes = [vp, ci, C.POINTER(C.c_int64), ci, ci, ci, ci]
     L.cgfd_b200_dd_load_block.argtypes = [vp, ci, ci, fp, fp]
-    L.cgfd_b200_launch_plan.argtypes = [C.POINTER(abi.Grid), C.POINTER((ci * 2) * 3), ci, ci, C.POINTER(ci * 4), C.POINTER(ci), C.POINTER(ci), ci]
+    L.cgfd_b200_launch_plan.argtypes = [C.POINTER(abi.Grid), C.POINTER((ci * 2) * 3), ci, ci, ci, C.POINTER(ci * 4), C.POINTER(ci), C.POINTER(ci), ci]
     L.cgfd_b200_metric_from_coords.argtypes = [ci, C.POINTER(abi.Grid), fp, fp, fp, ci, C.POINTER(ci), fp, C.POINTER(fp * 10)]
     _lib = L
     return L
@@ -254,18 +254,18 @@ def metric_from_coords(grid: dict, x, y, z, fd_indx=None, fd_coef=None, device=0
     return out
 
 
-def launch_plan(grid: dict, pml_nlay, free_top: int, rect, blocks_per_sm: int = 2):
+def launch_plan(grid: dict, pml_nlay, free_top: int, rect, blocks_per_sm: int = 2, dz: int = 1):
     """(zchunk, order) of the interior kernel for the tile rectangle rect = (bx0, bx1, by0, by1); pure host logic of the library."""
     L = load_library()
     g = abi.Grid(**grid)
     nl = ((C.c_int * 2) * 3)(*[(C.c_int * 2)(*row) for row in pml_nlay])
     rc = (C.c_int * 4)(*rect)
     zc = C.c_int(0)
-    n = L.cgfd_b200_launch_plan(C.byref(g), C.byref(nl), free_top, blocks_per_sm, C.byref(rc), C.byref(zc), None, 0)
+    n = L.cgfd_b200_launch_plan(C.byref(g), C.byref(nl), free_top, blocks_per_sm, dz, C.byref(rc), C.byref(zc), None, 0)
     if n < 0:
         raise CgfdError("launch_plan: bad arguments")
     order = (C.c_int * max(n, 1))()
-    L.cgfd_b200_launch_plan(C.byref(g), C.byref(nl), free_top, blocks_per_sm, C.byref(rc), C.byref(zc), order, n)
+    L.cgfd_b200_launch_plan(C.byref(g), C.byref(nl), free_top, blocks_per_sm, dz, C.byref(rc), C.byref(zc), order, n)
     return zc.value, list(order)[:n]
 
 

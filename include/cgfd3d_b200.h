@@ -245,8 +245,10 @@ int  cgfd_b200_snapshot_frames(cgfd_b200_ctx *ctx, int id);
 /* The launch plan of the interior kernel for the tile rectangle rect = {bx0, bx1, by0, by1} (tiles of 32 x 8 points counted from
  * (ni1, nj1)); pure host logic, no GPU needed. pml_nlay[idim][iside] = layers of the CFS-PML on that face (0 = none). Returns the
  * number of blocks, *zchunk = rows per z chunk, order[b] = (chunk * ntiles_y + tile_y) * ntiles_x + tile_x of the b-th block:
- * tiles that meet an x / y PML slab first (longest job first). -1 on bad arguments. */
-int  cgfd_b200_launch_plan(const cgfd_grid_t *grid, const int pml_nlay[3][2], int free_top, int blocks_per_sm, const int rect[4],
+ * tiles that meet an x / y PML slab first (longest job first); within each class bands of one wave of tiles run through their z chunks
+ * in the direction of the kernel's march (dz = the zeta direction index of the stage's operator) before the next band starts.
+ * -1 on bad arguments. */
+int  cgfd_b200_launch_plan(const cgfd_grid_t *grid, const int pml_nlay[3][2], int free_top, int blocks_per_sm, int dz, const int rect[4],
                            int *zchunk, int *order, int capacity);
 
 /* ---- measurement ----------------------------------------------------------------------------- */

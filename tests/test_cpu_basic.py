@@ -86,6 +86,15 @@ def test_launch_plan_longest_job_first():
     first_fast = flags.index(False)
     assert all(flags[:first_fast]) and not any(flags[first_fast:])
     assert 0 < first_fast < len(order)
-    # no PML at all: natural order
-    zc2, order2 = solver.launch_plan(grid, ((0, 0), (0, 0), (0, 0)), 0, (0, ntx, 0, nty))
+    # within a band of one wave (296 tiles) the chunks of a tile follow each other in the direction of the march
+    ntile = ntx * nty
+    for dz in (1, 0):
+        _, od = solver.launch_plan(grid, ((nl, nl), (nl, nl), (nl, 0)), 1, (0, ntx, 0, nty), dz=dz)
+        assert sorted(od) == list(range(ntile * nzc))
+        pos = {b: n for n, b in enumerate(od)}
+        t = od[first_fast] % ntile
+        seq = [pos[z * ntile + t] for z in (range(nzc) if dz else range(nzc - 1, -1, -1))]
+        assert seq == sorted(seq) and seq[1] - seq[0] <= 296
+    # no PML, one chunk-major band when there are fewer tiles than one wave
+    zc2, order2 = solver.launch_plan(dict(grid, nx=70, ni2=66), ((0, 0), (0, 0), (0, 0)), 0, (0, 2, 0, nty))
     assert order2 == list(range(len(order2)))
