@@ -28,7 +28,9 @@ if os.path.isfile(lf):
     for k, v in sorted(agg.items(), key=lambda x: -x[1][1]):
         out.append("%-72s n=%4d total=%9.3f ms avg=%8.4f ms share=%5.1f%%" % (k, v[0], v[1], v[1] / v[0], 100 * v[1] / tot))
         fam[k.split("<")[0].replace("void ", "").split("(")[0]] += v[1]
-    out.append("# by kernel family")
+    out.append("# by kernel family (the list covers the whole bench.py process: k_any_nonzero = grid-class check at create time,")
+    out.append("# k_repitch = set/get_wavefield of the e2e leg, k_pack_box = snapshot frames of the e2e leg; a device-resident step is")
+    out.append("# 4 x (k_top + k_main_tma + k_src_inject) + k_pg + k_record)")
     for k, v in sorted(fam.items(), key=lambda x: -x[1]):
         out.append("%-40s total=%9.3f ms share=%5.1f%%" % (k, v, 100 * v / tot))
 want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread", "launch__grid_size",
