@@ -95,6 +95,12 @@ def test_launch_plan_longest_job_first():
         t = od[first_fast] % ntile
         seq = [pos[z * ntile + t] for z in (range(nzc) if dz else range(nzc - 1, -1, -1))]
         assert seq == sorted(seq) and seq[1] - seq[0] <= 296
+    # the one-tile-wide rectangles of the boundary phase (tiles next to an inter-rank face) are permutations too
+    for rect in ((0, 1, 0, nty), (ntx - 1, ntx, 0, nty), (1, ntx - 1, 0, 1), (1, ntx - 1, nty - 1, nty)):
+        for dz in (0, 1):
+            zc, od = solver.launch_plan(grid, ((0, nl), (nl, 0), (nl, 0)), 1, rect, dz=dz)
+            nb = (rect[1] - rect[0]) * (rect[3] - rect[2]) * -(-(nk - 4) // zc)
+            assert sorted(od) == list(range(nb)), (rect, dz)
     # no PML, one chunk-major band when there are fewer tiles than one wave
     zc2, order2 = solver.launch_plan(dict(grid, nx=70, ni2=66), ((0, 0), (0, 0), (0, 0)), 0, (0, 2, 0, nty))
     assert order2 == list(range(len(order2)))
