@@ -65,3 +65,45 @@ def test_port_run_matches_reference_driver():
     for c in range(3):
         for ip in range(len(rec)):
             assert util.rel_l2(recp[:, c, ip], recr[:, c, ip]) <= 1e-5
+
+
+@need
+def test_host_metric_restatement_matches_reference():
+    """hostsetup.metric_from_coords (numpy, used to build every synthetic problem) against the reference's gd_curv_metric_cal
+    (forward/gd_t.c:190-402) on a hill grid with perturbed x-y lines: bit-identical, ghosts included."""
+    from cgfd3d_b200 import hostsetup as hs
+    prob = util.small_problem(ni=21, nj=18, nk=15)
+    x, y, z = (a.copy() for a in prob.coords)
+    rng = np.random.default_rng(4)
+    x += rng.uniform(-8, 8, x.shape).astype(np.float32)
+    y += rng.uniform(-8, 8, y.shape).astype(np.float32)
+    ref = ref_flat.RefSolver(prob).metric_from_coords(x, y, z)
+    mine = hs.metric_from_coords(x, y, z)
+    assert float(np.abs(ref[2]).max()) > 0
+    for m in range(10):
+        np.testing.assert_array_equal(mine[m], ref[m])
+
+
+@need
+def test_reference_dd_sources_and_graves_qs_run_on_cpu():
+    """the oracle-side plumbing of the two add-ons the GPU tests compare against: distributed sources fed block by block from
+    files (src_dd_accit_loadstf) give the same run whatever the block size, and Graves' Qs really attenuates"""
+    nt = 12
+    prob = util.small_problem(ni=22, nj=20, nk=18, pml_layers=4, nt_total=nt, src=None, seed=8)
+    pts = [(7 + q % 4, 8 + q // 4, prob.nk - 5 - (q % 4)) for q in range(8)]
+    indx = np.array([prob.iptr(*p) for p in pts], np.int64)
+    rng = np.random.default_rng(1)
+    mij = (1e15 * rng.uniform(-1, 1, (nt, 4, len(pts), 6))).astype(np.float32)
+    runs = []
+    for nb in (5, 12):
+        R = ref_flat.RefSolver(prob)
+        R.set_dd(indx, None, mij, nb)
+        runs.append(R.run(nt)[0])
+    assert float(np.abs(runs[0][0]).max()) > 0
+    np.testing.assert_array_equal(runs[0], runs[1])
+    prob.graves_Qs = np.full((prob.nz, prob.ny, prob.nx), 20.0, np.float32)
+    prob.graves_Qs_freq = 2.0
+    R = ref_flat.RefSolver(prob)
+    R.set_dd(indx, None, mij, 12)
+    wq = R.run(nt)[0]
+    assert 0 < float(np.abs(wq[2]).max()) < float(np.abs(runs[0][2]).max())
