@@ -12,6 +12,8 @@
  *   rhs_cfspml     forward/sv_curv_col_el_iso.c:644-1146  ADE CFS-PML, 6 faces
  *   rhs_src        forward/sv_curv_col_el.c:311-479       point / Gaussian force and moment sources
  *   surface force  forward/src_t.c:153-314
+ *   rhs_srcdd      forward/sv_curv_col_el.c:486-632       distributed (finite-fault) sources, added at the point
+ *   graves_Qs      forward/sv_curv_col_el.c:638-666       constant-Q attenuation of w_end after the last stage
  *   stage loop     forward/drv_rk_curv_col.c:167-544      RK4 axpy for wavefield and PML aux, level swap
  *
  * Parity of this restatement is PINNED against the reference itself: tests/test_cpu_oracle.py compares
@@ -48,6 +50,10 @@ typedef struct {
   face_t f[3][2];
   float *mvx, *mvy, *mf;
   float *srcsl[6]; /* TxSrc TySrc TzSrc VxSrc VySrc VzSrc */
+  /* Graves' attenuation: Qs array (NULL = off), forward/sv_curv_col_el.c:638-666 */
+  float *Qs; float Qs_freq;
+  /* distributed sources (forward/src_t.h:94-126): whole time functions in memory */
+  int dd_n, dd_nt; size_t *dd_indx; float *dd_vi, *dd_mij;
 } orc_t;
 
 static float *dupf(const float *s, size_t n)
@@ -66,6 +72,7 @@ void *cgfd_oracle_create(const cgfd_problem_t *p)
   o->L = o->nx; o->S = (long)o->nx * o->ny; o->V = (size_t)o->S * o->nz;
   for (int m = 0; m < 10; m++) o->metric[m] = dupf(p->metric[m], o->V);
   o->lam = dupf(p->media[0], o->V); o->mu = dupf(p->media[1], o->V); o->slw = dupf(p->media[2], o->V);
+  if (p->graves_Qs) { o->Qs = dupf(p->graves_Qs, o->V); o->Qs_freq = p->graves_Qs_freq; }
   for (int l = 0; l < 4; l++) o->lev[l] = dupf(NULL, o->V * 9);
   const cgfd_grid_t *g = &p->grid;
   for (int d = 0; d < 3; d++) for (int s = 0; s < 2; s++) {
@@ -97,6 +104,19 @@ void *cgfd_oracle_create(const cgfd_problem_t *p)
   s->Mxz = dupf(q->Mxz, nt); s->Myz = dupf(q->Myz, nt); s->Mxy = dupf(q->Mxy, nt);
   s->Fx_rate = dupf(q->Fx_rate, nr); s->Fy_rate = dupf(q->Fy_rate, nr); s->Fz_rate = dupf(q->Fz_rate, nr);
   return o;
+}
+
+/* distributed sources: vi [nt][4][n][3] and / or mij [nt][4][n][6] (NULL = not active); sv_curv_col_el_rhs_srcdd,
+ * forward/sv_curv_col_el.c:486-632 (steps >= nt get no dd source, like dd_is_valid = 0 past dd_max_nt) */
+int cgfd_oracle_set_dd(void *h, int n, const int64_t *indx, int nt, const float *vi, const float *mij)
+{
+  orc_t *o = h;
+  o->dd_n = n; o->dd_nt = nt;
+  o->dd_indx = malloc(sizeof(size_t) * n);
+  for (int q = 0; q < n; q++) o->dd_indx[q] = (size_t)indx[q];
+  o->dd_vi = vi ? dupf(vi, (size_t)nt * 4 * n * 3) : NULL;
+  o->dd_mij = mij ? dupf(mij, (size_t)nt * 4 * n * 6) : NULL;
+  return 0;
 }
 
 size_t cgfd_oracle_pml_aux_size(void *h, int d, int s) { orc_t *o = h; return o->f[d][s].on ? o->f[d][s].siz * 9 : 0; }
@@ -416,6 +436,22 @@ static void onestage(orc_t *o, const float *w, float *h, int it, int ipair, int 
   if (o->p.free_top) { rhs_timg(o, w, h, &op); rhs_vlow(o, w, h, &op); }
   rhs_cfspml(o, w, h, &op, aux_cur_level);
   if (o->p.src.total_number > 0) rhs_src(o, h, it, istage);
+  if (o->dd_n > 0 && it < o->dd_nt) {
+    /* sv_curv_col_el_rhs_srcdd: hV += vi * slw / J ; hT -= mij * (1 / J), table order xx yy zz yz xz xy */
+    static const int TC[6] = {3, 4, 5, 6, 7, 8};   /* Txx Tyy Tzz Tyz Txz Txy in wavefield order */
+    const size_t row = ((size_t)it * 4 + istage) * o->dd_n;
+    for (int q = 0; q < o->dd_n; q++) {
+      size_t p = o->dd_indx[q];
+      if (o->dd_vi) {
+        float Vw = o->slw[p] / o->metric[JAC][p];
+        for (int c = 0; c < 3; c++) h[c * o->V + p] += o->dd_vi[(row + q) * 3 + c] * Vw;
+      }
+      if (o->dd_mij) {
+        float rj = 1.0 / o->metric[JAC][p];
+        for (int c = 0; c < 6; c++) h[TC[c] * o->V + p] -= o->dd_mij[(row + q) * 6 + c] * rj;
+      }
+    }
+  }
 }
 
 int cgfd_oracle_onestage(void *hd, int it, int ipair, int istage, const float *w_cur, float *rhs)
@@ -451,6 +487,16 @@ int cgfd_oracle_run(void *hd, int nsteps, float *w, int nrec, const int64_t *rec
       float a = fd->rk_a[s] * o->p.dt, b = fd->rk_b[s] * o->p.dt;
       if (s < CGFD_NUM_STAGES - 1) axpy_set(tmp, pre, a, rhs, n);
       if (s == 0) axpy_set(end, pre, b, rhs, n); else axpy_add(end, b, rhs, n);
+      if (s == CGFD_NUM_STAGES - 1 && o->Qs) {
+        /* sv_curv_col_el_graves_Qs (forward/sv_curv_col_el.c:638-666, called at forward/drv_rk_curv_col.c:413-416) */
+        const cgfd_grid_t *g = &o->p.grid;
+        float coef = -3.14159265358979323846264338327950288419716939937510 * o->Qs_freq * o->p.dt;
+        for (int c = 0; c < 9; c++)
+          for (int k = g->nk1; k <= g->nk2; k++) for (int j = g->nj1; j <= g->nj2; j++) for (int i = g->ni1; i <= g->ni2; i++) {
+            size_t p = i + j * o->L + k * o->S;
+            end[c * o->V + p] *= expf(coef / o->Qs[p]);
+          }
+      }
       for (int d = 0; d < 3; d++) for (int q = 0; q < 2; q++) {
         face_t *f = &o->f[d][q];
         if (!f->on) continue;

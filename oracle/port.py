@@ -28,6 +28,7 @@ def lib():
         L.cgfd_oracle_set_pml_aux.argtypes = [C.c_void_p, C.c_int, C.c_int, fptr]
         L.cgfd_oracle_get_pml_aux.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, fptr]
         L.cgfd_oracle_onestage.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, fptr, fptr]
+        L.cgfd_oracle_set_dd.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.c_int, fptr, fptr]
         L.cgfd_oracle_run.argtypes = [C.c_void_p, C.c_int, fptr, C.c_int, C.POINTER(C.c_int64), fptr, C.POINTER(C.c_double)]
         _lib = L
     return _lib
@@ -63,6 +64,16 @@ class PortSolver:
 
     def get_pml_aux_rhs(self, idim, iside):
         return self.get_pml_aux(idim, iside, 2)
+
+    def set_dd(self, indx, vi, mij):
+        """distributed sources: vi [nt][4][n][3] and / or mij [nt][4][n][6] (None = not active)"""
+        indx = np.ascontiguousarray(indx, np.int64)
+        nt = (vi if vi is not None else mij).shape[0]
+        vi = None if vi is None else np.ascontiguousarray(vi, np.float32)
+        mij = None if mij is None else np.ascontiguousarray(mij, np.float32)
+        null = fptr()
+        assert lib().cgfd_oracle_set_dd(self.h, len(indx), indx.ctypes.data_as(C.POINTER(C.c_int64)), nt,
+                                        _f(vi) if vi is not None else null, _f(mij) if mij is not None else null) == 0
 
     def onestage(self, it, ipair, istage, w_cur):
         w_cur = np.ascontiguousarray(w_cur, np.float32)

@@ -101,9 +101,24 @@ def test_reference_dd_sources_and_graves_qs_run_on_cpu():
         runs.append(R.run(nt)[0])
     assert float(np.abs(runs[0][0]).max()) > 0
     np.testing.assert_array_equal(runs[0], runs[1])
-    prob.graves_Qs = np.full((prob.nz, prob.ny, prob.nx), 20.0, np.float32)
+    # the restatement of the dd injection
+    P = port.PortSolver(prob)
+    P.set_dd(indx, None, mij)
+    wp = P.run(nt)[0]
+    assert max(util.rel_l2(wp[c], runs[0][c]) for c in range(9)) <= 2e-6
+    # Graves' Qs on top of it: reference and restatement, and it really attenuates
+    vi = (1e9 * rng.uniform(-1, 1, (nt, 4, len(pts), 3))).astype(np.float32)
+    prob.graves_Qs = rng.uniform(15.0, 60.0, (prob.nz, prob.ny, prob.nx)).astype(np.float32)
     prob.graves_Qs_freq = 2.0
     R = ref_flat.RefSolver(prob)
-    R.set_dd(indx, None, mij, 12)
+    R.set_dd(indx, vi, mij, 5)
     wq = R.run(nt)[0]
-    assert 0 < float(np.abs(wq[2]).max()) < float(np.abs(runs[0][2]).max())
+    P = port.PortSolver(prob)
+    P.set_dd(indx, vi, mij)
+    wpq = P.run(nt)[0]
+    assert max(util.rel_l2(wpq[c], wq[c]) for c in range(9)) <= 2e-6
+    prob.graves_Qs = None
+    R = ref_flat.RefSolver(prob)
+    R.set_dd(indx, vi, mij, 5)
+    w0 = R.run(nt)[0]
+    assert 0 < float(np.abs(wq[2]).max()) < float(np.abs(w0[2]).max())
