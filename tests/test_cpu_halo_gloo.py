@@ -1,4 +1,4 @@
-"""world_size-2 (and 4) gloo runs of the x-y halo exchange on CPU: the strips come from the library's own halo plan
+"""world_size-2 (3, 4 and 8) gloo runs of the x-y halo exchange on CPU: the strips come from the library's own halo plan
 (cgfd_b200_halo_plan, the code the NCCL path uses), the transport is torch.distributed gloo send/recv.
 After the exchange every ghost strip an operator needs must equal the neighbour's physical values."""
 import os
@@ -85,7 +85,7 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("px,py", [(2, 1), (1, 2), (2, 2)])
+@pytest.mark.parametrize("px,py", [(2, 1), (1, 2), (2, 2), (3, 1), (4, 2)])   # (4, 2) = the 8-GPU process grid: ranks with neighbours on both x sides
 def test_halo_exchange_gloo(px, py):
     world = px * py
     ctx = mp.get_context("spawn")
