@@ -299,6 +299,9 @@ __global__ void __launch_bounds__(TX *TY, Lay<MED>::BLOCKS) k_main_tma(const Sta
 // =============================================================================================
 // free-surface rows: k in [nk2-3, nk2], one thread per point, neighbours straight from L1/L2
 // =============================================================================================
+#ifndef CGFD_TOP_SKIP
+#define CGFD_TOP_SKIP 0
+#endif
 #ifndef CGFD_TOP_BLOCKS
 #define CGFD_TOP_BLOCKS 3   // resident blocks per SM the free-surface kernel is compiled for (168 registers at 3)
 #endif
@@ -324,10 +327,26 @@ __global__ void __launch_bounds__(128, CGFD_TOP_BLOCKS) k_top(const StageArgs P)
     if (KIND != KIND_FIRST) pv[c] = __ldg(P.pre + c * V + p);
     if (KIND == KIND_LAST) ev[c] = P.end[c * V + p];
   }
+#if CGFD_TOP_SKIP
+  // EXPERIMENT (build switch, off by default, not yet validated on the GPU): in the rows where the traction image replaces the
+  // momentum RHS, the 18 plain derivatives of the stress components are only needed by the PML terms - skip their 90 loads at
+  // every point outside the PML slabs.
+  bool skip_stress = (k >= P.nk2 - (FZ + 4));
+#pragma unroll
+  for (int ax = 0; ax < 3; ax++)
+#pragma unroll
+    for (int sd = 0; sd < 2; sd++) {
+      const PmlFaceDev &F = P.pml[ax][sd];
+      if (F.on && i >= F.i1 && i <= F.i2 && j >= F.j1 && j <= F.j2 && k >= F.k1 && k <= F.k2) skip_stress = false;
+    }
+#else
+  constexpr bool skip_stress = false;
+#endif
 #pragma unroll
   for (int c = 0; c < 9; c++) {
     const float *w = P.cur + c * V + p;
     cur[c] = __ldg(w);
+    if (c >= 3 && skip_stress) { d.x[c] = d.y[c] = d.z[c] = 0.0f; continue; }
     d.x[c] = cx[0] * __ldg(w + FX) + cx[1] * __ldg(w + FX + 1) + cx[2] * __ldg(w + FX + 2) + cx[3] * __ldg(w + FX + 3)
            + cx[4] * __ldg(w + FX + 4);
     d.y[c] = cy[0] * __ldg(w + (FY + 0) * (long)L) + cy[1] * __ldg(w + (FY + 1) * (long)L)
