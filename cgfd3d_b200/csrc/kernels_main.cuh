@@ -139,6 +139,25 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
     for (int c = 0; c < 9; c++) qn[c] = __ldg(w + c * P.siz_vol);
   }
   if (PML && C.active && it + 1 < nplanes) pml_prefetch<KIND>(P, C.i, C.j, k + DIR);
+#if CGFD_VIS_PREFETCH
+  // EXPERIMENT (build switch, off by default, not yet validated on the GPU): the memory variables and Y arrays of the next
+  // plane requested into L2 by the first lane of every warp (one 128-byte line = the warp's 32 points per array and level)
+  if constexpr (MED == MED_VIS) {
+    if (C.active && C.tx == 0 && it + 1 < nplanes) {
+      const size_t pn = (size_t)(k + DIR) * P.siz_slice + C.pij;
+      for (int n = 0; n < P.nmaxwell; n++) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.media[3 + n] + pn));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.media[3 + P.nmaxwell + n] + pn));
+        for (int q = 0; q < 6; q++) {
+          const size_t o = (size_t)(9 + 6 * n + q) * P.siz_vol + pn;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(P.cur + o));
+          if (KIND != KIND_FIRST) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.pre + o));
+          if (KIND == KIND_LAST) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.end + o));
+        }
+      }
+    }
+  }
+#endif
   // Graves' attenuation factor of this point (last stage only; requested before the wait below so that it is there in time)
   float qatt = 1.0f;
   if (KIND == KIND_LAST && P.qatt && C.active) qatt = __ldg(P.qatt + (size_t)k * P.siz_slice + C.pij);
@@ -299,6 +318,9 @@ __global__ void __launch_bounds__(TX *TY, Lay<MED>::BLOCKS) k_main_tma(const Sta
 // =============================================================================================
 // free-surface rows: k in [nk2-3, nk2], one thread per point, neighbours straight from L1/L2
 // =============================================================================================
+#ifndef CGFD_VIS_PREFETCH
+#define CGFD_VIS_PREFETCH 0
+#endif
 #ifndef CGFD_TOP_SKIP
 #define CGFD_TOP_SKIP 0
 #endif
