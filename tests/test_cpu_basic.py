@@ -104,3 +104,28 @@ def test_launch_plan_longest_job_first():
     # no PML, one chunk-major band when there are fewer tiles than one wave
     zc2, order2 = solver.launch_plan(dict(grid, nx=70, ni2=66), ((0, 0), (0, 0), (0, 0)), 0, (0, 2, 0, nty))
     assert order2 == list(range(len(order2)))
+
+
+def test_bench_rank_problems_for_the_8_gpu_grid():
+    """bench.build_rank_problem on the 4x2 process grid of the 8-GPU run (small blocks, numpy set-up): neighbours follow the
+    reference's row-major cart (forward/mympi_t.c:32-40), inter-rank faces carry no PML, exactly one rank owns the source, and the
+    ghost metrics of an inter-rank face equal the neighbour's physical values."""
+    import bench
+    size, n = (24, 16, 12), 8
+    assert bench.proc_grid(n) == (4, 2)
+    probs = [bench.build_rank_problem(size, r, n) for r in range(n)]
+    owners = [r for r, p in enumerate(probs) if p.src and p.src.get("total_number", 0) > 0]
+    assert len(owners) == 1
+    px, py = 4, 2
+    for r, p in enumerate(probs):
+        ix, iy = r // py, r % py
+        want = (r - py if ix > 0 else -1, r + py if ix < px - 1 else -1, r - 1 if iy > 0 else -1, r + 1 if iy < py - 1 else -1)
+        assert tuple(p.neigh) == want
+        for side in range(4):
+            has_pml = (side // 2, side % 2) in p.pml
+            assert has_pml == (want[side] < 0)
+        assert (2, 0) in p.pml and p.free_top == 1
+    # x2 ghosts of rank 0 (ix=0, iy=0) = first physical columns of rank 2 (ix=1, iy=0), for every metric array
+    a, b = probs[0], probs[2]
+    for m in range(10):
+        np.testing.assert_array_equal(a.metric[m][3:-3, 3:-3, -3:], b.metric[m][3:-3, 3:-3, 3:6])
