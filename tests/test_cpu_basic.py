@@ -53,17 +53,18 @@ def test_device_setup_matches_host_setup():
     """devsetup (torch expressions, run on the GPU for the big bench blocks) == hostsetup (numpy), here both on the CPU"""
     import numpy as np
     from cgfd3d_b200 import devsetup as ds, hostsetup as hs
-    sub = (40, 0, 80, 36, (0, -1, -1, -1))
-    a = hs.build_problem(40, 36, 30, topo="hill", hill=(300.0, 800.0), pml_layers=6, dt=0.01, sub=sub)
-    b = ds.build_problem(40, 36, 30, device="cpu", hill=(300.0, 800.0), pml_layers=6, dt=0.01, sub=sub)
-    for m in range(10):
-        np.testing.assert_allclose(b.metric[m].numpy(), a.metric[m], rtol=1e-6, atol=0)
-    assert set(a.pml) == set(b.pml)
-    for k in a.pml:
-        for q in (1, 2, 3):
-            np.testing.assert_array_equal(a.pml[k][q], b.pml[k][q])
-    for n in ("matVx2Vz", "matVy2Vz", "matF2Vz"):
-        np.testing.assert_allclose(b.mats[n], a.mats[n], rtol=1e-6, atol=1e-30)
+    # an edge block with one neighbour, and a block of the 4x2 grid with neighbours on both x sides and one y side
+    for sub in ((40, 0, 80, 36, (0, -1, -1, -1)), (40, 36, 160, 72, (0, 4, 1, -1))):
+        a = hs.build_problem(40, 36, 30, topo="hill", hill=(300.0, 800.0), pml_layers=6, dt=0.01, sub=sub)
+        b = ds.build_problem(40, 36, 30, device="cpu", hill=(300.0, 800.0), pml_layers=6, dt=0.01, sub=sub)
+        for m in range(10):
+            np.testing.assert_allclose(b.metric[m].numpy(), a.metric[m], rtol=1e-6, atol=0)
+        assert set(a.pml) == set(b.pml)
+        for k in a.pml:
+            for q in (1, 2, 3):
+                np.testing.assert_array_equal(a.pml[k][q], b.pml[k][q])
+        for n in ("matVx2Vz", "matVy2Vz", "matF2Vz"):
+            np.testing.assert_allclose(b.mats[n], a.mats[n], rtol=1e-6, atol=1e-30)
 
 
 def test_launch_plan_longest_job_first():
