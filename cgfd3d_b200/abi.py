@@ -1,7 +1,7 @@
 """ctypes mirror of include/cgfd3d_b200.h (the C ABI of the hot path).
 
-Field order and types must match the header exactly; tests/test_abi.py checks sizeof() of every
-struct against the values the compiled library reports.
+Field order and types must match the header exactly; tests/test_cpu_basic.py checks sizeof(cgfd_problem_t)
+against the value the compiled library reports.
 """
 from __future__ import annotations
 

@@ -107,6 +107,7 @@ struct cgfd_b200_ctx {
   cudaStream_t st = nullptr;        // compute stream
   cudaStream_t st2 = nullptr;       // boundary phase: free-surface rows, tiles next to inter-rank faces, halo exchange
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int nsm = 148;                    // multiprocessors of the device (launch plan: resident blocks per wave)
   int l2mode = 3;                   // L2 eviction hints of the interior kernel (CGFD_L2MODE)
   int overlap = 1;                  // run the boundary phase concurrently with the interior kernel
   int toppar = 0;                   // single rank: free-surface kernel on the second stream beside the interior kernel (CGFD_TOPPAR)
@@ -155,6 +156,7 @@ struct cgfd_b200_ctx {
   struct {
     int n = 0, vi_on = 0, mij_on = 0, max_stage = 0, nt_block = 0;
     int64_t *iptr = nullptr; float *wV = nullptr, *rjac = nullptr;
+    int nb = 0; int *sel = nullptr;                // point numbers, the nb boundary-phase ones first (see run_stage)
     float *vi[2] = {nullptr, nullptr}, *mij[2] = {nullptr, nullptr};
     int it_first[2] = {-1, -1}, nt[2] = {0, 0};
     int next = 0;                                  // buffer the next block goes to
@@ -234,7 +236,8 @@ static encode_tiled_fn get_encode()
 // 4-D map over [ncomp][nz][ny][PX] float32 with box (bx, by, 1, bc)
 // phys = true: origin at the first physical point of a row / column, extents ni x nj (store maps: nothing outside the
 // physical x-y range is ever written)
-static int make_map(cgfd_b200_ctx *c, CUtensorMap *m, float *base, int ncomp, int bx, int by, int bc, bool phys = false)
+static int make_map(cgfd_b200_ctx *c, CUtensorMap *m, float *base, int ncomp, int bx, int by, int bc, bool phys = false,
+                    const char *promo_env = "CGFD_L2PROMO")
 {
   encode_tiled_fn enc = get_encode();
   if (!enc) return fail("cuTensorMapEncodeTiled is not available from this driver");
@@ -253,6 +256,7 @@ static int make_map(cgfd_b200_ctx *c, CUtensorMap *m, float *base, int ncomp, in
                                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B};
   int promo = 2;
   if (const char *e = getenv("CGFD_L2PROMO")) promo = atoi(e) & 3;
+  if (const char *e = getenv(promo_env)) promo = atoi(e) & 3;
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dim, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, promo_tab[promo], CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
@@ -460,6 +464,14 @@ extern "C" int cgfd_b200_create(const cgfd_problem_t *p, int device, cgfd_b200_c
   if (device < 0 || device >= ndev) return fail("cgfd_b200_create: bad device ordinal");
   if (check_fd(p->fd)) return 1;
   CK(cudaSetDevice(device));
+#define CKD(call)                                                                                  \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      cgfd_b200_destroy(c);                                                                        \
+      return fail(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
+    }                                                                                              \
+  } while (0)
   cgfd_b200_ctx *c = new cgfd_b200_ctx();
   c->device = device;
   c->g = p->grid; c->fd = p->fd; c->dt = p->dt;
@@ -485,20 +497,25 @@ extern "C" int cgfd_b200_create(const cgfd_problem_t *p, int device, cgfd_b200_c
   if (const char *e = getenv("CGFD_TOPPAR")) c->toppar = atoi(e);
   {
     int lo = 0, hi = 0;
-    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    CK(cudaStreamCreateWithPriority(&c->st, cudaStreamNonBlocking, lo));
-    CK(cudaStreamCreateWithPriority(&c->st2, cudaStreamNonBlocking, hi));
-    CK(cudaStreamCreateWithFlags(&c->st_io, cudaStreamNonBlocking));
+    CKD(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CKD(cudaStreamCreateWithPriority(&c->st, cudaStreamNonBlocking, lo));
+    CKD(cudaStreamCreateWithPriority(&c->st2, cudaStreamNonBlocking, hi));
+    CKD(cudaStreamCreateWithFlags(&c->st_io, cudaStreamNonBlocking));
     for (int b = 0; b < 2; b++) {
-      CK(cudaEventCreateWithFlags(&c->stage_full[b], cudaEventDisableTiming));
-      CK(cudaEventCreateWithFlags(&c->stage_free[b], cudaEventDisableTiming));
+      CKD(cudaEventCreateWithFlags(&c->stage_full[b], cudaEventDisableTiming));
+      CKD(cudaEventCreateWithFlags(&c->stage_free[b], cudaEventDisableTiming));
     }
-    CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    CKD(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CKD(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  }
+  {
+    cudaDeviceProp prop;
+    CKD(cudaGetDeviceProperties(&prop, device));
+    c->nsm = prop.multiProcessorCount;
   }
   c->ntx = (g.ni2 - g.ni1 + 1 + TILE_X - 1) / TILE_X; c->nty = (g.nj2 - g.nj1 + 1 + TILE_Y - 1) / TILE_Y;
-  if (kernels_init(c->med)) { delete c; return fail("cgfd_b200_create: cudaFuncSetAttribute failed (needs sm_100 shared memory sizes)"); }
-  CK(cudaEventCreate(&c->run0)); CK(cudaEventCreate(&c->run1));
+  if (kernels_init(c->med)) { cgfd_b200_destroy(c); return fail("cgfd_b200_create: cudaFuncSetAttribute failed (needs sm_100 shared memory sizes)"); }
+  CKD(cudaEventCreate(&c->run0)); CKD(cudaEventCreate(&c->run1));
 
   FdConst fc;
   for (int d = 0; d < 2; d++) {
@@ -506,7 +523,7 @@ extern "C" int cgfd_b200_create(const cgfd_problem_t *p, int device, cgfd_b200_c
     for (int n = 0; n < 2; n++) fc.lay2[d][n] = p->fd.lay_coef[1][d][n];
     for (int n = 0; n < 3; n++) fc.lay3[d][n] = p->fd.lay_coef[2][d][n];
   }
-  CK(cudaMemcpyToSymbol(c_fd, &fc, sizeof(fc)));
+  CKD(cudaMemcpyToSymbol(c_fd, &fc, sizeof(fc)));
 
   int rc = 0;
   for (int l = 0; l < 4; l++) rc |= upload(c, &c->lev[l], (const float *)nullptr, c->V * c->ncmp);
@@ -522,7 +539,7 @@ extern "C" int cgfd_b200_create(const cgfd_problem_t *p, int device, cgfd_b200_c
     c->media[m] = c->media_blk + (size_t)m * c->V + c->shift;
     rc |= copy_in3d(c, c->media_blk + (size_t)m * c->V, p->media[m], 1, c->st);
   }
-  CK(cudaStreamSynchronize(c->st));
+  CKD(cudaStreamSynchronize(c->st));
   if (rc) { cgfd_b200_destroy(c); return 1; }
   if (p->graves_Qs) {
     if (med == MED_VIS) { cgfd_b200_destroy(c); return fail("cgfd_b200_create: Graves Qs attenuation applies to the elastic media, not to the GMB visco-elastic one"); }
@@ -530,7 +547,7 @@ extern "C" int cgfd_b200_create(const cgfd_problem_t *p, int device, cgfd_b200_c
     if (copy_in3d(c, c->qatt, p->graves_Qs, 1, c->st)) { cgfd_b200_destroy(c); return 1; }
     const float coef = (float)(-M_PI * (double)p->graves_Qs_freq * (double)p->dt);   // float coef = - PI * md->visco_Qs_freq * dt, PI a double literal
     k_graves_factor<<<(unsigned)((c->V + 255) / 256), 256, 0, c->st>>>(c->qatt, c->V, coef);
-    CK(cudaStreamSynchronize(c->st));
+    CKD(cudaStreamSynchronize(c->st));
   }
   // grid class: do the four metric arrays that vanish on a vertically deformed grid vanish here? (physical points only:
   // the interior kernel uses the metric point-wise; the free-surface kernel stays general)
@@ -543,8 +560,8 @@ extern "C" int cgfd_b200_create(const cgfd_problem_t *p, int device, cgfd_b200_c
       k_any_nonzero<<<grd, blk, 0, c->st>>>(c->metric[zero_arrays[n]], c->PX, g.ny, g.ni1, g.ni2, g.nj1, g.nk1, flag);
     }
     int hflag = 1;
-    CK(cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    CKD(cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CKD(cudaStreamSynchronize(c->st));
     c->gz = (hflag == 0);
     if (const char *e = getenv("CGFD_GZ")) { if (atoi(e) == 0) c->gz = 0; }
   }
@@ -552,7 +569,8 @@ extern "C" int cgfd_b200_create(const cgfd_problem_t *p, int device, cgfd_b200_c
   {
     int mrc = 0;
     for (int l = 0; l < 4 && !mrc; l++) {
-      mrc |= make_map(c, &c->map_halo[l], c->lev[l], c->ncmp, TILE_X + 2 * HALO_X, TILE_Y + 4, 9);
+      // CGFD_L2PROMO_CUR: promotion of the halo boxes alone (their 16-byte x halo drags the neighbour tile's whole 128-byte line in)
+      mrc |= make_map(c, &c->map_halo[l], c->lev[l], c->ncmp, TILE_X + 2 * HALO_X, TILE_Y + 4, 9, false, "CGFD_L2PROMO_CUR");
       mrc |= make_map(c, &c->map_cen[l], c->lev[l], c->ncmp, TILE_X, TILE_Y, 9);
       mrc |= make_map(c, &c->map_out[l], c->lev[l], c->ncmp, TILE_X, TILE_Y, 9, true);
     }
@@ -594,11 +612,12 @@ extern "C" int cgfd_b200_create(const cgfd_problem_t *p, int device, cgfd_b200_c
   rc |= setup_sources(c, p);
   if (c->has_surf) rc |= upload(c, &c->srcslice, (const float *)nullptr, c->hslice * 6);
   if (rc) { cgfd_b200_destroy(c); return 1; }
-  CK(cudaDeviceSynchronize());
+  CKD(cudaDeviceSynchronize());
   *out = c;
   return 0;
 }
 
+#undef CKD
 extern "C" void cgfd_b200_destroy(cgfd_b200_ctx *c)
 {
   if (!c) return;
@@ -777,7 +796,7 @@ static int split_tiles(const cgfd_b200_ctx *c, bool split, int bnd[4][4], int in
 // its z chunks in the direction the kernel marches (dz = 1 upwards, 0 downwards) before the next band starts, so that the
 // 4 planes a chunk re-reads for its zeta queue are the ones the previous chunk of the same tile has just fetched (L2 hits
 // instead of a second DRAM read). lpt = 1: chunk-major order.
-static void compute_plan(const cgfd_grid_t &g, const int pml_r[2][2][3], int free_top, int blocks_per_sm, int waves, int minchunk,
+static void compute_plan(const cgfd_grid_t &g, const int pml_r[2][2][3], int free_top, int nsm, int blocks_per_sm, int waves, int minchunk,
                          int zchunk_explicit, int lpt, int dz, const int rect[4], int *zchunk, std::vector<int> *order)
 {
   *zchunk = 0; order->clear();
@@ -787,7 +806,7 @@ static void compute_plan(const cgfd_grid_t &g, const int pml_r[2][2][3], int fre
   int nzc = 1;
   if (zchunk_explicit > 0) nzc = (nk + zchunk_explicit - 1) / zchunk_explicit;
   else
-    while (nzc < nk && (long)bx * by * nzc < 148L * blocks_per_sm * waves && nk / (nzc + 1) >= minchunk) nzc++;
+    while (nzc < nk && (long)bx * by * nzc < (long)nsm * blocks_per_sm * waves && nk / (nzc + 1) >= minchunk) nzc++;
   *zchunk = (nk + nzc - 1) / nzc;
   nzc = (nk + *zchunk - 1) / *zchunk;
   if (!lpt) return;
@@ -804,7 +823,7 @@ static void compute_plan(const cgfd_grid_t &g, const int pml_r[2][2][3], int fre
     }
   for (int cl = 0; cl < 2; cl++) {
     const size_t nt = cls[cl].size();
-    const size_t band = (lpt >= 2) ? (size_t)148 * blocks_per_sm : (nt ? nt : 1);
+    const size_t band = (lpt >= 2) ? (size_t)nsm * blocks_per_sm : (nt ? nt : 1);
     for (size_t b0 = 0; b0 < nt; b0 += band)
       for (int zi = 0; zi < nzc; zi++) {
         const int z = (lpt >= 2 && dz == 0) ? nzc - 1 - zi : zi;
@@ -824,7 +843,7 @@ static const LaunchPlan *plan_for(cgfd_b200_ctx *c, const int rect[4], int dz)
     pml_r[d][sd][0] = f.on; pml_r[d][sd][1] = f.r[2 * d]; pml_r[d][sd][2] = f.r[2 * d + 1];
   }
   std::vector<int> order;
-  compute_plan(c->g, pml_r, c->free_top, blocks_per_sm(c->med), c->plan_waves, c->plan_minchunk, c->zchunk, c->plan_lpt, dz, rect, &pl.zchunk, &order);
+  compute_plan(c->g, pml_r, c->free_top, c->nsm, blocks_per_sm(c->med), c->plan_waves, c->plan_minchunk, c->zchunk, c->plan_lpt, dz, rect, &pl.zchunk, &order);
   if (!order.empty() && upload(c, &pl.order, order.data(), order.size())) return nullptr;
   return &(c->plans[key] = pl);
 }
@@ -839,9 +858,29 @@ extern "C" int cgfd_b200_launch_plan(const cgfd_grid_t *g, const int pml_nlay[3]
   }
   cgfd_b200_ctx defaults;
   std::vector<int> ord;
-  compute_plan(*g, pml_r, free_top, blocks_per_sm, defaults.plan_waves, defaults.plan_minchunk, 0, defaults.plan_lpt, dz, rect, zchunk, &ord);
+  compute_plan(*g, pml_r, free_top, 148 /* B200; the context itself asks the device */, blocks_per_sm, defaults.plan_waves, defaults.plan_minchunk, 0, defaults.plan_lpt, dz, rect, zchunk, &ord);
   if (order) for (size_t n = 0; n < ord.size() && (int)n < capacity; n++) order[n] = ord[n];
   return (int)ord.size();
+}
+
+// distributed sources: the resident time block that holds step `it` (srcdd is skipped outside every loaded block, like
+// dd_is_valid = 0 past dd_max_nt), and the launch of points sel[first .. first+count) of it on stream s
+static int dd_block_of(const cgfd_b200_ctx *c, int it)
+{
+  if (c->dd.n <= 0) return -1;
+  for (int bf = 0; bf < 2; bf++)
+    if (c->dd.it_first[bf] >= 0 && it >= c->dd.it_first[bf] && it < c->dd.it_first[bf] + c->dd.nt[bf]) return bf;
+  return -1;
+}
+static int launch_dd(cgfd_b200_ctx *c, int bf, int it, int istage, int first, int count, int itmp, int iend, float a, float b, int kind,
+                     const float *qatt, cudaStream_t s)
+{
+  const size_t row = ((size_t)(it - c->dd.it_first[bf]) * c->dd.max_stage + istage) * c->dd.n;
+  CK(cudaStreamWaitEvent(s, c->dd.loaded[bf], 0));
+  k_srcdd_inject<<<(count + 127) / 128, 128, 0, s>>>(count, c->dd.sel + first, c->dd.iptr, c->dd.wV, c->dd.rjac,
+      c->dd.vi_on ? c->dd.vi[bf] + row * 3 : nullptr, c->dd.mij_on ? c->dd.mij[bf] + row * 6 : nullptr,
+      c->lev[itmp] + c->shift, c->lev[iend] + c->shift, a, b, c->V, kind, qatt);
+  return 0;
 }
 
 // Launch everything of stage `istage` of step `it`; level roles: icur -> (itmp, iend), ipre.
@@ -887,53 +926,73 @@ static int run_stage(cgfd_b200_ctx *c, StageArgs &P, int it, int ipair, int ista
   }
   // two streams: with a halo exchange to hide, or (toppar) just to run the latency-bound free-surface kernel beside the interior one
   const bool two = (c->overlap && halo_w) || (c->toppar && c->free_top);
+  // toppar = 2 (single rank): the free-surface kernel is issued AFTER the interior kernel on the low-priority stream, so that its
+  // blocks fill the SMs the interior kernel's last wave leaves idle instead of running ahead of it
+  const bool top_late = !halo_w && c->toppar == 2 && c->free_top;
   cudaStream_t sb = two ? c->st2 : c->st;   // stream of the boundary phase
   int bnd[4][4], inner[4];
   const int nb = split_tiles(c, halo_w != nullptr, bnd, inner);
   if (two) { CK(cudaEventRecord(c->ev_fork, c->st)); CK(cudaStreamWaitEvent(c->st2, c->ev_fork, 0)); }
   // ---- boundary phase
-  launch_top(c->med, P, dir, kind, sb, &nl);
+  if (!top_late) launch_top(c->med, P, dir, kind, sb, &nl);
   for (int n = 0; n < nb; n++) {
     const LaunchPlan *pl = plan_for(c, bnd[n], dir[2]);
     if (!pl) return 1;
     P.order = pl->order;
     launch_main(c->med, P, mp, dir, kind, c->gz, pl->zchunk, bnd[n], sb, nullptr, nullptr, &nl);
   }
-  if (c->has_src && c->src_nb > 0) {
+  // Sources are pushed through the RK axpy AFTER the stage kernel of their point has written it (k_src_inject). The points were
+  // classified at create time by the declared neighbours (setup_sources); the tiles are only split when an exchange follows.
+  // With a split, the boundary-class points go in here, before the ghosts leave; without one, every point waits for the
+  // whole-rectangle interior kernel (which would otherwise overwrite the boundary-class ones).
+  const bool split = halo_w != nullptr;
+  const int ddbf = dd_block_of(c, it);   // resident time block of the distributed sources that holds this step, or -1
+  if (split && c->has_src && c->src_nb > 0) {
     k_src_inject<<<(c->src_nb + 127) / 128, 128, 0, sb>>>(c->src, 0, c->src_nb, it, istage, c->lev[itmp] + sh, c->lev[iend] + sh, a, b, c->V, kind, P.qatt);
+    nl++;
+  }
+  if (split && ddbf >= 0 && c->dd.nb > 0) {
+    // the reference adds srcdd to the RHS before the RK update and the pack (forward/sv_curv_col_el_iso.c:190-199): dd points in
+    // the boundary-phase tiles must be in before the ghosts leave
+    if (launch_dd(c, ddbf, it, istage, 0, c->dd.nb, itmp, iend, a, b, kind, P.qatt, sb)) return 1;
     nl++;
   }
   if (halo_w) {
     if (halo_exchange(c->halo, halo_w, halo_dx, halo_dy, sb)) return fail(halo_error());
     nl += halo_launches_per_exchange(c->halo);
   }
-  if (two) CK(cudaEventRecord(c->ev_join, c->st2));
+  if (two && !top_late) CK(cudaEventRecord(c->ev_join, c->st2));
   // ---- interior phase
   {
     const LaunchPlan *pl = plan_for(c, inner, dir[2]);
     if (!pl) return 1;
     P.order = pl->order;
-    launch_main(c->med, P, mp, dir, kind, c->gz, pl->zchunk, inner, c->st, e0, e1, &nl);
-  }
-  if (c->has_src && c->src.npts > c->src_nb) {
-    const int cnt = c->src.npts - c->src_nb;
-    k_src_inject<<<(cnt + 127) / 128, 128, 0, c->st>>>(c->src, c->src_nb, cnt, it, istage, c->lev[itmp] + sh, c->lev[iend] + sh, a, b, c->V, kind, P.qatt);
-    nl++;
-  }
-  if (c->dd.n > 0) {
-    // the time block that holds step `it` (srcdd is skipped outside every loaded block, like dd_is_valid = 0 past dd_max_nt)
-    for (int bf = 0; bf < 2; bf++) {
-      if (c->dd.it_first[bf] < 0 || it < c->dd.it_first[bf] || it >= c->dd.it_first[bf] + c->dd.nt[bf]) continue;
-      const size_t row = ((size_t)(it - c->dd.it_first[bf]) * c->dd.max_stage + istage) * c->dd.n;
-      if (two) CK(cudaStreamWaitEvent(c->st, c->ev_join, 0));   // dd points may lie in boundary-phase tiles
-      CK(cudaStreamWaitEvent(c->st, c->dd.loaded[bf], 0));
-      k_srcdd_inject<<<(c->dd.n + 127) / 128, 128, 0, c->st>>>(c->dd.n, c->dd.iptr, c->dd.wV, c->dd.rjac,
-          c->dd.vi_on ? c->dd.vi[bf] + row * 3 : nullptr, c->dd.mij_on ? c->dd.mij[bf] + row * 6 : nullptr,
-          c->lev[itmp] + sh, c->lev[iend] + sh, a, b, c->V, kind, P.qatt);
-      CK(cudaEventRecord(c->dd.used[bf], c->st));
-      nl++;
-      break;
+    // top_late: the interior kernel takes the high-priority stream, the free-surface kernel follows on the low-priority one
+    cudaStream_t sm = top_late ? c->st2 : c->st;
+    launch_main(c->med, P, mp, dir, kind, c->gz, pl->zchunk, inner, sm, e0, e1, &nl);
+    if (top_late) {
+      CK(cudaEventRecord(c->ev_join, c->st2));
+      launch_top(c->med, P, dir, kind, c->st, &nl);
     }
+  }
+  // without a split the boundary-class points (free-surface rows, which another stream may own) are injected here as well
+  if (!split && two) CK(cudaStreamWaitEvent(c->st, c->ev_join, 0));
+  {
+    const int first = split ? c->src_nb : 0, cnt = c->has_src ? c->src.npts - first : 0;
+    if (cnt > 0) {
+      k_src_inject<<<(cnt + 127) / 128, 128, 0, c->st>>>(c->src, first, cnt, it, istage, c->lev[itmp] + sh, c->lev[iend] + sh, a, b, c->V, kind, P.qatt);
+      nl++;
+    }
+    const int dfirst = split ? c->dd.nb : 0, dcnt = c->dd.n - dfirst;
+    if (ddbf >= 0 && dcnt > 0) {
+      if (launch_dd(c, ddbf, it, istage, dfirst, dcnt, itmp, iend, a, b, kind, P.qatt, c->st)) return 1;
+      nl++;
+    }
+  }
+  if (ddbf >= 0) {
+    // both phases are done with the block's tables once st has joined st2
+    if (two) CK(cudaStreamWaitEvent(c->st, c->ev_join, 0));
+    CK(cudaEventRecord(c->dd.used[ddbf], c->st));
   }
   if (two) CK(cudaStreamWaitEvent(c->st, c->ev_join, 0));
   c->total_launches += nl;
@@ -1111,6 +1170,12 @@ extern "C" int cgfd_b200_set_record_points(cgfd_b200_ctx *c, int n, const int64_
 {
   CK(cudaSetDevice(c->device));
   c->nrec = 0; c->rec_count = 0;
+  for (void **q : {(void **)&c->rec_iptr, (void **)&c->rec}) {   // a second call replaces the first one's buffers
+    if (!*q) continue;
+    CK(cudaStreamSynchronize(c->st));
+    for (auto it = c->owned.begin(); it != c->owned.end(); ++it) if (*it == *q) { c->owned.erase(it); break; }
+    cudaFree(*q); *q = nullptr;
+  }
   if (n <= 0) return 0;
   for (int i = 0; i < n; i++) if (iptr[i] < 0 || (size_t)iptr[i] >= c->hV) return fail("set_record_points: index out of range");
   std::vector<int64_t> dv(n);
@@ -1191,21 +1256,26 @@ extern "C" int cgfd_b200_dd_set_points(cgfd_b200_ctx *c, int n, const int64_t *i
   CK(cudaSetDevice(c->device));
   if (c->dd.n > 0) return fail("dd_set_points: already set");
   if (n <= 0 || !indx || max_stage <= 0 || nt_per_block <= 0 || (!vi_actived && !mij_actived)) return fail("dd_set_points: bad arguments");
-  if (c->halo && c->overlap) {
-    // with the two-phase schedule the ghosts of w_tmp leave before the interior-phase sources are added: points inside the
-    // strips next to an inter-rank face would reach the neighbour one stage late
-    const cgfd_grid_t &g = c->g;
-    for (int q = 0; q < n; q++) {
-      const int64_t i = indx[q] % g.nx, j = (indx[q] / g.nx) % g.ny;
-      if ((c->neigh[0] >= 0 && i < g.ni1 + TILE_X) || (c->neigh[1] >= 0 && i > g.ni2 - TILE_X) || (c->neigh[2] >= 0 && j < g.nj1 + TILE_Y) ||
-          (c->neigh[3] >= 0 && j > g.nj2 - TILE_Y))
-        return fail("dd_set_points: a dd point lies in a boundary-phase tile of an inter-rank face; run this rank with CGFD_OVERLAP=0");
-    }
-  }
   std::vector<int64_t> dv(n);
   for (int q = 0; q < n; q++) {
     if (indx[q] < 0 || (size_t)indx[q] >= c->hV) return fail("dd_set_points: index out of range");
     dv[q] = dev_index(c, indx[q]);
+  }
+  {
+    // boundary-phase points first (free-surface rows and the tiles next to a declared inter-rank face: same rule as setup_sources)
+    const cgfd_grid_t &g = c->g;
+    std::vector<int> sel, rest;
+    for (int q = 0; q < n; q++) {
+      const int i = (int)(indx[q] % g.nx), j = (int)((indx[q] / g.nx) % g.ny), k = (int)(indx[q] / ((int64_t)g.nx * g.ny));
+      const int tx = (i - g.ni1) / TILE_X, ty = (j - g.nj1) / TILE_Y;
+      const bool bnd = (c->free_top && k >= g.nk2 - 3) || i < g.ni1 || j < g.nj1 || tx >= c->ntx || ty >= c->nty ||
+                       (c->neigh[0] >= 0 && tx == 0) || (c->neigh[1] >= 0 && tx == c->ntx - 1) ||
+                       (c->neigh[2] >= 0 && ty == 0) || (c->neigh[3] >= 0 && ty == c->nty - 1);
+      (bnd ? sel : rest).push_back(q);
+    }
+    c->dd.nb = (int)sel.size();
+    sel.insert(sel.end(), rest.begin(), rest.end());
+    if (upload(c, &c->dd.sel, sel.data(), sel.size())) return 1;
   }
   if (upload(c, &c->dd.iptr, dv.data(), n)) return 1;
   if (upload(c, &c->dd.wV, (const float *)nullptr, n) || upload(c, &c->dd.rjac, (const float *)nullptr, n)) return 1;

@@ -44,11 +44,12 @@ __global__ void k_src_inject(SrcDev S, int first, int count, int it, int istage,
 // Distributed (finite-fault) sources, sv_curv_col_el_rhs_srcdd (forward/sv_curv_col_el.c:486-632, add-at-point branch):
 // hV += vi * slw/J, hT -= mij / J at every dd point, pushed through the RK axpy like k_src_inject. vi / mij point at the rows of
 // this step and stage inside the resident time block: [n][3] and [n][6] (component order xx yy zz yz xz xy = TXX..TXY).
-__global__ void k_srcdd_inject(int n, const int64_t *iptr, const float *wV, const float *rjac, const float *vi, const float *mij,
-                               float *tmp, float *end, float a, float b, size_t V, int kind, const float *qatt)
+__global__ void k_srcdd_inject(int count, const int *sel, const int64_t *iptr, const float *wV, const float *rjac, const float *vi,
+                               const float *mij, float *tmp, float *end, float a, float b, size_t V, int kind, const float *qatt)
 {
-  const int is = blockIdx.x * blockDim.x + threadIdx.x;
-  if (is >= n) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  const int is = sel[t];   // point number: column of the time-function tables
   const size_t p = iptr[is];
   float add[9];
 #pragma unroll

@@ -25,8 +25,9 @@ struct SrcDev {
 __global__ void k_src_inject(SrcDev S, int first, int count, int it, int istage, float *tmp, float *end, float a, float b, size_t V,
                              int kind, const float *qatt);
 __global__ void k_graves_factor(float *q, size_t n, float coef);
-__global__ void k_srcdd_inject(int n, const int64_t *iptr, const float *wV, const float *rjac, const float *vi, const float *mij,
-                               float *tmp, float *end, float a, float b, size_t V, int kind, const float *qatt);
+// points sel[0 .. count) (point numbers = columns of the time-function tables vi [n][3], mij [n][6] of this step and stage)
+__global__ void k_srcdd_inject(int count, const int *sel, const int64_t *iptr, const float *wV, const float *rjac, const float *vi,
+                               const float *mij, float *tmp, float *end, float a, float b, size_t V, int kind, const float *qatt);
 __global__ void k_srcdd_weights(int n, const int64_t *iptr, const float *slw, const float *jac, float *wV, float *rjac);
 __global__ void k_src_surface(SrcDev S, int it, int istage, float *Tx, float *Ty, float *Tz, float *Vx, float *Vy, float *Vz);
 __global__ void k_record(const float *w, size_t V, int ncmp, int npts, const int64_t *iptr, float *rec_it);

@@ -133,7 +133,7 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
   const float *cx = c_fd.coef[DX], *cy = c_fd.coef[DY], *cz = c_fd.coef[DZ];
 #pragma unroll
   for (int c = 0; c < 9; c++) q4[c] = qn[c];
-  if (C.inarr && it + 1 < nplanes) {
+  if (C.inarr && it + 1 < nplanes && !(P.l2mode & 128)) {   // bit 7: DIAGNOSTIC (wrong results): no z-ahead loads
     const float *w = C.qptr + (long)(k + 2 * DIR) * (long)P.siz_slice;
 #pragma unroll
     for (int c = 0; c < 9; c++) qn[c] = __ldg(w + c * P.siz_vol);
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(TX *TY, Lay<MED>::BLOCKS) k_main_tma(const Sta
   float q0[9], q1[9], q2[9], q3[9], q4[9], qn[9];
 #pragma unroll
   for (int c = 0; c < 9; c++) { q0[c] = q1[c] = q2[c] = q3[c] = q4[c] = qn[c] = 0.0f; }
-  if (C.inarr) {
+  if (C.inarr && !(P.l2mode & 256)) {   // bit 8: DIAGNOSTIC (wrong results): no queue priming
     const long sd = (long)DIR * (long)P.siz_slice;
 #pragma unroll
     for (int c = 0; c < 9; c++) {
@@ -490,8 +490,8 @@ __global__ void __launch_bounds__(128, CGFD_TOP_BLOCKS) k_top(const StageArgs P)
   pml_all<KIND, 0, MED>(P, i, j, k, d, m, md, h);
   pml_all<KIND, 1, MED>(P, i, j, k, d, m, md, h);
   if constexpr (MED == MED_VIS) atten_update<KIND>(P, p, md.lam, md.mu, h);
-#pragma unroll
   const float qatt = (KIND == KIND_LAST && P.qatt) ? __ldg(P.qatt + p) : 1.0f;
+#pragma unroll
   for (int c = 0; c < 9; c++) rk_wave<KIND>(P.tmp, P.end, c * V + p, cur[c], pv[c], ev[c], h[c], P.a, P.b, P.c, qatt);
 }
 

@@ -300,6 +300,63 @@ def fun_ricker(t, fc, t0):
     return f32((1 - u * u / 2.0) * math.exp(-u * u / 4.0))
 
 
+def fun_ricker_deriv(t, fc, t0):
+    """forward/src_t.c:2169-2176 (float in, double inside, float out)."""
+    u = float(f32((float(f32(t)) - float(f32(t0))) * 2.0 * math.pi * float(f32(fc))))
+    return f32(u * (-3 + 1.0 / 2.0 * u * u) * math.exp(-u * u / 4.0) * math.pi * float(f32(fc)))
+
+
+# ---------------------------------------------------------------------------------------------
+# exponential sponge (ablexp)
+# ---------------------------------------------------------------------------------------------
+def _ablexp_mask(i, vel, dt, num_lay, dh):
+    """bdry_ablexp_cal_mask (forward/bdry_t.c:814-832), float32 arithmetic."""
+    ln = f32(f32(num_lay) * f32(dh))
+    num_step = int(f32(f32(ln / f32(vel)) / f32(dt)))
+    total = f32(0.0)
+    for n in range(num_step):
+        total = f32(total + f32(math.pow(float(f32(f32(f32(n) * f32(dt)) * f32(vel)) / ln), 2.0)))
+    alpha = f32(0.6 / float(total))
+    return f32(math.exp(float(f32(-alpha * f32(math.pow(float(f32(f32(i) / f32(num_lay))), 2.0))))))
+
+
+def ablexp_profiles(x, y, z, grid, layers, dt, vel=7000.0):
+    """The six shell blocks and the 1-D damping profiles of bdry_ablexp_set (forward/bdry_t.c:513-796).
+    layers[idim][iside] = number of sponge layers on that face (0 = none; inter-rank faces must be 0).
+    Returns (blk[6][7] int32 = enable, ni1, ni2, nj1, nj2, nk1, nk2; Ex[nx]; Ey[ny]; Ez[nz])."""
+    g = grid
+    ni1, ni2, nj1, nj2, nk1, nk2 = g["ni1"], g["ni2"], g["nj1"], g["nj2"], g["nk1"], g["nk2"]
+    ni, nj, nk = ni2 - ni1 + 1, nj2 - nj1 + 1, nk2 - nk1 + 1
+    E = [np.ones(g["nx"], f32), np.ones(g["ny"], f32), np.ones(g["nz"], f32)]
+    blk = np.zeros((6, 7), np.int32)
+    blk[:, 2::2] = -1
+    L = layers
+    nix, njy = L[0][0] + L[0][1], L[1][0] + L[1][1]
+    # (count, first) per axis of the six blocks x1 x2 y1 y2 z1 z2: y blocks exclude the x shells, z blocks the x and y shells
+    spec = [
+        ((L[0][0], ni1), (nj, nj1), (nk, nk1)),
+        ((L[0][1], ni2 - L[0][1] + 1), (nj, nj1), (nk, nk1)),
+        ((ni - nix, ni1 + L[0][0]), (L[1][0], nj1), (nk, nk1)),
+        ((ni - nix, ni1 + L[0][0]), (L[1][1], nj2 - L[1][1] + 1), (nk, nk1)),
+        ((ni - nix, ni1 + L[0][0]), (nj - njy, nj1 + L[1][0]), (L[2][0], nk1)),
+        ((ni - nix, ni1 + L[0][0]), (nj - njy, nj1 + L[1][0]), (L[2][1], nk2 - L[2][1] + 1)),
+    ]
+    for n, sp in enumerate(spec):
+        idim, iside = n // 2, n % 2
+        rng = [[a1, a1 + cnt - 1] for (cnt, a1) in sp]
+        blk[n, 1:] = [rng[0][0], rng[0][1], rng[1][0], rng[1][1], rng[2][0], rng[2][1]]
+        if min(cnt for cnt, _ in sp) <= 0:
+            continue
+        blk[n, 0] = 1
+        _, dh = _abl_len_dh(x, y, z, rng, idim)
+        cnt, a1 = sp[idim]
+        for a in range(a1, a1 + cnt):
+            # the first point of the layer gets the weakest damping on the "2" sides, the strongest on the "1" sides
+            i = cnt - (a - a1) if iside == 0 else a - a1 + 1
+            E[idim][a] = _ablexp_mask(i, vel, dt, cnt, dh)
+    return blk, E[0], E[1], E[2]
+
+
 @dataclass
 class HostProblem:
     """numpy arrays of one subdomain + conversion to the C ABI struct."""
@@ -321,6 +378,7 @@ class HostProblem:
     coords: tuple | None = None
     graves_Qs: np.ndarray | None = None   # Qs [nz][ny][nx]: Graves' attenuation of an elastic medium (None = off)
     graves_Qs_freq: float = 1.0
+    ablexp: tuple | None = None   # (blk[6][7], Ex, Ey, Ez) of ablexp_profiles(), None = no sponge
     _keep: list = field(default_factory=list, repr=False)
 
     @property
@@ -411,6 +469,13 @@ class HostProblem:
             p.src.max_stage = 4
         for n in range(4):
             p.neigh[n] = self.neigh[n]
+        if self.ablexp is not None:
+            blk, Ex, Ey, Ez = self.ablexp
+            p.ablexp_enabled = 1
+            for n in range(6):
+                for q in range(7):
+                    p.ablexp_blk[n][q] = int(blk[n][q])
+            p.ablexp_Ex, p.ablexp_Ey, p.ablexp_Ez = abi.as_f(Ex), abi.as_f(Ey), abi.as_f(Ez)
         p.graves_Qs = abi.as_f(self.graves_Qs)
         p.graves_Qs_freq = float(self.graves_Qs_freq)
         keep.append(p)
@@ -418,9 +483,13 @@ class HostProblem:
 
 
 def make_source(prob: HostProblem, si, sj, sk, *, nt_total, kind="moment", mech=(1e16, 1e16, 1e16, 0, 0, 0),
-                fc=2.0, t0=0.5, stf_len=1.0, spatial="point", inc=(0.0, 0.0, 0.0), t_start=0.0):
+                fc=2.0, t0=0.5, stf_len=1.0, spatial="point", inc=(0.0, 0.0, 0.0), t_start=0.0, strict=1):
     """One point source by LOCAL physical index (0-based), Ricker STF; tables as forward/src_t.c:984-1174.
-    mech = (Mxx,Myy,Mzz,Myz,Mxz,Mxy) for kind='moment' (the .src file order), (Fx,Fy,Fz) for 'force'."""
+    mech = (Mxx,Myy,Mzz,Myz,Mxz,Mxy) for kind='moment' (the .src file order), (Fx,Fy,Fz) for 'force'.
+    A force whose footprint reaches the free surface (sk + half extent >= top row; half extent 0 for a point source, 3 for a
+    Gaussian one, forward/src_t.c:361-371, 416-421) is a SURFACE force when strict = 1 (par source_surface_force_strict): it gets
+    a rate table Fx_rate.. = d(stf)/dt * F (forward/src_t.c:1083-1090) and is applied through the traction / velocity slices of
+    src_set_surface_layer_for_force (forward/src_t.c:153-314)."""
     dt = f32(prob.dt)
     it_begin = int(t_start / float(dt))
     max_nt = int(float(f32(stf_len)) / float(dt) + 0.5)  # forward/src_t.c:550-552
@@ -429,6 +498,8 @@ def make_source(prob: HostProblem, si, sj, sk, *, nt_total, kind="moment", mech=
     tab = {n: np.zeros((1, max_nt, max_stage), f32) for n in ("Fx", "Fy", "Fz", "Mxx", "Myy", "Mzz", "Mxz", "Myz", "Mxy")}
     rate = {n: np.zeros((1, max_nt, max_stage), f32) for n in ("Fx_rate", "Fy_rate", "Fz_rate")}
     t_shift = f32(f32(t_start) - f32(f32(it_begin) * dt + f32(0.0)))
+    half = 3 if spatial == "gauss" else 0
+    surf = bool(kind == "force" and strict and prob.free_top and sk + half >= prob.nk - 1)
     for it in range(max_nt):
         for st in range(max_stage):
             t = f32(f32(f32(it) * dt + f32(RK_RHS_TIME[st]) * dt) - t_shift)
@@ -446,11 +517,16 @@ def make_source(prob: HostProblem, si, sj, sk, *, nt_total, kind="moment", mech=
                 tab["Fx"][0, it, st] = v * fx
                 tab["Fy"][0, it, st] = v * fy
                 tab["Fz"][0, it, st] = v * fz
+                if surf:
+                    r = fun_ricker_deriv(t, fc, t0)
+                    rate["Fx_rate"][0, it, st] = r * fx
+                    rate["Fy_rate"][0, it, st] = r * fy
+                    rate["Fz_rate"][0, it, st] = r * fz
     src = dict(total_number=1, max_nt=max_nt, max_stage=max_stage,
                si=np.array([si + NG], np.int32), sj=np.array([sj + NG], np.int32), sk=np.array([sk + NG], np.int32),
                si_inc=np.array([inc[0]], f32), sj_inc=np.array([inc[1]], f32), sk_inc=np.array([inc[2]], f32),
                it_begin=np.array([it_begin], np.int32), it_end=np.array([it_end], np.int32),
-               is_surface_force_strict=1, total_number_surface_force=0, force_rate_indx=np.zeros(1, np.int32),
+               is_surface_force_strict=int(strict), total_number_surface_force=1 if surf else 0, force_rate_indx=np.zeros(1, np.int32),
                itype_spatial_ext=abi.SRC_SPATIAL_GAUSSIAN if spatial == "gauss" else abi.SRC_SPATIAL_POINT,
                ext_half_npoint=3, ext_func_coef=1.5,
                force_actived=1 if kind == "force" else 0, moment_actived=1 if kind == "moment" else 0)

@@ -213,7 +213,10 @@ drv_rk_curv_col_allstep(
     int64_t *dd_indx = (int64_t *)malloc(sizeof(int64_t) * src->dd_total_number);
     for (int q = 0; q < src->dd_total_number; q++) dd_indx[q] = (int64_t)src->dd_indx[q];
     GPU(cgfd_b200_dd_set_points(ctx, src->dd_total_number, dd_indx, src->dd_vi_actived, src->dd_mij_actived, src->max_stage, src->dd_nt_per_read));
-    GPU(cgfd_b200_dd_load_block(ctx, 0, src->dd_nt_this_read, src->dd_vi, src->dd_mij));
+    /* the block src_dd_read2local left in memory holds dd_nt_per_read steps (forward/src_t.c:1841); dd_nt_this_read is only
+     * assigned by the reloads inside src_dd_accit_loadstf (forward/src_t.c:1962-1964) and is uninitialised here */
+    int nt_first = src->dd_nt_per_read < src->dd_max_nt ? src->dd_nt_per_read : src->dd_max_nt;
+    GPU(cgfd_b200_dd_load_block(ctx, 0, nt_first, src->dd_vi, src->dd_mij));
     free(dd_indx);
   }
 

@@ -103,6 +103,9 @@ void *cgfd_oracle_create(const cgfd_problem_t *p)
   s->Mxx = dupf(q->Mxx, nt); s->Myy = dupf(q->Myy, nt); s->Mzz = dupf(q->Mzz, nt);
   s->Mxz = dupf(q->Mxz, nt); s->Myz = dupf(q->Myz, nt); s->Mxy = dupf(q->Mxy, nt);
   s->Fx_rate = dupf(q->Fx_rate, nr); s->Fy_rate = dupf(q->Fy_rate, nr); s->Fz_rate = dupf(q->Fz_rate, nr);
+  if (p->ablexp_enabled) {
+    o->p.ablexp_Ex = dupf(p->ablexp_Ex, o->nx); o->p.ablexp_Ey = dupf(p->ablexp_Ey, o->ny); o->p.ablexp_Ez = dupf(p->ablexp_Ez, o->nz);
+  }
   return o;
 }
 
@@ -503,6 +506,18 @@ int cgfd_oracle_run(void *hd, int nsteps, float *w, int nrec, const int64_t *rec
         size_t m = f->siz * 9;
         if (s < CGFD_NUM_STAGES - 1) axpy_set(f->lev[1], f->lev[apre], a, f->lev[2], m);
         if (s == 0) axpy_set(f->lev[aend], f->lev[apre], b, f->lev[2], m); else axpy_add(f->lev[aend], b, f->lev[2], m);
+      }
+    }
+    if (o->p.ablexp_enabled) {
+      /* bdry_ablexp_apply (forward/bdry_t.c:840-890, called at forward/drv_rk_curv_col.c:483-485): W *= min(Ex[i], Ey[j], Ez[k]) in the shell blocks */
+      for (int c = 0; c < 9; c++) for (int nb = 0; nb < 6; nb++) {
+        const int32_t *B = o->p.ablexp_blk[nb];
+        if (B[0] != 1) continue;
+        for (int k = B[5]; k <= B[6]; k++) for (int j = B[3]; j <= B[4]; j++) for (int i = B[1]; i <= B[2]; i++) {
+          float m = (o->p.ablexp_Ex[i] < o->p.ablexp_Ey[j]) ? o->p.ablexp_Ex[i] : o->p.ablexp_Ey[j];
+          if (m > o->p.ablexp_Ez[k]) m = o->p.ablexp_Ez[k];
+          end[c * o->V + (size_t)k * o->S + (size_t)j * o->L + i] *= m;
+        }
       }
     }
     for (int ip = 0; ip < nrec; ip++) for (int c = 0; c < 9; c++) rec[((size_t)it * 9 + c) * nrec + ip] = end[c * o->V + rec_iptr[ip]];

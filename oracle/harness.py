@@ -110,9 +110,16 @@ def make_par(
     return par
 
 
-def write_case(workdir: str, par: dict, src_text: str, stations: list) -> str:
-    """stations: list of (name, is_coord, is_depth, x, y, z)."""
+def write_case(workdir: str, par: dict, src_text: str, stations: list, coords=None) -> str:
+    """stations: list of (name, is_coord, is_depth, x, y, z). coords = (x, y, z) arrays [nz][ny][nx] incl. ghosts: written as
+    IN/coord_px0_py0.nc for "grid_generation_method": {"import": "IN"} (gd_curv_coord_import, forward/gd_t.c:741-783)."""
     os.makedirs(os.path.join(workdir, "OUT"), exist_ok=True)
+    if coords is not None:
+        os.makedirs(os.path.join(workdir, "IN"), exist_ok=True)
+        x, y, z = coords
+        nz, ny, nx = x.shape
+        write_cgnc(os.path.join(workdir, "IN", "coord_px0_py0.nc"), {"k": nz, "j": ny, "i": nx},
+                   {"x": (("k", "j", "i"), x), "y": (("k", "j", "i"), y), "z": (("k", "j", "i"), z)})
     with open(os.path.join(workdir, "case.json"), "w") as f:
         json.dump(par, f, indent=1)
     with open(os.path.join(workdir, "case.src"), "w") as f:

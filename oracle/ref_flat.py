@@ -14,20 +14,21 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "_ref", "libcgfd_ref_flat.so")
+# the same adapter over the MIRROR restatement of the traction image (oracle/patch_timg.py): oracle of timg_mode = CGFD_TIMG_MIRROR
+LIB_MIRROR = os.path.join(HERE, "_ref", "libcgfd_ref_flat_mirror.so")
 fptr = C.POINTER(C.c_float)
 
 
-def available() -> bool:
-    return os.path.isfile(LIB)
+def available(mirror: bool = False) -> bool:
+    return os.path.isfile(LIB_MIRROR if mirror else LIB)
 
 
-_lib = None
+_libs = {}
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        L = C.CDLL(LIB)
+def lib(mirror: bool = False):
+    if mirror not in _libs:
+        L = C.CDLL(LIB_MIRROR if mirror else LIB)
         L.cgfd_ref_create.restype = C.c_void_p
         L.cgfd_ref_create.argtypes = [C.c_void_p]
         L.cgfd_ref_ncmp.argtypes = [C.c_void_p]
@@ -42,8 +43,8 @@ def lib():
         L.cgfd_ref_set_dd.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.c_int, C.c_int, C.c_int, C.c_int, fptr, fptr, C.c_char_p]
         L.cgfd_ref_run.argtypes = [C.c_void_p, C.c_int, fptr, C.c_int, C.POINTER(C.c_int64), fptr, C.c_char_p,
                                    C.POINTER(C.c_double)]
-        _lib = L
-    return _lib
+        _libs[mirror] = L
+    return _libs[mirror]
 
 
 def _f(a):
@@ -57,17 +58,18 @@ class _RefSolverImpl:
     def __init__(self, prob):
         self.prob = prob
         self._c = prob.to_c()
-        self.h = lib().cgfd_ref_create(C.byref(self._c))
+        self.L = lib(mirror=bool(getattr(prob, "timg_mode", 0)))
+        self.h = self.L.cgfd_ref_create(C.byref(self._c))
         if not self.h:
             raise RuntimeError("cgfd_ref_create failed")
-        self.ncmp = lib().cgfd_ref_ncmp(self.h)
+        self.ncmp = self.L.cgfd_ref_ncmp(self.h)
         if getattr(prob, "coords", None) is not None:
             x, y, z = (np.ascontiguousarray(a, np.float32) for a in prob.coords)
-            assert lib().cgfd_ref_set_coords(self.h, _f(x), _f(y), _f(z)) == 0
+            assert self.L.cgfd_ref_set_coords(self.h, _f(x), _f(y), _f(z)) == 0
         self.shape = (self.ncmp, prob.nz, prob.ny, prob.nx)
 
     def pml_aux_size(self, idim, iside):
-        return lib().cgfd_ref_pml_aux_size(self.h, idim, iside)
+        return self.L.cgfd_ref_pml_aux_size(self.h, idim, iside)
 
     def set_pml_aux(self, idim, iside, aux):
         """aux: the 9 components in use; the reference allocates ncmp per level (forward/bdry_t.c:300), the rest stays 0"""
@@ -75,11 +77,11 @@ class _RefSolverImpl:
         full = np.zeros(self.pml_aux_size(idim, iside), np.float32)
         assert aux.size == full.size // self.ncmp * 9
         full[:aux.size] = aux
-        assert lib().cgfd_ref_set_pml_aux(self.h, idim, iside, _f(full)) == 0
+        assert self.L.cgfd_ref_set_pml_aux(self.h, idim, iside, _f(full)) == 0
 
     def get_pml_aux(self, idim, iside, level=0):
         out = np.zeros(self.pml_aux_size(idim, iside), np.float32)
-        assert lib().cgfd_ref_get_pml_aux(self.h, idim, iside, level, _f(out)) == 0
+        assert self.L.cgfd_ref_get_pml_aux(self.h, idim, iside, level, _f(out)) == 0
         return out[:out.size // self.ncmp * 9].copy()
 
     def get_pml_aux_rhs(self, idim, iside):
@@ -89,7 +91,7 @@ class _RefSolverImpl:
         """the reference's gd_curv_metric_cal on this grid: array [10][nz][ny][nx]"""
         x, y, z = (np.ascontiguousarray(a, np.float32) for a in (x, y, z))
         out = np.zeros((10,) + x.shape, np.float32)
-        assert lib().cgfd_ref_metric_from_coords(self.h, _f(x), _f(y), _f(z), _f(out)) == 0
+        assert self.L.cgfd_ref_metric_from_coords(self.h, _f(x), _f(y), _f(z), _f(out)) == 0
         return out
 
     def set_dd(self, indx, vi, mij, nt_per_read):
@@ -100,7 +102,7 @@ class _RefSolverImpl:
         mij = None if mij is None else np.ascontiguousarray(mij, np.float32)
         self._ddtmp = tempfile.TemporaryDirectory()
         null = fptr()
-        rc = lib().cgfd_ref_set_dd(self.h, len(indx), indx.ctypes.data_as(C.POINTER(C.c_int64)), int(vi is not None), int(mij is not None),
+        rc = self.L.cgfd_ref_set_dd(self.h, len(indx), indx.ctypes.data_as(C.POINTER(C.c_int64)), int(vi is not None), int(mij is not None),
                                    nt, nt_per_read, _f(vi) if vi is not None else null, _f(mij) if mij is not None else null,
                                    os.path.join(self._ddtmp.name, "dd").encode())
         assert rc == 0
@@ -108,13 +110,13 @@ class _RefSolverImpl:
     def dvh2dvz(self):
         n = self.prob.nx * self.prob.ny * 9
         outs = [np.zeros(n, np.float32) for _ in range(4)]
-        assert lib().cgfd_ref_dvh2dvz(self.h, *[_f(o) for o in outs]) == 0
+        assert self.L.cgfd_ref_dvh2dvz(self.h, *[_f(o) for o in outs]) == 0
         return dict(matVx2Vz=outs[0], matVy2Vz=outs[1], matF2Vz=outs[2], matD=outs[3])
 
     def onestage(self, it, ipair, istage, w_cur):
         w_cur = np.ascontiguousarray(w_cur, np.float32)
         rhs = np.zeros(self.shape, np.float32)
-        assert lib().cgfd_ref_onestage(self.h, it, ipair, istage, _f(w_cur), _f(rhs)) == 0
+        assert self.L.cgfd_ref_onestage(self.h, it, ipair, istage, _f(w_cur), _f(rhs)) == 0
         return rhs
 
     def run(self, nsteps, w0=None, rec_iptr=None, outdir=None):
@@ -128,7 +130,7 @@ class _RefSolverImpl:
         if outdir is None:
             tmp = tempfile.TemporaryDirectory()
             outdir = tmp.name
-        rc = lib().cgfd_ref_run(self.h, nsteps, _f(w), nrec, idx.ctypes.data_as(C.POINTER(C.c_int64)), _f(rec),
+        rc = self.L.cgfd_ref_run(self.h, nsteps, _f(w), nrec, idx.ctypes.data_as(C.POINTER(C.c_int64)), _f(rec),
                                 outdir.encode(), C.byref(secs))
         assert rc == 0
         if tmp is not None:
@@ -167,7 +169,7 @@ class RefSolver:
 
     def __init__(self, prob):
         import multiprocessing as mp
-        lib()   # dlopen before the fork, the child inherits the mapping
+        lib(mirror=bool(getattr(prob, "timg_mode", 0)))   # dlopen before the fork, the child inherits the mapping
         ctx = mp.get_context("fork")
         self._conn, child = ctx.Pipe()
         self._p = ctx.Process(target=_serve, args=(child, prob), daemon=True)

@@ -122,3 +122,52 @@ def test_reference_dd_sources_and_graves_qs_run_on_cpu():
     R.set_dd(indx, vi, mij, 5)
     w0 = R.run(nt)[0]
     assert 0 < float(np.abs(wq[2]).max()) < float(np.abs(w0[2]).max())
+
+
+@need
+@pytest.mark.parametrize("spatial", ["point", "gauss"])
+def test_port_surface_force(spatial):
+    """strict surface force: traction / velocity slices + the matF2Vz term, one RHS evaluation in both zeta directions and a run"""
+    prob = util.surface_force_problem(spatial)
+    _stage(prob, 6, 2, 1, 5)
+    _stage(prob, 7, 5, 2, 6)
+    nt = 24
+    wr, _, _ = ref_flat.RefSolver(prob).run(nt)
+    wp, _, _ = port.PortSolver(prob).run(nt)
+    assert float(np.abs(wr[2]).max()) > 0
+    for c in range(9):
+        assert util.rel_l2(wp[c], wr[c]) <= 1e-5, (util.CMP[c], util.rel_l2(wp[c], wr[c]))
+
+
+@need
+def test_port_timg_mirror():
+    """CGFD_TIMG_MIRROR against the MIRROR copy of the reference (oracle/patch_timg.py); the two restatements of the traction
+    image differ (ZERO vs MIRROR: checked too, so that the test cannot pass by accident)"""
+    if not ref_flat.available(mirror=True):
+        pytest.skip("oracle/_ref/libcgfd_ref_flat_mirror.so not built")
+    from cgfd3d_b200 import abi
+    prob = util.small_problem(seed=7, timg_mode=abi.TIMG_MIRROR)
+    for ipair in (0, 1, 2, 3):   # both zeta directions
+        _stage(prob, 3, ipair, 0, 300 + ipair)
+        _stage(prob, 3, ipair, 1, 400 + ipair)
+    w, _ = util.random_state(prob, 9)
+    pz = util.small_problem(seed=7)
+    rz = ref_flat.RefSolver(pz).onestage(3, 0, 0, w)
+    rm = ref_flat.RefSolver(prob).onestage(3, 0, 0, w)
+    assert util.rel_max(rm[2], rz[2]) > 1e-3
+
+
+@need
+@pytest.mark.parametrize("mixed", [False, True])
+def test_port_sponge(mixed):
+    nt = 40
+    prob = util.sponge_problem(mixed=mixed, ni=30, nj=26, nk=24, nt_total=nt)
+    wr, _, _ = ref_flat.RefSolver(prob).run(nt)
+    wp, _, _ = port.PortSolver(prob).run(nt)
+    assert float(np.abs(wr[0]).max()) > 0
+    for c in range(9):
+        assert util.rel_l2(wp[c], wr[c]) <= 1e-5, (util.CMP[c], util.rel_l2(wp[c], wr[c]))
+    # the sponge does something: the same run without it differs
+    prob.ablexp = None
+    w0, _, _ = ref_flat.RefSolver(prob).run(nt)
+    assert util.rel_l2(w0[2], wr[2]) > 1e-3

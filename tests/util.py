@@ -72,3 +72,25 @@ def rel_l2(a, b):
     nb = np.linalg.norm(b)
     na = np.linalg.norm(a - b)
     return 0.0 if na == 0.0 else (na / nb if nb > 0 else float("inf"))
+
+
+def surface_force_problem(spatial="point", nt_total=40, **kw):
+    """hill problem with a strict surface force: a point force ON the top row, or a Gaussian one two rows below it whose
+    footprint reaches the surface (forward/src_t.c:361-371) -- both go through the traction / velocity slices of
+    src_set_surface_layer_for_force (forward/src_t.c:153-314) and the matF2Vz term (forward/sv_curv_col_el_iso.c:583-592)"""
+    prob = small_problem(src=None, nt_total=nt_total, **kw)
+    sk = prob.nk - 1 if spatial == "point" else prob.nk - 3
+    hs.make_source(prob, prob.ni // 2 + 1, prob.nj // 2, sk, nt_total=nt_total, kind="force", mech=(1e12, -2e12, 3e12),
+                   spatial=spatial, inc=(0.1, 0.2, -0.3), fc=3.0, t0=0.3, stf_len=0.8)
+    assert prob.src["total_number_surface_force"] == 1
+    return prob
+
+
+def sponge_problem(layers=6, mixed=False, **kw):
+    """exponential sponge (bdry_ablexp_apply, forward/bdry_t.c:840-890; the example script's default boundary) on the five
+    non-free faces; mixed = CFS-PML on the x faces and the sponge on y and bottom"""
+    kw.setdefault("pml_faces", ((0, 0), (0, 1)) if mixed else ())
+    prob = small_problem(**kw)
+    lay = [[0, 0] if mixed else [layers, layers], [layers, layers], [layers, 0]]
+    prob.ablexp = hs.ablexp_profiles(*prob.coords, prob.grid, lay, prob.dt)
+    return prob
