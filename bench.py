@@ -292,7 +292,7 @@ def run_ours(args):
             "wall_s_timed": round(tw1 - tw0, 4), "finite": finite,
         }
         if nranks == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(1, steps=args.cpu_steps)
+            out["cpu_baseline"] = cpu_baseline(os.cpu_count() or 1, steps=args.cpu_steps)
     S.close()
     if nranks > 1:
         dist.barrier()
@@ -312,39 +312,57 @@ def ncu_traffic(size):
 
 
 # ---- reference CPU arm --------------------------------------------------------------------------
-SAMPLE = (100, 100, 60)
+# The reference program itself (oracle/_ref/ref_main_zero = unmodified CGFD3D sources, compiled by oracle/Makefile where
+# /root/reference exists) on the bench workload: the SAME 400x400x200 Gaussian-hill problem, imported through the reference's own
+# coord_px?_py?.nc route and split over one MPI rank per host core (x-y blocks by gd_indx_set, real halo exchange every RK stage).
+# There is no MPI in the image: the ranks are forked by the shared-memory stand-in of oracle/shims/mpi_shim.c.
+REF_SIZE = (400, 400, 200)
+REF_HILL = (1000.0, 4000.0)     # the hill of build_rank_problem at this size (sigma = 0.1 * 400 * 100 m)
+REF_DT = 0.012
 
 
-def _ref_worker(q, steps):
-    from cgfd3d_b200 import hostsetup as hs
-    from oracle import ref_flat
-    ni, nj, nk = SAMPLE
-    prob = hs.build_problem(ni, nj, nk, topo="hill", hill=(1000.0, 1000.0), pml_layers=10, free_top=True, dt=0.012)
-    hs.make_source(prob, ni // 2, nj // 2, nk - 1 - 20, nt_total=100000)
-    R = ref_flat.RefSolver(prob)
-    _, _, secs = R.run(steps)
-    q.put(secs)
+def _rank_grid(n):
+    """px x py = n ranks, as square as possible, px >= py"""
+    py = int(n ** 0.5)
+    while n % py:
+        py -= 1
+    return n // py, py
 
 
-def cpu_baseline(cores, steps=4):
-    """reference CPU code (drv_rk_curv_col_allstep of oracle/_ref) on a bounded sample, `cores` replicas."""
-    import multiprocessing as mp
-    from oracle import ref_flat
-    if not ref_flat.available():
+def _ref_program_seconds(size, px, py, nt, hill):
+    """wall seconds of one run of the reference program with px*py ranks (set-up + nt time steps)"""
+    import shutil
+    import tempfile
+    from oracle import harness as H
+    wd = tempfile.mkdtemp(prefix="cgfd_refarm_")
+    try:
+        H.write_multirank_hill_case(wd, size, px, py, nt, REF_DT, hill=hill, pml_layers=10, src=H.moment_src(size[0] // 2, size[1] // 2, 20))
+        env = dict(os.environ, CGFD_SHIM_NPROCS=str(px * py), CGFD_SHIM_MSG_MB="64")
+        wall, out = H.run(H.ref_binary("ref_main_zero"), wd, verbose=1, timeout=3000, env=env)
+        sac = H.read_sac_dir(os.path.join(wd, "OUT"))
+        finite = all(bool(np.isfinite(v).all()) for v in sac.values()) and len(sac) > 0
+        return wall, finite
+    finally:
+        shutil.rmtree(wd, ignore_errors=True)
+
+
+def cpu_baseline(cores, steps=4, warm=1, size=REF_SIZE, hill=REF_HILL):
+    """Gpoint-updates/s of the reference program on `cores` ranks: (wall of a run of warm + steps steps) - (wall of a run of warm
+    steps), i.e. the time loop alone (the program's own timer has a resolution of one second)."""
+    from oracle import harness as H
+    if not H.have_ref("ref_main_zero"):
         return {"value": None, "unit": "Gpoint-updates/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    ps = [ctx.Process(target=_ref_worker, args=(q, steps)) for _ in range(cores)]
-    for p in ps:
-        p.start()
-    secs = [q.get() for _ in ps]
-    for p in ps:
-        p.join()
-    npts = SAMPLE[0] * SAMPLE[1] * SAMPLE[2]
-    v = cores * npts * steps / max(secs) / 1e9
-    return {"value": round(v, 6), "unit": "Gpoint-updates/s", "cores": cores, "kind": "reference",
-            "sample": "%d steps of the same physics (hill, CFS-PML 10x5, free surface) on a %dx%dx%d block; %d independent single-rank "
-                      "replicas of the unmodified reference (no MPI in the image: upper bound, no halo cost)" % ((steps,) + SAMPLE + (cores,))}
+    px, py = _rank_grid(cores)
+    t_w, ok1 = _ref_program_seconds(size, px, py, warm, hill)
+    t_wk, ok2 = _ref_program_seconds(size, px, py, warm + steps, hill)
+    secs = max(t_wk - t_w, 1e-6)
+    npts = size[0] * size[1] * size[2]
+    return {"value": round(npts * steps / secs / 1e9, 6), "unit": "Gpoint-updates/s", "cores": cores, "kind": "reference",
+            "ranks": "%dx%d" % (px, py), "seconds_per_step": round(secs / steps, 4), "setup_s": round(t_w, 2), "finite": bool(ok1 and ok2),
+            "sample": "%d RK4 steps of the bench workload itself (isotropic, Gaussian hill %dx%dx%d through gd_curv_coord_import, CFS-PML 10x5, "
+                      "free surface, 1 moment source) by the unmodified reference program on %dx%d ranks with halo exchange "
+                      "(fork/shared-memory MPI stand-in: no MPI in the image); time = wall(%d steps) - wall(%d steps)"
+                      % ((steps,) + tuple(size) + (px, py, warm + steps, warm))}
 
 
 def run_reference(args):
@@ -352,24 +370,22 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    K, W = args.steps, args.warmup
-    # one "step" of this arm = one RK4 step of the sample on every core; W warm-up steps are folded into the same call
-    steps = max(1, min(K, 8))
-    cpu_baseline(min(cores, 2), steps=1)  # warm-up (page-in)
+    K = max(1, min(args.steps, 6))
     t0 = time.time()
-    cb = cpu_baseline(cores, steps=steps)
+    cb = cpu_baseline(cores, steps=K, warm=1)
+    # one core, for scale: a 200x200x100 cut of the same physics (the full block needs minutes per step on one core)
+    one = cpu_baseline(1, steps=2, warm=1, size=(200, 200, 100), hill=(1000.0, 2000.0)) if args.one_core else None
     wall = time.time() - t0
-    out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "Gpoint-updates/s", "n_gpus": args.gpus, "steps": steps,
-           "warmup": 1, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-           "data": "synthetic",
-           "config": {"workload": "isotropic elastic, Gaussian-hill topography, CFS-PML 10 layers x 5 faces, traction-image free surface; "
-                                  "CPU sample %dx%dx%d per core" % SAMPLE},
+    out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "Gpoint-updates/s", "n_gpus": args.gpus, "steps": K,
+           "warmup": 1, "ms_per_step": None if cb["value"] is None else round(cb["seconds_per_step"] * 1e3, 2), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "isotropic elastic, Gaussian-hill topography (curvilinear), %dx%dx%d, CFS-PML 10 layers x 5 faces, "
+                                  "traction-image free surface, 1 moment source; reference CPU program on %s host ranks" % (REF_SIZE + (cb.get("ranks"),))},
            "cpu_baseline": cb,
            "e2e": {"value": cb["value"], "unit": "Gpoint-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "wall_s": round(wall, 2)}
-    if cb["value"] is not None:
-        npts = SAMPLE[0] * SAMPLE[1] * SAMPLE[2]
-        out["ms_per_step"] = round(cores * npts / (cb["value"] * 1e9) * 1e3, 3)
+    if one:
+        out["cpu_one_core"] = one
     emit(out)
 
 
@@ -408,6 +424,7 @@ def main():
                     help="constitutive law (default iso = the BASELINE.json metric; the others are side measurements)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--one-core", action="store_true", help="--impl reference: also time one core on a 200x200x100 cut")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl != "reference":
         args.warmup = 3

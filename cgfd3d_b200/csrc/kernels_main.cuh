@@ -316,59 +316,58 @@ __global__ void __launch_bounds__(TX *TY, Lay<MED>::BLOCKS) k_main_tma(const Sta
 }
 
 // =============================================================================================
-// free-surface rows: k in [nk2-3, nk2], one thread per point, neighbours straight from L1/L2
+// free-surface rows: k in [nk2-3, nk2], one thread per point and HALF of the RHS, neighbours straight from L1/L2.
+// HALF 0 = the six stress components (needs the velocity derivatives only: reduced-order / matrix Dz, Hooke, PML part 0,
+// attenuation), HALF 1 = the three velocity components (needs the stress derivatives only: momentum, traction image, PML part 1).
+// The two halves share nothing but read-only inputs and write disjoint components, so they run as independent blocks of one
+// launch (blockIdx.z = row * 2 + half): twice the parallelism at ~half the registers of a thread that does both (168 registers,
+// 12 warps per SM: latency bound, ncu r1x: long-scoreboard 4.5 per issue, 30 % of the DRAM rate, 6 % of a step for 2 % of the points).
 // =============================================================================================
 #ifndef CGFD_VIS_PREFETCH
 #define CGFD_VIS_PREFETCH 0
 #endif
-#ifndef CGFD_TOP_SKIP
-#define CGFD_TOP_SKIP 0
-#endif
-#ifndef CGFD_TOP_BLOCKS
-#define CGFD_TOP_BLOCKS 3   // resident blocks per SM the free-surface kernel is compiled for (168 registers at 3)
-#endif
-template <int DX, int DY, int DZ, int KIND, int MED>
-__global__ void __launch_bounds__(128, CGFD_TOP_BLOCKS) k_top(const StageArgs P)
+template <int DX, int DY, int DZ, int KIND, int MED, int HALF>
+__device__ __forceinline__ void top_half(const StageArgs &P, int k)
 {
   // 32 x 4 points per block: the eta neighbours of a row are mostly rows of the same block (L1 hits)
   const int i = P.ni1 + blockIdx.x * 32 + threadIdx.x;
   const int j = P.nj1 + blockIdx.y * 4 + threadIdx.y;
-  const int k = P.kbeg + blockIdx.z;
   if (i > P.ni2 || j > P.nj2 || k > P.kend) return;
   const size_t L = P.siz_line, S = P.siz_slice, V = P.siz_vol;
   const size_t p = (size_t)k * S + (size_t)j * L + i;
   const size_t p2 = (size_t)j * P.nx + i;
   const float *cx = c_fd.coef[DX], *cy = c_fd.coef[DY], *cz = c_fd.coef[DZ];
   constexpr int FX = Ofs<DX>::first, FY = Ofs<DY>::first, FZ = Ofs<DZ>::first;
+  constexpr int C0 = HALF ? 0 : 3, NC = HALF ? 3 : 6;   // components this half updates
+  constexpr int D0 = HALF ? 3 : 0, ND = HALF ? 6 : 3;   // components whose derivatives it needs
   const int nsurf = P.nk2 - k;   // 0 at the surface
+  const int kmin = P.nk2 - (FZ + 4);   // first row whose momentum RHS is the traction-image one
 
-  Deriv d;
-  float cur[9], pv[9], ev[9];
+  float cur[NC], pv[NC], ev[NC];
 #pragma unroll
-  for (int c = 0; c < 9; c++) {
-    if (KIND != KIND_FIRST) pv[c] = __ldg(P.pre + c * V + p);
-    if (KIND == KIND_LAST) ev[c] = P.end[c * V + p];
+  for (int c = 0; c < NC; c++) {
+    cur[c] = __ldg(P.cur + (C0 + c) * V + p);
+    if (KIND != KIND_FIRST) pv[c] = __ldg(P.pre + (C0 + c) * V + p);
+    if (KIND == KIND_LAST) ev[c] = P.end[(C0 + c) * V + p];
   }
-#if CGFD_TOP_SKIP
-  // EXPERIMENT (build switch, off by default, not yet validated on the GPU): in the rows where the traction image replaces the
-  // momentum RHS, the 18 plain derivatives of the stress components are only needed by the PML terms - skip their 90 loads at
-  // every point outside the PML slabs.
-  bool skip_stress = (k >= P.nk2 - (FZ + 4));
+  // In the rows where the traction image replaces the momentum RHS, the plain derivatives of the stress components are only
+  // needed by the PML terms: outside the slabs their 90 loads are skipped.
+  bool need_plain = true;
+  if (HALF == 1 && k >= kmin) {
+    need_plain = false;
 #pragma unroll
-  for (int ax = 0; ax < 3; ax++)
+    for (int ax = 0; ax < 3; ax++)
 #pragma unroll
-    for (int sd = 0; sd < 2; sd++) {
-      const PmlFaceDev &F = P.pml[ax][sd];
-      if (F.on && i >= F.i1 && i <= F.i2 && j >= F.j1 && j <= F.j2 && k >= F.k1 && k <= F.k2) skip_stress = false;
-    }
-#else
-  constexpr bool skip_stress = false;
-#endif
+      for (int sd = 0; sd < 2; sd++) {
+        const PmlFaceDev &F = P.pml[ax][sd];
+        if (F.on && i >= F.i1 && i <= F.i2 && j >= F.j1 && j <= F.j2 && k >= F.k1 && k <= F.k2) need_plain = true;
+      }
+  }
+  Deriv d;
 #pragma unroll
-  for (int c = 0; c < 9; c++) {
+  for (int c = D0; c < D0 + ND; c++) {
+    if (!need_plain) { d.x[c] = d.y[c] = d.z[c] = 0.0f; continue; }
     const float *w = P.cur + c * V + p;
-    cur[c] = __ldg(w);
-    if (c >= 3 && skip_stress) { d.x[c] = d.y[c] = d.z[c] = 0.0f; continue; }
     d.x[c] = cx[0] * __ldg(w + FX) + cx[1] * __ldg(w + FX + 1) + cx[2] * __ldg(w + FX + 2) + cx[3] * __ldg(w + FX + 3)
            + cx[4] * __ldg(w + FX + 4);
     d.y[c] = cy[0] * __ldg(w + (FY + 0) * (long)L) + cy[1] * __ldg(w + (FY + 1) * (long)L)
@@ -383,292 +382,126 @@ __global__ void __launch_bounds__(128, CGFD_TOP_BLOCKS) k_top(const StageArgs P)
   Med<MED> md;
   md.load([&](int n) { return __ldg(P.media[n] + p); });
   const float slw = md.slw;
-
-  // --- velocity gradient along zeta in the top three rows (vlow, iso.c:503-593)
-  if (nsurf == 0) {
-    // the surface point-force term exists in the isotropic operator only (iso.c:583-592)
-    constexpr bool FSRC = (MED == MED_ISO || MED == MED_VIS);
-    const float *A = P.matVx2Vz + p2 * 9, *B = P.matVy2Vz + p2 * 9, *F = P.matF2Vz + p2 * 9;
-    float sx = (FSRC && P.VxSrc) ? __ldg(P.VxSrc + p2) : 0.0f, sy = (FSRC && P.VySrc) ? __ldg(P.VySrc + p2) : 0.0f,
-          sz = (FSRC && P.VzSrc) ? __ldg(P.VzSrc + p2) : 0.0f;
-#pragma unroll
-    for (int r = 0; r < 3; r++) {
-      float v = __ldg(A + 3 * r + 0) * d.x[VX] + __ldg(A + 3 * r + 1) * d.x[VY] + __ldg(A + 3 * r + 2) * d.x[VZ]
-              + __ldg(B + 3 * r + 0) * d.y[VX] + __ldg(B + 3 * r + 1) * d.y[VY] + __ldg(B + 3 * r + 2) * d.y[VZ];
-      if (FSRC) v += __ldg(F + 3 * r + 0) * sx + __ldg(F + 3 * r + 1) * sy + __ldg(F + 3 * r + 2) * sz;
-      d.z[r] = v;
-    }
-  } else if (nsurf == 1) {
-    const long o0 = DZ ? -(long)S : 0, o1 = DZ ? 0 : (long)S;
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-      const float *w = P.cur + c * V + p;
-      d.z[c] = c_fd.lay2[DZ][0] * __ldg(w + o0) + c_fd.lay2[DZ][1] * __ldg(w + o1);
-    }
-  } else if (nsurf == 2) {
-    const long o0 = DZ ? -2 * (long)S : 0;
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-      const float *w = P.cur + c * V + p + o0;
-      d.z[c] = c_fd.lay3[DZ][0] * __ldg(w) + c_fd.lay3[DZ][1] * __ldg(w + S) + c_fd.lay3[DZ][2] * __ldg(w + 2 * S);
-    }
-  }
-
   float h[9];
-  momentum(d, m, slw, h);
-  hooke<MED>(d, m, md, h);
 
-  // --- traction image: momentum RHS in conservative form (sv_curv_col_el.c:84-304)
-  const int kmin = P.nk2 - (FZ + 4);
-  if (k >= kmin) {
-    const int n_free = P.nk2 - k - FZ;
-    const float jac = __ldg(P.metric[M_JAC] + p);
-    const float slwjac = slw / jac;
-    // component triplets (T1,T2,T3) with flux_n = J*(e_x T1 + e_y T2 + e_z T3)
-    const int T1[3] = {TXX, TXY, TXZ}, T2[3] = {TXY, TYY, TYZ}, T3[3] = {TXZ, TYZ, TZZ};
-    const float *Ts[3] = {P.TxSrc, P.TySrc, P.TzSrc};
-    // the xi / eta flux derivatives are accumulated term by term (left to right, like M_FD_NOINDX, forward/fd_t.h:33-38);
-    // only the zeta fluxes are kept, because the image terms refer back to them
-    float Dxf[3], Dyf[3], fz[3][5];
+  if (HALF == 0) {
+    // --- velocity gradient along zeta in the top three rows (vlow, iso.c:503-593)
+    if (nsurf == 0) {
+      // the surface point-force term exists in the isotropic operator only (iso.c:583-592)
+      constexpr bool FSRC = (MED == MED_ISO || MED == MED_VIS);
+      const float *A = P.matVx2Vz + p2 * 9, *B = P.matVy2Vz + p2 * 9, *F = P.matF2Vz + p2 * 9;
+      float sx = (FSRC && P.VxSrc) ? __ldg(P.VxSrc + p2) : 0.0f, sy = (FSRC && P.VySrc) ? __ldg(P.VySrc + p2) : 0.0f,
+            sz = (FSRC && P.VzSrc) ? __ldg(P.VzSrc + p2) : 0.0f;
 #pragma unroll
-    for (int n = 0; n < 5; n++) {
-      {
-        const size_t pp = p + (FX + n);
-        const float jn = __ldg(P.metric[M_JAC] + pp), ex = __ldg(P.metric[M_XIX] + pp), ey = __ldg(P.metric[M_XIY] + pp),
-                    ez = __ldg(P.metric[M_XIZ] + pp);
-#pragma unroll
-        for (int v = 0; v < 3; v++) {
-          const float f = jn * (ex * __ldg(P.cur + T1[v] * V + pp) + ey * __ldg(P.cur + T2[v] * V + pp) + ez * __ldg(P.cur + T3[v] * V + pp));
-          if (n == 0) Dxf[v] = cx[0] * f; else Dxf[v] += cx[n] * f;
-        }
+      for (int r = 0; r < 3; r++) {
+        float v = __ldg(A + 3 * r + 0) * d.x[VX] + __ldg(A + 3 * r + 1) * d.x[VY] + __ldg(A + 3 * r + 2) * d.x[VZ]
+                + __ldg(B + 3 * r + 0) * d.y[VX] + __ldg(B + 3 * r + 1) * d.y[VY] + __ldg(B + 3 * r + 2) * d.y[VZ];
+        if (FSRC) v += __ldg(F + 3 * r + 0) * sx + __ldg(F + 3 * r + 1) * sy + __ldg(F + 3 * r + 2) * sz;
+        d.z[r] = v;
       }
-      {
-        const size_t pp = p + (long)(FY + n) * (long)L;
-        const float jn = __ldg(P.metric[M_JAC] + pp), ex = __ldg(P.metric[M_ETX] + pp), ey = __ldg(P.metric[M_ETY] + pp),
-                    ez = __ldg(P.metric[M_ETZ] + pp);
+    } else if (nsurf == 1) {
+      const long o0 = DZ ? -(long)S : 0, o1 = DZ ? 0 : (long)S;
 #pragma unroll
-        for (int v = 0; v < 3; v++) {
-          const float f = jn * (ex * __ldg(P.cur + T1[v] * V + pp) + ey * __ldg(P.cur + T2[v] * V + pp) + ez * __ldg(P.cur + T3[v] * V + pp));
-          if (n == 0) Dyf[v] = cy[0] * f; else Dyf[v] += cy[n] * f;
-        }
+      for (int c = 0; c < 3; c++) {
+        const float *w = P.cur + c * V + p;
+        d.z[c] = c_fd.lay2[DZ][0] * __ldg(w + o0) + c_fd.lay2[DZ][1] * __ldg(w + o1);
       }
-      if (n < n_free) {
-        const size_t pp = p + (long)(FZ + n) * (long)S;
-        const float jn = __ldg(P.metric[M_JAC] + pp), ex = __ldg(P.metric[M_ZTX] + pp), ey = __ldg(P.metric[M_ZTY] + pp),
-                    ez = __ldg(P.metric[M_ZTZ] + pp);
+    } else if (nsurf == 2) {
+      const long o0 = DZ ? -2 * (long)S : 0;
 #pragma unroll
-        for (int v = 0; v < 3; v++)
-          fz[v][n] = jn * (ex * __ldg(P.cur + T1[v] * V + pp) + ey * __ldg(P.cur + T2[v] * V + pp) + ez * __ldg(P.cur + T3[v] * V + pp));
+      for (int c = 0; c < 3; c++) {
+        const float *w = P.cur + c * V + p + o0;
+        d.z[c] = c_fd.lay3[DZ][0] * __ldg(w) + c_fd.lay3[DZ][1] * __ldg(w + S) + c_fd.lay3[DZ][2] * __ldg(w + 2 * S);
       }
     }
-#pragma unroll
-    for (int v = 0; v < 3; v++) {
-      const float ts = Ts[v] ? __ldg(Ts[v] + p2) : 0.0f;
+    hooke<MED>(d, m, md, h);
+    pml_all<KIND, 0, MED>(P, i, j, k, d, m, md, h);
+    if constexpr (MED == MED_VIS) atten_update<KIND>(P, p, md.lam, md.mu, h);
+  } else {
+    if (k < kmin) momentum(d, m, slw, h);
+    else {
+      // --- traction image: momentum RHS in conservative form (sv_curv_col_el.c:84-304)
+      const int n_free = P.nk2 - k - FZ;
+      const float jac = __ldg(P.metric[M_JAC] + p);
+      const float slwjac = slw / jac;
+      // component triplets (T1,T2,T3) with flux_n = J*(e_x T1 + e_y T2 + e_z T3)
+      const int T1[3] = {TXX, TXY, TXZ}, T2[3] = {TXY, TYY, TYZ}, T3[3] = {TXZ, TYZ, TZZ};
+      const float *Ts[3] = {P.TxSrc, P.TySrc, P.TzSrc};
+      // the xi / eta flux derivatives are accumulated term by term (left to right, like M_FD_NOINDX, forward/fd_t.h:33-38);
+      // only the zeta fluxes are kept, because the image terms refer back to them
+      float Dxf[3], Dyf[3], fz[3][5];
 #pragma unroll
       for (int n = 0; n < 5; n++) {
-        if (n == n_free) fz[v][n] = ts;
-        else if (n > n_free) {
-          const int im = 2 * n_free - n;    // mirror index inside the window
-          float below;
-          if (im >= 0) below = fz[v][im < 0 ? 0 : im];
-          else if (P.timg_mode == 0) below = 0.0f;
-          else {
-            // image row k + indx[n] - 2(n - n_free) (sv_curv_col_el.c:154-159)
-            const size_t pp = p + (long)(FZ + n - 2 * (n - n_free)) * (long)S;
-            const float jn = __ldg(P.metric[M_JAC] + pp), ex = __ldg(P.metric[M_ZTX] + pp), ey = __ldg(P.metric[M_ZTY] + pp),
-                        ez = __ldg(P.metric[M_ZTZ] + pp);
-            below = jn * (ex * __ldg(P.cur + T1[v] * V + pp) + ey * __ldg(P.cur + T2[v] * V + pp) + ez * __ldg(P.cur + T3[v] * V + pp));
+        {
+          const size_t pp = p + (FX + n);
+          const float jn = __ldg(P.metric[M_JAC] + pp), ex = __ldg(P.metric[M_XIX] + pp), ey = __ldg(P.metric[M_XIY] + pp),
+                      ez = __ldg(P.metric[M_XIZ] + pp);
+#pragma unroll
+          for (int v = 0; v < 3; v++) {
+            const float f = jn * (ex * __ldg(P.cur + T1[v] * V + pp) + ey * __ldg(P.cur + T2[v] * V + pp) + ez * __ldg(P.cur + T3[v] * V + pp));
+            if (n == 0) Dxf[v] = cx[0] * f; else Dxf[v] += cx[n] * f;
           }
-          fz[v][n] = 2.0f * ts - below;
+        }
+        {
+          const size_t pp = p + (long)(FY + n) * (long)L;
+          const float jn = __ldg(P.metric[M_JAC] + pp), ex = __ldg(P.metric[M_ETX] + pp), ey = __ldg(P.metric[M_ETY] + pp),
+                      ez = __ldg(P.metric[M_ETZ] + pp);
+#pragma unroll
+          for (int v = 0; v < 3; v++) {
+            const float f = jn * (ex * __ldg(P.cur + T1[v] * V + pp) + ey * __ldg(P.cur + T2[v] * V + pp) + ez * __ldg(P.cur + T3[v] * V + pp));
+            if (n == 0) Dyf[v] = cy[0] * f; else Dyf[v] += cy[n] * f;
+          }
+        }
+        if (n < n_free) {
+          const size_t pp = p + (long)(FZ + n) * (long)S;
+          const float jn = __ldg(P.metric[M_JAC] + pp), ex = __ldg(P.metric[M_ZTX] + pp), ey = __ldg(P.metric[M_ZTY] + pp),
+                      ez = __ldg(P.metric[M_ZTZ] + pp);
+#pragma unroll
+          for (int v = 0; v < 3; v++)
+            fz[v][n] = jn * (ex * __ldg(P.cur + T1[v] * V + pp) + ey * __ldg(P.cur + T2[v] * V + pp) + ez * __ldg(P.cur + T3[v] * V + pp));
         }
       }
-      float Dz = cz[0] * fz[v][0]; Dz += cz[1] * fz[v][1]; Dz += cz[2] * fz[v][2]; Dz += cz[3] * fz[v][3]; Dz += cz[4] * fz[v][4];
-      h[v] = (Dxf[v] + Dyf[v] + Dz) * slwjac;
+#pragma unroll
+      for (int v = 0; v < 3; v++) {
+        const float ts = Ts[v] ? __ldg(Ts[v] + p2) : 0.0f;
+#pragma unroll
+        for (int n = 0; n < 5; n++) {
+          if (n == n_free) fz[v][n] = ts;
+          else if (n > n_free) {
+            const int im = 2 * n_free - n;    // mirror index inside the window
+            float below;
+            if (im >= 0) below = fz[v][im < 0 ? 0 : im];
+            else if (P.timg_mode == 0) below = 0.0f;
+            else {
+              // image row k + indx[n] - 2(n - n_free) (sv_curv_col_el.c:154-159)
+              const size_t pp = p + (long)(FZ + n - 2 * (n - n_free)) * (long)S;
+              const float jn = __ldg(P.metric[M_JAC] + pp), ex = __ldg(P.metric[M_ZTX] + pp), ey = __ldg(P.metric[M_ZTY] + pp),
+                          ez = __ldg(P.metric[M_ZTZ] + pp);
+              below = jn * (ex * __ldg(P.cur + T1[v] * V + pp) + ey * __ldg(P.cur + T2[v] * V + pp) + ez * __ldg(P.cur + T3[v] * V + pp));
+            }
+            fz[v][n] = 2.0f * ts - below;
+          }
+        }
+        float Dz = cz[0] * fz[v][0]; Dz += cz[1] * fz[v][1]; Dz += cz[2] * fz[v][2]; Dz += cz[3] * fz[v][3]; Dz += cz[4] * fz[v][4];
+        h[v] = (Dxf[v] + Dyf[v] + Dz) * slwjac;
+      }
     }
+    pml_all<KIND, 1, MED>(P, i, j, k, d, m, md, h);
   }
-
-  pml_all<KIND, 0, MED>(P, i, j, k, d, m, md, h);
-  pml_all<KIND, 1, MED>(P, i, j, k, d, m, md, h);
-  if constexpr (MED == MED_VIS) atten_update<KIND>(P, p, md.lam, md.mu, h);
   const float qatt = (KIND == KIND_LAST && P.qatt) ? __ldg(P.qatt + p) : 1.0f;
 #pragma unroll
-  for (int c = 0; c < 9; c++) rk_wave<KIND>(P.tmp, P.end, c * V + p, cur[c], pv[c], ev[c], h[c], P.a, P.b, P.c, qatt);
+  for (int c = 0; c < NC; c++) rk_wave<KIND>(P.tmp, P.end, (C0 + c) * V + p, cur[c], pv[c], ev[c], h[C0 + c], P.a, P.b, P.c, qatt);
 }
-
-
-#ifndef CGFD_TOP_TILED
-#define CGFD_TOP_TILED 0
+#ifndef CGFD_TOP_BLOCKS
+#define CGFD_TOP_BLOCKS 4   // resident blocks of 128 threads per SM the free-surface kernel is compiled for (<= 128 registers)
 #endif
-#if CGFD_TOP_TILED
-// =============================================================================================
-// EXPERIMENT (build switch -DCGFD_TOP_TILED=1, off by default, NOT yet validated on a GPU): k_top with the x-y neighbours of the
-// wavefield and of the metric staged in shared memory. Same arithmetic, term by term, as k_top (results must be bit-identical);
-// only where the operands come from differs: one block = 32 x 8 points of ONE of the four rows, a cooperative coalesced load of
-//   * the 9 wavefield components on the (32 + 2*4) x (8 + 4) halo tile of the row (columns i0-4 .. i0+35, rows j0-YL .. j0+11-YL),
-//   * jac, xi_x, xi_y, xi_z, eta_x, eta_y, eta_z on the same tile (the traction-image fluxes need them at the x / y neighbours),
-// and everything along zeta (same column, coalesced) straight from global memory as before.
-// =============================================================================================
-constexpr int TT_X = 32, TT_Y = 8, TT_SX = TT_X + 2 * HALO_X, TT_SY = TT_Y + 4, TT_NM = 7;
 template <int DX, int DY, int DZ, int KIND, int MED>
-__global__ void __launch_bounds__(TT_X *TT_Y, 2) k_top_tiled(const StageArgs P)
+__global__ void __launch_bounds__(128, CGFD_TOP_BLOCKS) k_top(const StageArgs P)
 {
-  __shared__ float s_cur[9][TT_SY][TT_SX];
-  __shared__ float s_met[TT_NM][TT_SY][TT_SX];   // jac, xi_x, xi_y, xi_z, eta_x, eta_y, eta_z
-  constexpr int YL = Ofs<DY>::left;
-  const int i0 = P.ni1 + blockIdx.x * TT_X, j0 = P.nj1 + blockIdx.y * TT_Y;
-  const int k = P.kbeg + blockIdx.z;
-  const size_t L = P.siz_line, S = P.siz_slice, V = P.siz_vol;
-  {
-    const int met_of[TT_NM] = {M_JAC, M_XIX, M_XIY, M_XIZ, M_ETX, M_ETY, M_ETZ};
-    const int t = threadIdx.y * TT_X + threadIdx.x;
-    for (int e = t; e < TT_SY * TT_SX; e += TT_X * TT_Y) {
-      const int sx = e % TT_SX, sy = e / TT_SX;
-      const int gi = i0 - HALO_X + sx, gj = j0 - YL + sy;
-      const bool in = gi >= 0 && gi < P.nx && gj >= 0 && gj < P.ny;
-      const size_t q = (size_t)k * S + (size_t)gj * L + gi;
-#pragma unroll
-      for (int c = 0; c < 9; c++) s_cur[c][sy][sx] = in ? __ldg(P.cur + c * V + q) : 0.0f;
-#pragma unroll
-      for (int m = 0; m < TT_NM; m++) s_met[m][sy][sx] = in ? __ldg(P.metric[met_of[m]] + q) : 0.0f;
-    }
-  }
-  __syncthreads();
-  const int i = i0 + threadIdx.x, j = j0 + threadIdx.y;
-  if (i > P.ni2 || j > P.nj2 || k > P.kend) return;
-  const int cx0 = threadIdx.x + HALO_X, cy0 = threadIdx.y + YL;   // this thread's point inside the tiles
-  const size_t p = (size_t)k * S + (size_t)j * L + i;
-  const size_t p2 = (size_t)j * P.nx + i;
-  const float *cx = c_fd.coef[DX], *cy = c_fd.coef[DY], *cz = c_fd.coef[DZ];
-  constexpr int FX = Ofs<DX>::first, FY = Ofs<DY>::first, FZ = Ofs<DZ>::first;
-  const int nsurf = P.nk2 - k;   // 0 at the surface
-
-  Deriv d;
-  float cur[9], pv[9], ev[9];
-#pragma unroll
-  for (int c = 0; c < 9; c++) {
-    if (KIND != KIND_FIRST) pv[c] = __ldg(P.pre + c * V + p);
-    if (KIND == KIND_LAST) ev[c] = P.end[c * V + p];
-  }
-#pragma unroll
-  for (int c = 0; c < 9; c++) {
-    const float *w = P.cur + c * V + p;
-    const float(*t)[TT_SX] = s_cur[c];
-    cur[c] = t[cy0][cx0];
-    d.x[c] = cx[0] * t[cy0][cx0 + FX] + cx[1] * t[cy0][cx0 + FX + 1] + cx[2] * t[cy0][cx0 + FX + 2] + cx[3] * t[cy0][cx0 + FX + 3]
-           + cx[4] * t[cy0][cx0 + FX + 4];
-    d.y[c] = cy[0] * t[cy0 + FY][cx0] + cy[1] * t[cy0 + FY + 1][cx0] + cy[2] * t[cy0 + FY + 2][cx0] + cy[3] * t[cy0 + FY + 3][cx0]
-           + cy[4] * t[cy0 + FY + 4][cx0];
-    d.z[c] = cz[0] * __ldg(w + (FZ + 0) * (long)S) + cz[1] * __ldg(w + (FZ + 1) * (long)S)
-           + cz[2] * __ldg(w + (FZ + 2) * (long)S) + cz[3] * __ldg(w + (FZ + 3) * (long)S)
-           + cz[4] * __ldg(w + (FZ + 4) * (long)S);
-  }
-  const Met m = load_metric(P, p);
-  Med<MED> md;
-  md.load([&](int n) { return __ldg(P.media[n] + p); });
-  const float slw = md.slw;
-
-  if (nsurf == 0) {
-    constexpr bool FSRC = (MED == MED_ISO || MED == MED_VIS);
-    const float *A = P.matVx2Vz + p2 * 9, *B = P.matVy2Vz + p2 * 9, *F = P.matF2Vz + p2 * 9;
-    float sx = (FSRC && P.VxSrc) ? __ldg(P.VxSrc + p2) : 0.0f, sy = (FSRC && P.VySrc) ? __ldg(P.VySrc + p2) : 0.0f,
-          sz = (FSRC && P.VzSrc) ? __ldg(P.VzSrc + p2) : 0.0f;
-#pragma unroll
-    for (int r = 0; r < 3; r++) {
-      float v = __ldg(A + 3 * r + 0) * d.x[VX] + __ldg(A + 3 * r + 1) * d.x[VY] + __ldg(A + 3 * r + 2) * d.x[VZ]
-              + __ldg(B + 3 * r + 0) * d.y[VX] + __ldg(B + 3 * r + 1) * d.y[VY] + __ldg(B + 3 * r + 2) * d.y[VZ];
-      if (FSRC) v += __ldg(F + 3 * r + 0) * sx + __ldg(F + 3 * r + 1) * sy + __ldg(F + 3 * r + 2) * sz;
-      d.z[r] = v;
-    }
-  } else if (nsurf == 1) {
-    const long o0 = DZ ? -(long)S : 0, o1 = DZ ? 0 : (long)S;
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-      const float *w = P.cur + c * V + p;
-      d.z[c] = c_fd.lay2[DZ][0] * __ldg(w + o0) + c_fd.lay2[DZ][1] * __ldg(w + o1);
-    }
-  } else if (nsurf == 2) {
-    const long o0 = DZ ? -2 * (long)S : 0;
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-      const float *w = P.cur + c * V + p + o0;
-      d.z[c] = c_fd.lay3[DZ][0] * __ldg(w) + c_fd.lay3[DZ][1] * __ldg(w + S) + c_fd.lay3[DZ][2] * __ldg(w + 2 * S);
-    }
-  }
-
-  float h[9];
-  momentum(d, m, slw, h);
-  hooke<MED>(d, m, md, h);
-
-  const int kmin = P.nk2 - (FZ + 4);
-  if (k >= kmin) {
-    const int n_free = P.nk2 - k - FZ;
-    const float jac = s_met[0][cy0][cx0];
-    const float slwjac = slw / jac;
-    const int T1[3] = {TXX, TXY, TXZ}, T2[3] = {TXY, TYY, TYZ}, T3[3] = {TXZ, TYZ, TZZ};
-    const float *Ts[3] = {P.TxSrc, P.TySrc, P.TzSrc};
-    float Dxf[3], Dyf[3], fz[3][5];
-#pragma unroll
-    for (int n = 0; n < 5; n++) {
-      {
-        const int xx = cx0 + FX + n;
-        const float jn = s_met[0][cy0][xx], ex = s_met[1][cy0][xx], ey = s_met[2][cy0][xx], ez = s_met[3][cy0][xx];
-#pragma unroll
-        for (int v = 0; v < 3; v++) {
-          const float f = jn * (ex * s_cur[T1[v]][cy0][xx] + ey * s_cur[T2[v]][cy0][xx] + ez * s_cur[T3[v]][cy0][xx]);
-          if (n == 0) Dxf[v] = cx[0] * f; else Dxf[v] += cx[n] * f;
-        }
-      }
-      {
-        const int yy = cy0 + FY + n;
-        const float jn = s_met[0][yy][cx0], ex = s_met[4][yy][cx0], ey = s_met[5][yy][cx0], ez = s_met[6][yy][cx0];
-#pragma unroll
-        for (int v = 0; v < 3; v++) {
-          const float f = jn * (ex * s_cur[T1[v]][yy][cx0] + ey * s_cur[T2[v]][yy][cx0] + ez * s_cur[T3[v]][yy][cx0]);
-          if (n == 0) Dyf[v] = cy[0] * f; else Dyf[v] += cy[n] * f;
-        }
-      }
-      if (n < n_free) {
-        const size_t pp = p + (long)(FZ + n) * (long)S;
-        const float jn = __ldg(P.metric[M_JAC] + pp), ex = __ldg(P.metric[M_ZTX] + pp), ey = __ldg(P.metric[M_ZTY] + pp),
-                    ez = __ldg(P.metric[M_ZTZ] + pp);
-#pragma unroll
-        for (int v = 0; v < 3; v++)
-          fz[v][n] = jn * (ex * __ldg(P.cur + T1[v] * V + pp) + ey * __ldg(P.cur + T2[v] * V + pp) + ez * __ldg(P.cur + T3[v] * V + pp));
-      }
-    }
-#pragma unroll
-    for (int v = 0; v < 3; v++) {
-      const float ts = Ts[v] ? __ldg(Ts[v] + p2) : 0.0f;
-#pragma unroll
-      for (int n = 0; n < 5; n++) {
-        if (n == n_free) fz[v][n] = ts;
-        else if (n > n_free) {
-          const int im = 2 * n_free - n;
-          float below;
-          if (im >= 0) below = fz[v][im < 0 ? 0 : im];
-          else if (P.timg_mode == 0) below = 0.0f;
-          else {
-            const size_t pp = p + (long)(FZ + n - 2 * (n - n_free)) * (long)S;
-            const float jn = __ldg(P.metric[M_JAC] + pp), ex = __ldg(P.metric[M_ZTX] + pp), ey = __ldg(P.metric[M_ZTY] + pp),
-                        ez = __ldg(P.metric[M_ZTZ] + pp);
-            below = jn * (ex * __ldg(P.cur + T1[v] * V + pp) + ey * __ldg(P.cur + T2[v] * V + pp) + ez * __ldg(P.cur + T3[v] * V + pp));
-          }
-          fz[v][n] = 2.0f * ts - below;
-        }
-      }
-      float Dz = cz[0] * fz[v][0]; Dz += cz[1] * fz[v][1]; Dz += cz[2] * fz[v][2]; Dz += cz[3] * fz[v][3]; Dz += cz[4] * fz[v][4];
-      h[v] = (Dxf[v] + Dyf[v] + Dz) * slwjac;
-    }
-  }
-
-  pml_all<KIND, 0, MED>(P, i, j, k, d, m, md, h);
-  pml_all<KIND, 1, MED>(P, i, j, k, d, m, md, h);
-  if constexpr (MED == MED_VIS) atten_update<KIND>(P, p, md.lam, md.mu, h);
-  const float qatt = (KIND == KIND_LAST && P.qatt) ? __ldg(P.qatt + p) : 1.0f;
-#pragma unroll
-  for (int c = 0; c < 9; c++) rk_wave<KIND>(P.tmp, P.end, c * V + p, cur[c], pv[c], ev[c], h[c], P.a, P.b, P.c, qatt);
+  const int k = P.kbeg + (blockIdx.z >> 1);
+  if (blockIdx.z & 1) top_half<DX, DY, DZ, KIND, MED, 0>(P, k);
+  else top_half<DX, DY, DZ, KIND, MED, 1>(P, k);   // the velocity half of a row (traction image: ~2x the loads) starts first
 }
-#endif   // CGFD_TOP_TILED
 
 // =============================================================================================
 // interior rows of the tile rectangle [bx0,bx1) x [by0,by1) (tiles of TX x TY points counted from (ni1,nj1))
@@ -700,7 +533,7 @@ static void launch_main_t(const StageArgs &P0, const TmaMaps *maps, int zchunk, 
   (*nlaunch)++;
 }
 
-// the free-surface rows (whole x-y range)
+// the free-surface rows (whole x-y range): blockIdx.z = row * 2 + half
 template <int DX, int DY, int DZ, int KIND, int MED>
 static void launch_top_t(const StageArgs &P0, cudaStream_t st, int *nlaunch)
 {
@@ -709,13 +542,8 @@ static void launch_top_t(const StageArgs &P0, cudaStream_t st, int *nlaunch)
   const int ni = P.ni2 - P.ni1 + 1, nj = P.nj2 - P.nj1 + 1;
   const int ktop = P.nk2 - 3;
   P.kbeg = (ktop < P.nk1) ? P.nk1 : ktop; P.kend = P.nk2;
-#if CGFD_TOP_TILED
-  dim3 block(TT_X, TT_Y), grid((ni + TT_X - 1) / TT_X, (nj + TT_Y - 1) / TT_Y, P.kend - P.kbeg + 1);
-  k_top_tiled<DX, DY, DZ, KIND, MED><<<grid, block, 0, st>>>(P);
-#else
-  dim3 block(32, 4), grid((ni + 31) / 32, (nj + 3) / 4, P.kend - P.kbeg + 1);
+  dim3 block(32, 4), grid((ni + 31) / 32, (nj + 3) / 4, (P.kend - P.kbeg + 1) * 2);
   k_top<DX, DY, DZ, KIND, MED><<<grid, block, 0, st>>>(P);
-#endif
   (*nlaunch)++;
 }
 

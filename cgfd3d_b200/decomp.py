@@ -37,6 +37,25 @@ def split(n: int, parts: int, which: int):
     return start, cnt
 
 
+def ref_split(n: int, parts: int, which: int, nlay1: int = 0, nlay2: int = 0):
+    """(start, count) of block `which` along one axis exactly as gd_indx_set deals them out (forward/gd_t.c:2775-2849): the
+    absorbing layers of the two physical faces count twice as load (n + nlay1 + nlay2 points are dealt evenly, the remainder to
+    the first blocks), and the blocks that own a physical face give their layers back."""
+    n_et = n + nlay1 + nlay2
+    avg, left = divmod(n_et, parts)
+    cnt = avg
+    if which == 0:
+        cnt -= nlay1
+    if which == parts - 1:
+        cnt -= nlay2
+    if which < left:
+        cnt += 1
+    start = 0 if which == 0 else which * avg - nlay1
+    if left:
+        start += which if which < left else left
+    return start, cnt
+
+
 def local_block(rank, px, py, gni, gnj):
     ix, iy = rank_coords(rank, px, py)
     gi0, ni = split(gni, px, ix)

@@ -55,6 +55,7 @@ def make_par(
     slices: dict | None = None,
     export: bool = False,
     check_stability: int = 1,
+    ddsource: dict | None = None,
 ) -> dict:
     """Build the par dict. Paths are relative to workdir/cwd."""
     par = {
@@ -105,6 +106,11 @@ def make_par(
         par["snapshot"] = snapshots
     if slices:
         par["slice"] = slices
+    if ddsource:
+        # distributed (finite-fault) sources: nc file of write_ddsource(), read block-wise by src_dd_read2local / src_dd_accit_loadstf
+        par["in_ddsource_file"] = ddsource.get("file", "case_dd.nc")
+        par["ddsource_add_at_point"] = 1
+        par["ddsource_nt_per_read"] = int(ddsource.get("nt_per_read", 100))
     par["check_nan_every_nummber_of_steps"] = 0
     par["output_all"] = 0
     return par
@@ -259,6 +265,51 @@ def write_cgnc(path: str, dims: dict, variables: dict, atts: dict | None = None)
             b = an.encode()
             av = np.asarray(av, dtype="<i4").ravel()
             f.write(struct.pack("<i", len(b)) + b + struct.pack("<i", av.size) + av.tobytes())
+
+
+def write_multirank_hill_case(workdir: str, size, px: int, py: int, nt: int, dt: float, hill=(1000.0, 2000.0), pml_layers: int = 10,
+                              src=None, lines=None, snapshots=None, medium_type: str = "elastic_iso", visco: dict | None = None,
+                              pml_sides=("x_left", "x_right", "y_front", "y_back", "z_bottom"), ablexp_sides=()) -> str:
+    """A px x py-rank run of the reference program on a Gaussian-hill grid (BASELINE.json configs[1] / [2] physics): the grid goes
+    in through gd_curv_coord_import, one coord_px?_py?.nc per rank holding that rank's block incl. ghosts, blocks dealt out by
+    gd_indx_set's rule (cgfd3d_b200.decomp.ref_split). Run it with CGFD_SHIM_NPROCS = px * py (oracle/shims/mpi_shim.c)."""
+    from cgfd3d_b200 import decomp, hostsetup as hs
+    ni, nj, nk = size
+    par = make_par(workdir, ni, nj, nk, nt, dt, pml_layers=pml_layers, grid={"import": "IN"}, lines=lines, snapshots=snapshots,
+                   medium_type=medium_type, visco=visco, pml_sides=pml_sides, ablexp_sides=ablexp_sides)
+    par["number_of_mpiprocs_x"], par["number_of_mpiprocs_y"] = px, py
+    os.makedirs(os.path.join(workdir, "IN"), exist_ok=True)
+    sides = set(pml_sides) | set(ablexp_sides)
+    lx = (pml_layers if "x_left" in sides else 0, pml_layers if "x_right" in sides else 0)
+    ly = (pml_layers if "y_front" in sides else 0, pml_layers if "y_back" in sides else 0)
+    for ix in range(px):
+        gi0, lni = decomp.ref_split(ni, px, ix, *lx)
+        for iy in range(py):
+            gj0, lnj = decomp.ref_split(nj, py, iy, *ly)
+            x, y, z = hs.hill_coords(lni, lnj, nk, height=hill[0], sigma=hill[1], gi0=gi0, gj0=gj0, gni=ni, gnj=nj)
+            nz_, ny_, nx_ = x.shape
+            write_cgnc(os.path.join(workdir, "IN", "coord_px%d_py%d.nc" % (ix, iy)), {"k": nz_, "j": ny_, "i": nx_},
+                       {"x": (("k", "j", "i"), x), "y": (("k", "j", "i"), y), "z": (("k", "j", "i"), z)})
+    write_case(workdir, par, src or moment_src(ni // 2, nj // 2, 20), [("r1", 0, 1, ni // 2 + 10, nj // 2 + 5, 0)])
+    return os.path.join(workdir, "case.json")
+
+
+def write_ddsource(path: str, t, xyz, force=None, moment_rate=None) -> None:
+    """The distributed-source input of src_dd_read2local (forward/src_t.c:1181-1927): dims time / number, global attributes
+    location_is_axis = 0 (grid index) and z_is_depth = 1, vars time(time), x / y / z(number) and Fx Fy Fz (number, time) and / or
+    Mxx_rate Myy_rate Mzz_rate Myz_rate Mxz_rate Mxy_rate (number, time).
+    t [nt]; xyz [n][3] = (i, j, depth below the surface) in grid indices; force [n][3][nt]; moment_rate [n][6][nt] (xx yy zz yz xz xy)."""
+    xyz = np.asarray(xyz, np.float32)
+    n, nt = xyz.shape[0], len(t)
+    var = {"time": (("time",), np.asarray(t, np.float32)),
+           "x": (("number",), xyz[:, 0].copy()), "y": (("number",), xyz[:, 1].copy()), "z": (("number",), xyz[:, 2].copy())}
+    if force is not None:
+        for c, name in enumerate(("Fx", "Fy", "Fz")):
+            var[name] = (("number", "time"), np.ascontiguousarray(force[:, c, :], np.float32))
+    if moment_rate is not None:
+        for c, name in enumerate(("Mxx_rate", "Myy_rate", "Mzz_rate", "Myz_rate", "Mxz_rate", "Mxy_rate")):
+            var[name] = (("number", "time"), np.ascontiguousarray(moment_rate[:, c, :], np.float32))
+    write_cgnc(path, {"time": nt, "number": n}, var, {"location_is_axis": [0], "z_is_depth": [1]})
 
 
 def rel_l2(a: np.ndarray, b: np.ndarray) -> float:

@@ -31,14 +31,18 @@ def _need():
         pytest.fail("no CUDA device")
 
 
-def _run_case(binary, par, src, stations):
+def _run_case(binary, par, src, stations, coords=None, env=None, prepare=None):
+    """run `binary` on the case files in a scratch directory; returns (sac dict, snapshot nc, PG nc, stdout, output dir)"""
     wd = tempfile.mkdtemp(prefix="cgfd_dropin_")
-    H.write_case(wd, par, src, stations)
-    wall, out = H.run(binary, wd, timeout=3000)
-    sac = H.read_sac_dir(os.path.join(wd, "OUT"))
-    snap = H.read_cgnc(os.path.join(wd, "OUT", "surf_px0_py0.nc"))
-    pg = H.read_cgnc(os.path.join(wd, "OUT", "PG_V_A_D_px0_py0.nc"))
-    return sac, snap, pg, out
+    H.write_case(wd, par, src, stations, coords)
+    if prepare:
+        prepare(wd)
+    wall, out = H.run(binary, wd, timeout=3000, env=env)
+    outdir = os.path.join(wd, "OUT")
+    sac = H.read_sac_dir(outdir)
+    snap = H.read_cgnc(os.path.join(outdir, "surf_px0_py0.nc"))
+    pg = H.read_cgnc(os.path.join(outdir, "PG_V_A_D_px0_py0.nc"))
+    return sac, snap, pg, out, outdir
 
 
 def _joint(got, ref):
@@ -88,17 +92,46 @@ def _compare(sac, snap, gold):
     assert not bad, bad
 
 
-@pytest.mark.parametrize("name", ["small", "config1"])
+def _compare_extras(got, gold):
+    """station seismograms (io_recv_keep with its 8-corner interpolation; 9 wavefield + 6 strain components written by
+    io_recv_output_sac / io_recv_output_sac_el_iso_strain) and slice frames (io_slice_nc_put), where the fixture has them:
+    joint relative L2 <= 1e-4 per group of components that belong together"""
+    bad = []
+    groups = [("sta_V", ["sta_Vx", "sta_Vy", "sta_Vz"]), ("sta_T", ["sta_Txx", "sta_Tyy", "sta_Tzz", "sta_Tyz", "sta_Txz", "sta_Txy"]),
+              ("sta_E", ["sta_Exx", "sta_Eyy", "sta_Ezz", "sta_Eyz", "sta_Exz", "sta_Exy"])]
+    for ax in "xyz":
+        names = sorted(k for k in gold if k.startswith("slice%s_" % ax))
+        groups += [(k, [k]) for k in names]
+    n = 0
+    for label, names in groups:
+        if names[0] not in gold:
+            continue
+        num, den = _joint([got[k] for k in names], [gold[k] for k in names])
+        assert den > 0, label
+        n += 1
+        if not num <= TOL * den:
+            bad.append((label, num / den))
+    assert not bad, bad
+    return n
+
+
+@pytest.mark.parametrize("name", ["small", "config1", "hill100", "hill200"])
 def test_dropin_matches_golden(name):
+    """small / config1: Cartesian grid (BASELINE.json configs[0] at 1000 steps). hill100 / hill200: the CURVILINEAR route of
+    configs[1] -- a Gaussian-hill grid imported through gd_curv_coord_import, metrics by the reference's own gd_curv_metric_cal --
+    at 100x100x60 x 1000 steps and 200x200x100 x 100 steps, with a station at a fractional grid position and x / y / z slices."""
     _need()
     path = os.path.join(os.path.dirname(__file__), "golden", "ref_%s.npz" % name)
     if not os.path.isfile(path):
         pytest.fail("golden fixture %s missing (tests/golden/make_golden.py %s)" % (path, name))
     gold = dict(np.load(path))
-    par, src, stations = make_golden.case_files(name, None)
-    sac, snap, pg, out = _run_case(BIN, par, src, stations)
+    par, src, stations, coords = make_golden.case_files(name, None)
+    sac, snap, pg, out, outdir = _run_case(BIN, par, src, stations, coords)
     assert "GPU time loop" in out
     _compare(sac, snap, gold)
+    if name.startswith("hill"):
+        got = make_golden.collect(name, outdir)
+        assert _compare_extras(got, gold) >= (3 if name == "hill100" else 6)
 
 
 def test_dropin_matches_live_reference_gauss_source():
@@ -112,12 +145,70 @@ def test_dropin_matches_live_reference_gauss_source():
                                  "save_velocity": 1, "save_stress": 0, "save_strain": 0}])
     src = H.moment_src(20, 18, 9, m=(1e16, 0.5e16, 2e16, 0.2e16, -0.1e16, 0.3e16))
     stations = [("r1", 0, 1, 25, 20, 0)]
-    sac_r, snap_r, pg_r, _ = _run_case(H.ref_binary("ref_main_zero"), par, src, stations)
-    sac_g, snap_g, pg_g, _ = _run_case(BIN, par, src, stations)
+    sac_r, snap_r, pg_r, _, _ = _run_case(H.ref_binary("ref_main_zero"), par, src, stations)
+    sac_g, snap_g, pg_g, _, _ = _run_case(BIN, par, src, stations)
     gold = {k.replace(".", "_"): v for k, v in sac_r.items() if ".L1." in k}
     for v in ("Vx", "Vy", "Vz"):
         gold["snap_" + v] = snap_r["vars"][v]
     _compare(sac_g, snap_g, gold)
     # peak-ground-motion maps (PG_calcu + PG_slice_output)
+    for v in ("PGV", "PGVz", "PGA", "PGD"):
+        assert util.rel_l2(pg_g["vars"][v], pg_r["vars"][v]) <= 1e-4, v
+
+
+def _dd_file(wd, ni, nj, nk, nt, dt):
+    """a small finite fault: 7 points on a dipping line, moment-rate and force time functions with different onsets"""
+    t = np.arange(nt + 1, dtype=np.float64) * dt
+    n = 7
+    xyz = np.array([[14 + 2 * q, 12 + q, 10 + q] for q in range(n)], np.float32)
+    mr = np.zeros((n, 6, nt + 1), np.float32)
+    fo = np.zeros((n, 3, nt + 1), np.float32)
+    for q in range(n):
+        g = np.exp(-((t - 0.25 - 0.04 * q) / 0.08) ** 2)
+        for c, a in enumerate((1.0, 0.6, 1.3, 0.2, -0.4, 0.3)):
+            mr[q, c] = 1e15 * a * g
+        for c, a in enumerate((0.5, -1.0, 0.8)):
+            fo[q, c] = 1e11 * a * g
+    H.write_ddsource(os.path.join(wd, "case_dd.nc"), t, xyz, force=fo, moment_rate=mr)
+
+
+LIVE_CASES = {
+    # the other three constitutive laws through the reference's own media set-up ("input_way": "code", forward/md_t.c:501-595, 929-946)
+    "vti": dict(par=dict(medium_type="elastic_vti"), dt=0.012),
+    "aniso": dict(par=dict(medium_type="elastic_aniso"), dt=0.012),
+    "visco": dict(par=dict(medium_type="viscoelastic_iso",
+                           visco={"type": "gmb", "number_of_maxwell": 3, "max_freq": 10.0, "min_freq": 0.1, "refer_freq": 1.0}), dt=0.012),
+    # the example script's default boundary: exponential sponge on five faces (example/cgfd3d.example.sh:154-184)
+    "ablexp": dict(par=dict(pml_sides=(), ablexp_sides=("x_left", "x_right", "y_front", "y_back", "z_bottom")), dt=0.02),
+    # strict surface force: a point force on the free surface (source_surface_force_strict defaults to 1, forward/par_t.c:820-822)
+    "surface_force": dict(par=dict(), dt=0.02, src=lambda: H.force_src(22, 17, 0, fvec=(1e12, -2e12, 3e12))),
+    # finite-fault (dd) sources read block-wise from file: 3 blocks of 50 steps, the last one short
+    "ddsource": dict(par=dict(ddsource={"nt_per_read": 50}), dt=0.02, prepare=_dd_file),
+}
+
+
+@pytest.mark.parametrize("case", sorted(LIVE_CASES))
+def test_dropin_matches_live_reference(case):
+    """The same input files through the reference program (oracle/_ref/ref_main_zero) and through the drop-in binary, for the paths
+    the golden cases do not take: VTI / general anisotropic / visco-elastic media, the sponge, a strict surface force, dd sources."""
+    _need()
+    C = LIVE_CASES[case]
+    ni, nj, nk, nt = 40, 36, 30, 120
+    dt = C["dt"]
+    par = H.make_par(None, ni, nj, nk, nt, dt, pml_layers=6, src_spatial="point",
+                     lines=[{"name": "L1", "grid_index_start": [6, 8, nk - 1], "grid_index_incre": [6, 5, 0], "grid_index_count": 5}],
+                     snapshots=[{"name": "surf", "grid_index_start": [0, 0, nk - 1], "grid_index_count": [ni // 2, nj // 2, 1],
+                                 "grid_index_incre": [2, 2, 1], "time_index_start": 0, "time_index_incre": 10,
+                                 "save_velocity": 1, "save_stress": 0, "save_strain": 0}], **C["par"])
+    src = C["src"]() if "src" in C else H.moment_src(20, 18, 9, m=(1e16, 0.5e16, 2e16, 0.2e16, -0.1e16, 0.3e16))
+    stations = [("r1", 0, 1, 25, 20, 0)]
+    prep = (lambda wd: C["prepare"](wd, ni, nj, nk, nt, dt)) if "prepare" in C else None
+    sac_r, snap_r, pg_r, _, _ = _run_case(H.ref_binary("ref_main_zero"), par, src, stations, prepare=prep)
+    sac_g, snap_g, pg_g, out, _ = _run_case(BIN, par, src, stations, prepare=prep)
+    assert "GPU time loop" in out
+    gold = {k.replace(".", "_"): v for k, v in sac_r.items() if ".L1." in k}
+    for v in ("Vx", "Vy", "Vz"):
+        gold["snap_" + v] = snap_r["vars"][v]
+    _compare(sac_g, snap_g, gold)
     for v in ("PGV", "PGVz", "PGA", "PGD"):
         assert util.rel_l2(pg_g["vars"][v], pg_r["vars"][v]) <= 1e-4, v
