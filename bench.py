@@ -126,39 +126,41 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(self.rows), "how": getattr(self, "how", None)}
 
 
-def build_rank_problem(size, rank, nranks, device=None, medium="iso"):
-    """One rank's block of the global hill problem. device=None: numpy on the host (hostsetup); device='cuda:N': the same
-    formulas as torch expressions on that GPU (devsetup) -- used for the 800x800x400-per-GPU runs, where the numpy route
-    needs ~45 GB of host memory and minutes per rank."""
-    from cgfd3d_b200 import hostsetup as hs
-    ni, nj, nk = size
+def build_rank_problem(size, rank, nranks, device=None, medium="iso", global_size=None):
+    """One rank's block of the global hill problem. size = per-rank block (weak scaling: the global domain is px x py blocks), or
+    global_size = the whole domain, dealt out evenly over the process grid (BASELINE.json configs[3], [4]).
+    device=None: numpy on the host (hostsetup); device='cuda:N': the same formulas as torch expressions on that GPU (devsetup) --
+    used for the 800x800x400-per-GPU runs, where the numpy route needs ~45 GB of host memory and minutes per rank."""
+    from cgfd3d_b200 import decomp, hostsetup as hs
     px, py = proc_grid(nranks)
     ix, iy = rank // py, rank % py   # row-major, y fastest (MPI_Cart_create, forward/mympi_t.c:32-40)
-    def rk(a, b):
-        return a * py + b if (0 <= a < px and 0 <= b < py) else -1
-    neigh = (rk(ix - 1, iy), rk(ix + 1, iy), rk(ix, iy - 1), rk(ix, iy + 1))
-    gni, gnj = ni * px, nj * py
+    neigh = decomp.neighbours(rank, px, py)
+    if global_size is None:
+        ni, nj, nk = size
+        gni, gnj = ni * px, nj * py
+        gi0, gj0 = ix * ni, iy * nj
+    else:
+        gni, gnj, nk = global_size
+        gi0, ni, gj0, nj = decomp.local_block(rank, px, py, gni, gnj)
     # hill spans the global domain (sigma ~ 1/10 of it, height ~ 10 cells)
     dh = (100.0, 100.0, 100.0)
     sigma = 0.1 * max(gni, gnj) * dh[0]
+    sub = (gi0, gj0, gni, gnj, neigh)
     # dt below the CFL bound of the stretched grid (estimate_dt on the full array is slow; checked in tests)
     if medium != "iso":
-        # the other constitutive laws (BASELINE.json configs[3], [4] are parity cases, not bench lines): CFS-PML on all six
-        # faces, because their free-surface matrices come from the reference's own host set-up code
-        prob = hs.build_problem(ni, nj, nk, dh=dh, topo="hill", hill=(1000.0, sigma), pml_layers=10, free_top=False,
-                                pml_faces=((0, 0), (0, 1), (1, 0), (1, 1), (2, 0), (2, 1)), dt=0.008,
-                                sub=(ix * ni, iy * nj, gni, gnj, neigh), medium=medium)
+        prob = hs.build_problem(ni, nj, nk, dh=dh, topo="hill", hill=(1000.0, sigma), pml_layers=10, free_top=True, dt=0.008, sub=sub, medium=medium)
+        # free-surface matrices of the other constitutive laws: computed by the library on the device (cgfd_b200_dvh2dvz)
+        from cgfd3d_b200 import solver
+        prob.mats = solver.dvh2dvz(prob)
     elif device is None:
-        prob = hs.build_problem(ni, nj, nk, dh=dh, topo="hill", hill=(1000.0, sigma), pml_layers=10, free_top=True,
-                                dt=0.012, sub=(ix * ni, iy * nj, gni, gnj, neigh))
+        prob = hs.build_problem(ni, nj, nk, dh=dh, topo="hill", hill=(1000.0, sigma), pml_layers=10, free_top=True, dt=0.012, sub=sub)
     else:
         from cgfd3d_b200 import devsetup
-        prob = devsetup.build_problem(ni, nj, nk, device=device, dh=dh, hill=(1000.0, sigma), pml_layers=10, free_top=True,
-                                      dt=0.012, sub=(ix * ni, iy * nj, gni, gnj, neigh))
+        prob = devsetup.build_problem(ni, nj, nk, device=device, dh=dh, hill=(1000.0, sigma), pml_layers=10, free_top=True, dt=0.012, sub=sub)
     # one explosive moment source under the hill top, on the rank that owns it
     gsi, gsj = gni // 2, gnj // 2
-    if ix * ni <= gsi < (ix + 1) * ni and iy * nj <= gsj < (iy + 1) * nj:
-        hs.make_source(prob, gsi - ix * ni, gsj - iy * nj, nk - 1 - 20, nt_total=100000, kind="moment",
+    if gi0 <= gsi < gi0 + ni and gj0 <= gsj < gj0 + nj:
+        hs.make_source(prob, gsi - gi0, gsj - gj0, nk - 1 - 20, nt_total=100000, kind="moment",
                        mech=(1e16, 1e16, 1e16, 0, 0, 0), fc=2.0, t0=0.5, stf_len=1.0)
     return prob
 
@@ -166,7 +168,7 @@ def build_rank_problem(size, rank, nranks, device=None, medium="iso"):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from cgfd3d_b200 import solver
+    from cgfd3d_b200 import nrank_check, solver
 
     nranks = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -177,26 +179,6 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if nranks > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    size = args.size or ((400, 400, 200) if nranks == 1 else (800, 800, 400))
-    t0 = time.time()
-    on_device = size[0] * size[1] * size[2] > 64e6 and args.medium == "iso"   # big blocks: set-up arrays built on the GPU (devsetup.py)
-    prob = build_rank_problem(size, rank, nranks, device=("cuda:%d" % local) if on_device else None, medium=args.medium)
-    t_host = time.time() - t0
-    t0 = time.time()
-    S = solver.Solver(prob, device=local)
-    t_upload = time.time() - t0
-    if on_device:   # the library holds its own padded copies
-        prob.metric = prob.media = None
-        torch.cuda.empty_cache()
-    if nranks > 1:
-        uid = [solver.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        S.comm_init(uid[0], rank, nranks)
-    if args.variant:
-        S.set_variant(args.variant)
-    ni, nj, nk = size
-    npts = ni * nj * nk
-    K, W = args.steps, args.warmup
 
     def barrier():
         torch.cuda.synchronize()
@@ -204,55 +186,135 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing -----------------------------------------------------------------
-    # the 8 operator pairs (it % 8) use 8 different kernel instantiations: touch all of them before timing
-    S.run(max(W, 8), it0=0)
-    W = max(W, 8)
-    S.set_profiling(True)
-    barrier()
-    with ClockSampler(local) as clk:
+    def allmax(v):
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        if nranks > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    K, W = args.steps, max(args.warmup, 8)   # the 8 operator pairs (it % 8) are 8 kernel instantiations: touch all before timing
+    px, py = proc_grid(nranks)
+
+    # ---- N ranks reproduce 1 rank: value check on this run's own process grid, before anything is timed --------------------
+    parity = None
+    if nranks > 1 and not args.no_parity:
+        parity = nrank_check.check(rank, nranks, local, px, py, dist, medium=args.medium)
+        ok = [parity["ok"] if rank == 0 else None]
+        dist.broadcast_object_list(ok, src=0)
+        if not ok[0]:
+            if rank == 0:
+                emit({"error": "N-rank run does not reproduce the 1-rank run", "parity_nrank": parity})
+            dist.destroy_process_group()
+            raise SystemExit(1)
+
+    def measure(size, global_size=None, e2e=True, sample_clocks=True):
+        """device-resident (and end-to-end) Gpoint-updates/s of one problem; returns a dict"""
+        t0 = time.time()
+        gs = global_size
+        big = (size[0] * size[1] * size[2] if gs is None else gs[0] * gs[1] * gs[2] / nranks) > 64e6
+        on_device = big and args.medium == "iso"   # big blocks: set-up arrays built on the GPU (devsetup.py)
+        prob = build_rank_problem(size, rank, nranks, device=("cuda:%d" % local) if on_device else None, medium=args.medium, global_size=gs)
+        t_host = time.time() - t0
+        t0 = time.time()
+        S = solver.Solver(prob, device=local)
+        t_upload = time.time() - t0
+        if on_device:   # the library holds its own padded copies
+            prob.metric = prob.media = None
+            torch.cuda.empty_cache()
+        if nranks > 1:
+            uid = [solver.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            S.comm_init(uid[0], rank, nranks)
+        if args.variant:
+            S.set_variant(args.variant)
+        ni, nj, nk = prob.ni, prob.nj, prob.nk
+        npts_all = (size[0] * size[1] * size[2] * nranks) if gs is None else gs[0] * gs[1] * gs[2]
+        S.run(W, it0=0)
+        S.set_profiling(True)
+        barrier()
+        clk = ClockSampler(local) if sample_clocks else None
+        if clk:
+            clk.__enter__()
         tw0 = time.time()
         S.run(K, it0=W)
         barrier()
         tw1 = time.time()
-    ms = S.last_run_ms()
-    main_ms, main_n, launches = S.get_profile()
-    S.set_profiling(False)
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if nranks > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = npts * nranks * K / (ms_max * 1e-3) / 1e9
+        if clk:
+            clk.__exit__()
+        ms_max = allmax(S.last_run_ms())
+        main_ms, main_n, launches = S.get_profile()
+        S.set_profiling(False)
+        R = {"value": npts_all * K / (ms_max * 1e-3) / 1e9, "ms_per_step": ms_max / K, "main_ms": main_ms, "main_n": main_n,
+             "launches": launches, "clocks": clk.summary() if clk else None, "wall": tw1 - tw0, "npts_all": npts_all,
+             "block": (ni, nj, nk), "free_top": prob.free_top, "gz": S.grid_class(), "t_host": t_host, "t_upload": t_upload,
+             "on_device": on_device, "e2e": []}
+        if e2e:
+            # ---- end to end from host buffers: the call sequence of a production run -- initial wavefield from pinned host memory,
+            # Ke steps with the outputs the reference's example writes (receiver traces + a surface Vx/Vy/Vz snapshot EVERY step,
+            # example/cgfd3d.example.sh:323-334) streamed to pinned host buffers while the steps run, final wavefield back to the host.
+            # The state transfer is a one-off: the rate depends on the number of steps it is spread over, so two lengths are reported.
+            rec = [prob.iptr(ni // 2 + 5 * n, nj // 2 + 3 * n, nk - 1) for n in range(-4, 5)]
+            w_host = torch.zeros(S.shape, dtype=torch.float32).pin_memory().numpy()
+            ncmp = S.shape[0]
+            it0 = W + K
+            for Ke in ((K,) if args.short_e2e else (K, 100)):
+                S.set_record_points(rec, Ke)
+                snap = torch.zeros((Ke, 3, 1, nj, ni), dtype=torch.float32).pin_memory().numpy()
+                S.add_snapshot((0, 1, 2), (3, ni, 1, 3, nj, 1, prob.nz - 4, 1, 1), max_frames=Ke, it1=it0, out=snap)
+                barrier()
+                te0 = time.time()
+                S.set_wavefield(w_host)
+                te1 = time.time()
+                S.run(Ke, it0=it0)
+                traces = S.get_record(0, Ke)
+                te2 = time.time()
+                S.get_wavefield(out=w_host)
+                barrier()
+                te3 = time.time()
+                secs = allmax(te3 - te0)
+                R["e2e"].append({"steps": Ke, "value": npts_all * Ke / secs / 1e9, "h2d": w_host.nbytes / Ke,
+                                 "d2h": w_host.nbytes / Ke + len(rec) * ncmp * 4 + snap.nbytes / Ke,
+                                 "ms": {"set_wavefield": round((te1 - te0) * 1e3, 2), "steps_with_outputs": round((te2 - te1) * 1e3, 2),
+                                        "get_wavefield": round((te3 - te2) * 1e3, 2)},
+                                 "finite": bool(np.isfinite(w_host).all()) and bool(np.isfinite(snap).all()) and bool(np.isfinite(traces).all())})
+                it0 += Ke
+                del snap
+        S.close()
+        del S, prob
+        torch.cuda.empty_cache()
+        return R
 
-    # ---- end to end from host buffers -------------------------------------------------------------
-    # the call sequence of a production run: initial wavefield from pinned host memory, K steps with the outputs the
-    # reference's example writes (receiver traces + a surface Vx/Vy/Vz snapshot EVERY step, example/cgfd3d.example.sh
-    # :323-334) streamed to pinned host buffers while the steps run, final wavefield back to the host
-    rec = [prob.iptr(ni // 2 + 5 * n, nj // 2 + 3 * n, nk - 1) for n in range(-4, 5)]
-    S.set_record_points(rec, K + 8)
-    w_host = torch.zeros(S.shape, dtype=torch.float32).pin_memory().numpy()
-    ncmp = S.shape[0]
-    snap = torch.zeros((K, 3, 1, nj, ni), dtype=torch.float32).pin_memory().numpy()
-    S.add_snapshot((0, 1, 2), (3, ni, 1, 3, nj, 1, prob.nz - 4, 1, 1), max_frames=K, it1=W + K, out=snap)
-    h2d = w_host.nbytes / K
-    d2h = w_host.nbytes / K + len(rec) * ncmp * 4 + snap.nbytes / K
-    barrier()
-    te0 = time.time()
-    S.set_wavefield(w_host)
-    te1 = time.time()
-    S.run(K, it0=W + K)
-    traces = S.get_record(0, K)
-    te2 = time.time()
-    S.get_wavefield(out=w_host)
-    barrier()
-    te3 = time.time()
-    te = torch.tensor([te3 - te0], dtype=torch.float64, device="cuda")
-    if nranks > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e = npts * nranks * K / float(te.item()) / 1e9
-    e2e_ms = {"set_wavefield": round((te1 - te0) * 1e3, 2), "steps_with_outputs": round((te2 - te1) * 1e3, 2),
-              "get_wavefield": round((te3 - te2) * 1e3, 2)}
-    finite = bool(np.isfinite(w_host).all()) and bool(np.isfinite(snap).all()) and bool(np.isfinite(traces).all())
+    # ---- the measured workload --------------------------------------------------------------------------------------------
+    gs = args.global_size
+    size = None if gs else (args.size or ((400, 400, 200) if nranks == 1 else (800, 800, 400)))
+    R = measure(size, gs)
+
+    # ---- weak-scaling base: the per-GPU block of the multi-GPU runs on ONE GPU, so that the efficiency of an N-GPU line can be
+    # recomputed from the lines themselves. N = 1: a second problem in this process. N > 1: rank 0 starts a one-GPU bench.py on its
+    # own device once the N-rank problem is released; the other ranks wait at the barrier.
+    weak = None
+    if not args.no_weak_base and args.medium == "iso" and gs is None and args.size is None:
+        if nranks == 1:
+            Rw = measure((800, 800, 400), None, e2e=False, sample_clocks=False)
+            weak = {"size": "800x800x400", "value": round(Rw["value"], 4), "ms_per_step": round(Rw["ms_per_step"], 4),
+                    "what": "BASELINE.json configs[2] block on one GPU (all four x-y faces CFS-PML), same process, %d steps" % K}
+        else:
+            if rank == 0:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                dev = vis.split(",")[local] if vis else str(local)
+                env = {k: v for k, v in os.environ.items()
+                       if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT", "LOCAL_WORLD_SIZE", "GROUP_RANK",
+                                    "ROLE_RANK", "ROLE_WORLD_SIZE", "GROUP_WORLD_SIZE", "TORCHELASTIC_RUN_ID")}
+                env["CUDA_VISIBLE_DEVICES"] = dev
+                pr = subprocess.run([sys.executable, os.path.abspath(__file__), "--gpus", "1", "--steps", str(K), "--warmup", str(W), "--size",
+                                     "800x800x400", "--no-cpu-baseline", "--short-e2e", "--no-weak-base"], capture_output=True, text=True, env=env, timeout=900)
+                try:
+                    j = json.loads(pr.stdout.strip().splitlines()[-1])
+                    weak = {"size": "800x800x400", "value": j["value"], "ms_per_step": j["ms_per_step"],
+                            "what": "the per-GPU block of this run on ONE GPU (all four x-y faces CFS-PML), measured by rank 0 on its own device right after the timed region"}
+                except Exception as e:   # noqa: BLE001
+                    weak = {"error": "weak base run failed: %r %s" % (e, pr.stderr[-300:])}
+            barrier()
 
     out = None
     if rank == 0:
@@ -262,38 +324,57 @@ def run_ours(args):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
+        main_ms, main_n = R["main_ms"], R["main_n"]
         kb = (main_ms / max(main_n, 1)) * 1e-3
-        # algorithmic bytes of one interior-kernel launch = 768/4 B per point-stage x the points it covers
+        # algorithmic bytes of one interior-kernel launch = (bytes per point-step / 4 stages) x the points it covers
         bpps = BYTES_PER_POINT_STEP[args.medium]
-        main_pts = ni * nj * (nk - 4 if prob.free_top else nk)   # the free-surface kernel owns the top 4 rows
+        ni, nj, nk = R["block"]
+        main_pts = ni * nj * (nk - 4 if R["free_top"] else nk)   # the free-surface kernel owns the top 4 rows
         ach = (bpps / 4.0) * main_pts / kb / 1e9 if main_n else None
+        e0 = R["e2e"][0]
+        workload = "%s, Gaussian-hill topography (curvilinear), " % WORKLOAD[args.medium]
+        if gs is None:
+            workload += "%dx%dx%d per GPU%s, " % (tuple(size) + (" (weak scaling)" if nranks > 1 else "",))
+        else:
+            workload += "%dx%dx%d global over %d GPUs (rank 0 block %dx%dx%d), " % (tuple(gs) + (nranks, ni, nj, nk))
+        workload += ("CFS-PML 10 layers x 5 faces, traction-image free surface, 1 moment source" if R["free_top"]
+                     else "CFS-PML 10 layers x 6 faces, 1 moment source")
         out = {
-            "metric": METRIC, "value": round(value, 4), "unit": "Gpoint-updates/s", "n_gpus": nranks, "steps": K, "warmup": W,
-            "ms_per_step": round(ms_max / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": round(R["value"], 4), "unit": "Gpoint-updates/s", "n_gpus": nranks, "steps": K, "warmup": W,
+            "ms_per_step": round(R["ms_per_step"], 4), "higher_is_better": True, "scaling": "weak" if gs is None else "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": ("%s, Gaussian-hill topography (curvilinear), %dx%dx%d per GPU, " % ((WORKLOAD[args.medium],) + tuple(size)))
-                                   + ("CFS-PML 10 layers x 5 faces, traction-image free surface, 1 moment source" if prob.free_top
-                                      else "CFS-PML 10 layers x 6 faces, 1 moment source"),
-                       "proc_grid": "%dx%d" % proc_grid(nranks), "l2": "working set >> 126 MB L2 (no flush needed)",
-                       "variant": args.variant or "default",
-                       "kernels": "vertically-deformed-grid (4 metric arrays identically zero)" if S.grid_class() else "general curvilinear"},
-            "e2e": {"value": round(e2e, 4), "unit": "Gpoint-updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "what": "set_wavefield (H2D) + run(K) with receiver traces and a surface Vx/Vy/Vz snapshot streamed to pinned host "
-                            "memory every step + get_wavefield (D2H)", "ms": e2e_ms},
-            "gpu_launches": int(launches),
-            "clocks": clk.summary(),
+            "config": {"workload": workload, "proc_grid": "%dx%d" % (px, py), "l2": "working set >> 126 MB L2 (no flush needed)",
+                       "variant": args.variant or "default", "medium": args.medium,
+                       "kernels": "vertically-deformed-grid (4 metric arrays identically zero)" if R["gz"] else "general curvilinear"},
+            "e2e": {"value": round(e0["value"], 4), "unit": "Gpoint-updates/s", "h2d_bytes_per_step": int(e0["h2d"]), "d2h_bytes_per_step": int(e0["d2h"]),
+                    "steps": e0["steps"],
+                    "what": "set_wavefield (H2D) + run(steps) with receiver traces and a surface Vx/Vy/Vz snapshot streamed to pinned host "
+                            "memory every step + get_wavefield (D2H); the whole-wavefield transfers are a one-off, so the rate grows with "
+                            "the number of steps they are spread over (e2e_k100 = the same over 100 steps)", "ms": e0["ms"]},
+            "gpu_launches": int(R["launches"]),
+            "clocks": R["clocks"],
             "roofline": {"bound": "hbm", "kernel": "k_main_tma", "achieved": None if ach is None else round(ach, 1), "peak": peak,
-                         "unit": "GB/s", "frac": None if ach is None else round(ach / peak, 4), "traffic": ncu_traffic(size),
+                         "unit": "GB/s", "frac": None if ach is None else round(ach / peak, 4), "traffic": ncu_traffic(R["block"], args.medium),
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                          "launches_timed": int(main_n), "avg_launch_ms": round(main_ms / max(main_n, 1), 4),
                          "algorithmic_bytes_per_launch": int((bpps / 4.0) * main_pts),
-                         "whole_step_frac": round(bpps * npts / (ms_max / K * 1e-3) / 1e9 / peak, 4)},
-            "setup_s": {"arrays": round(t_host, 2), "arrays_built_on": "gpu (torch)" if on_device else "host (numpy)", "upload": round(t_upload, 2)},
-            "wall_s_timed": round(tw1 - tw0, 4), "finite": finite,
+                         "whole_step_frac": round(bpps * (R["npts_all"] / nranks) / (R["ms_per_step"] * 1e-3) / 1e9 / peak, 4)},
+            "setup_s": {"arrays": round(R["t_host"], 2), "arrays_built_on": "gpu (torch)" if R["on_device"] else "host (numpy)", "upload": round(R["t_upload"], 2)},
+            "wall_s_timed": round(R["wall"], 4), "finite": all(e["finite"] for e in R["e2e"]),
         }
+        if len(R["e2e"]) > 1:
+            e1 = R["e2e"][1]
+            out["e2e_k100"] = {"value": round(e1["value"], 4), "steps": e1["steps"], "h2d_bytes_per_step": int(e1["h2d"]),
+                               "d2h_bytes_per_step": int(e1["d2h"]), "ms": e1["ms"]}
+        if nranks > 1:
+            out["per_gpu"] = round(R["value"] / nranks, 4)
+            out["parity_nrank"] = parity
+        if weak is not None:
+            out["weak_base"] = weak
+            if nranks > 1 and "value" in weak:
+                out["efficiency_vs_weak_base"] = round(R["value"] / nranks / weak["value"], 4)
         if nranks == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(os.cpu_count() or 1, steps=args.cpu_steps)
-    S.close()
     if nranks > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -301,12 +382,13 @@ def run_ours(args):
         emit(out)
 
 
-def ncu_traffic(size):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed ncu --set full
-    capture (profiles/traffic.json), valid for the workload it was captured on; None otherwise."""
+def ncu_traffic(size, medium="iso"):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed ncu capture
+    (profiles/traffic.json, one entry per medium), valid for the workload it was captured on; None otherwise."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        return t["bytes_per_launch"] if list(size) == t["size"] else None
+        e = t.get(medium)
+        return e["bytes_per_launch"] if e and list(size) == list(e["size"]) else None
     except Exception:
         return None
 
@@ -418,12 +500,16 @@ def main():
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--size", type=parse_size, default=None)
+    ap.add_argument("--size", type=parse_size, default=None, help="per-GPU block NIxNJxNK (weak scaling)")
+    ap.add_argument("--global-size", type=parse_size, default=None, help="whole domain NIxNJxNK dealt out over the GPUs (BASELINE.json configs[3], [4])")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the N-rank-vs-1-rank value check before timing")
+    ap.add_argument("--no-weak-base", action="store_true", help="skip the one-GPU measurement of the weak-scaling block")
+    ap.add_argument("--short-e2e", action="store_true", help="only the K-step end-to-end leg (not the 100-step one)")
     ap.add_argument("--variant", default="")
     ap.add_argument("--medium", default="iso", choices=["iso", "vti", "aniso", "visco"],
                     help="constitutive law (default iso = the BASELINE.json metric; the others are side measurements)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--one-core", action="store_true", help="--impl reference: also time one core on a 200x200x100 cut")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl != "reference":

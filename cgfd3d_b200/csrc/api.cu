@@ -126,6 +126,8 @@ struct cgfd_b200_ctx {
   float *metric_blk = nullptr, *media_blk = nullptr;
   float *qatt = nullptr;            // Graves' attenuation factor per point (padded layout, unshifted base) or nullptr
   CUtensorMap map_halo[4], map_cen[4], map_out[4], map_met, map_met5, map_med;
+  CUtensorMap map_jcen[4], map_jout[4], map_y;   // visco-elastic medium: memory variables of each level, Ylam / Ymu
+  int vis_staged = 0;               // memory variables staged by TMA in the interior kernel (nmaxwell <= VIS_MAX_STAGED)
   int gz = 0;                       // xi_y = xi_z = eta_x = eta_z == 0 at every physical point: GZ kernels (cgfd_dev.cuh)
   bool have_maps = false;
   int zchunk = 0;                   // explicit rows per z chunk (CGFD_ZCHUNK), 0 = chosen by plan_for()
@@ -578,6 +580,17 @@ extern "C" int cgfd_b200_create(const cgfd_problem_t *p, int device, cgfd_b200_c
     if (!mrc) mrc |= make_map(c, &c->map_met5, c->metric_blk + c->V, 9, TILE_X, TILE_Y, 5);
     const int ntile = (med == MED_ISO || med == MED_VIS) ? 3 : p->nmedia;   // media arrays staged per plane (Med<MED>::NTILE)
     if (!mrc) mrc |= make_map(c, &c->map_med, c->media_blk, p->nmedia, TILE_X, TILE_Y, ntile);
+    if (med == MED_VIS && c->nmaxwell <= VIS_MAX_STAGED && !mrc) {
+      // staged attenuation: tensors that start at the first memory variable of a level / at Ylam[0]
+      const int nj = 6 * c->nmaxwell;
+      for (int l = 0; l < 4 && !mrc; l++) {
+        mrc |= make_map(c, &c->map_jcen[l], c->lev[l] + 9 * c->V, nj, TILE_X, TILE_Y, nj);
+        mrc |= make_map(c, &c->map_jout[l], c->lev[l] + 9 * c->V, nj, TILE_X, TILE_Y, nj, true);
+      }
+      if (!mrc) mrc |= make_map(c, &c->map_y, c->media_blk + 3 * c->V, 2 * c->nmaxwell, TILE_X, TILE_Y, 2 * c->nmaxwell);
+      c->vis_staged = 1;
+      if (const char *e = getenv("CGFD_VIS_STAGED")) c->vis_staged = atoi(e) != 0;
+    }
     c->have_maps = (mrc == 0);
     if (mrc) { cgfd_b200_destroy(c); return 1; }
   }
@@ -753,7 +766,7 @@ static void fill_args(cgfd_b200_ctx *c, StageArgs &P)
   P.siz_line = c->PX; P.siz_slice = c->slice; P.siz_vol = c->V;
   for (int m = 0; m < NMETRIC; m++) P.metric[m] = c->metric[m];
   for (int m = 0; m < c->nmedia; m++) P.media[m] = c->media[m];
-  P.nmaxwell = c->nmaxwell;
+  P.nmaxwell = c->nmaxwell; P.vis_staged = c->vis_staged;
   P.qatt = c->qatt ? c->qatt + c->shift : nullptr;
   for (int n = 0; n < MAX_MAXWELL; n++) P.wl[n] = c->wl[n];
   P.free_top = c->free_top; P.timg_mode = c->timg_mode; P.l2mode = c->l2mode;
@@ -901,6 +914,10 @@ static int run_stage(cgfd_b200_ctx *c, StageArgs &P, int it, int ipair, int ista
     maps.cur = c->map_halo[icur]; maps.pre = c->map_cen[ipre]; maps.end = c->map_cen[iend];
     maps.met = c->map_met; maps.met5 = c->map_met5; maps.med = c->map_med;
     maps.out_tmp = c->map_out[itmp]; maps.out_end = c->map_out[iend];
+    if (c->vis_staged) {
+      maps.jcur = c->map_jcen[icur]; maps.jpre = c->map_jcen[ipre]; maps.jend = c->map_jcen[iend]; maps.ymed = c->map_y;
+      maps.jout_tmp = c->map_jout[itmp]; maps.jout_end = c->map_jout[iend];
+    }
   }
   const TmaMaps *mp = c->have_maps ? &maps : nullptr;
   for (int idim = 0; idim < 3; idim++) for (int is = 0; is < 2; is++) {
@@ -1127,6 +1144,10 @@ extern "C" int cgfd_b200_onestage(cgfd_b200_ctx *c, int it, int ipair, int istag
     maps.cur = c->map_halo[icur]; maps.pre = c->map_cen[iz2]; maps.end = c->map_cen[izero];
     maps.met = c->map_met; maps.met5 = c->map_met5; maps.med = c->map_med;
     maps.out_tmp = c->map_out[iout]; maps.out_end = c->map_out[izero];
+    if (c->vis_staged) {
+      maps.jcur = c->map_jcen[icur]; maps.jpre = c->map_jcen[iz2]; maps.jend = c->map_jcen[izero]; maps.ymed = c->map_y;
+      maps.jout_tmp = c->map_jout[iout]; maps.jout_end = c->map_jout[izero];
+    }
   }
   // aux: cur = copy of level n, pre = zeros, tmp = out, end = scratch
   // run_stage sets aux pointers from level indices; patch aux_pre to the zero buffer afterwards is not
@@ -1247,6 +1268,54 @@ extern "C" int cgfd_b200_metric_from_coords(int device, const cgfd_grid_t *g, co
   if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) return done(fail("metric_from_coords: kernel failed"));
   for (int m = 0; m < 10; m++)
     if (!metric_out[m] || cudaMemcpy(metric_out[m], out.a[m], nb, cudaMemcpyDefault) != cudaSuccess) return done(fail("metric_from_coords: copy of the result failed"));
+  return done(0);
+}
+
+extern "C" int cgfd_b200_dvh2dvz(int device, const cgfd_problem_t *p, const float *x, const float *y, const float *z, int fd_len,
+                                 const int *fd_indx, const float *fd_coef, float *matVx2Vz, float *matVy2Vz, float *matF2Vz, float *matD)
+{
+  if (!p || !matVx2Vz || !matVy2Vz) return fail("dvh2dvz: bad arguments");
+  const int med = med_of(p->medium_type);
+  if (med < 0) return fail("dvh2dvz: unknown medium type");
+  if (med == MED_VIS && (!x || !y || !z || !fd_indx || !fd_coef || !matD || fd_len <= 0 || fd_len > 16))
+    return fail("dvh2dvz: the visco-elastic medium needs the coordinates, the centred operator and matD");
+  const cgfd_grid_t &g = p->grid;
+  CK(cudaSetDevice(device));
+  const size_t S = (size_t)g.nx * g.ny, off = (size_t)g.nk2 * S;   // the k = nk2 plane of every array
+  const int nmed = (med == MED_ISO || med == MED_VIS) ? 2 : (med == MED_VTI) ? 5 : 21;
+  const int nin = 9 + nmed + (med == MED_VIS ? 3 : 0);
+  float *buf = nullptr; int *dindx = nullptr; float *dcoef = nullptr;
+  CK(cudaMalloc((void **)&buf, (size_t)(nin + 4 * 9) * S * sizeof(float)));
+  auto done = [&](int rc) { cudaFree(buf); if (dindx) cudaFree(dindx); if (dcoef) cudaFree(dcoef); return rc; };
+  DvhArgs a;
+  memset(&a, 0, sizeof(a));
+  a.med = med; a.nx = g.nx; a.ni1 = g.ni1; a.ni2 = g.ni2; a.nj1 = g.nj1; a.nj2 = g.nj2;
+  int slot = 0;
+  auto plane = [&](const float *src) -> const float * {
+    float *d = buf + (size_t)slot++ * S;
+    if (!src || cudaMemcpy(d, src + off, S * sizeof(float), cudaMemcpyDefault) != cudaSuccess) return nullptr;
+    return d;
+  };
+  for (int m = 1; m < 10; m++) if (!(a.metric[m] = plane(p->metric[m]))) return done(fail("dvh2dvz: copy of a metric plane failed"));
+  for (int m = 0; m < nmed; m++) if (!(a.media[m] = plane(p->media[m]))) return done(fail("dvh2dvz: copy of a media plane failed"));
+  if (med == MED_VIS) {
+    if (!(a.x = plane(x)) || !(a.y = plane(y)) || !(a.z = plane(z))) return done(fail("dvh2dvz: copy of a coordinate plane failed"));
+    if (cudaMalloc((void **)&dindx, fd_len * sizeof(int)) != cudaSuccess || cudaMalloc((void **)&dcoef, fd_len * sizeof(float)) != cudaSuccess)
+      return done(fail("dvh2dvz: out of device memory"));
+    cudaMemcpy(dindx, fd_indx, fd_len * sizeof(int), cudaMemcpyHostToDevice);
+    cudaMemcpy(dcoef, fd_coef, fd_len * sizeof(float), cudaMemcpyHostToDevice);
+    a.fd_len = fd_len; a.fd_indx = dindx; a.fd_coef = dcoef;
+  }
+  float *out = buf + (size_t)nin * S;
+  cudaMemset(out, 0, 4 * 9 * S * sizeof(float));
+  a.matVx2Vz = out; a.matVy2Vz = out + 9 * S; a.matF2Vz = out + 18 * S; a.matD = out + 27 * S;
+  dim3 blk(128), grd((g.ni2 - g.ni1 + 128) / 128, g.nj2 - g.nj1 + 1);
+  k_dvh2dvz<<<grd, blk>>>(a);
+  if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) return done(fail("dvh2dvz: kernel failed"));
+  float *dst[4] = {matVx2Vz, matVy2Vz, matF2Vz, matD};
+  for (int n = 0; n < 4; n++)
+    if (dst[n] && cudaMemcpy(dst[n], out + (size_t)n * 9 * S, 9 * S * sizeof(float), cudaMemcpyDefault) != cudaSuccess)
+      return done(fail("dvh2dvz: copy of the result failed"));
   return done(0);
 }
 

@@ -187,6 +187,128 @@ __global__ void k_metric_mirror(MetricOut out, int axis, int nx, int ny, int nz,
   a[q] = a[q + off * stride];
 }
 
+// The free-surface conversion matrices of the four constitutive laws (one-shot set-up):
+//   sv_curv_col_el_iso_dvh2dvz   forward/sv_curv_col_el_iso.c:1258-1375    A^-1 B, A^-1 C, A^-1
+//   sv_curv_col_el_vti_dvh2dvz   forward/sv_curv_col_el_vti.c:1085-1205    -(A^-1 B), -(A^-1 C)
+//   sv_curv_col_el_aniso_dvh2dvz forward/sv_curv_col_el_aniso.c:1267-1422  -(A^-1 B), -(A^-1 C)
+//   sv_curv_col_vis_iso_dvh2dvz  forward/sv_curv_col_vis_iso.c:353-507     A^-1 B, A^-1 C and the rotation matD into the local
+//                                                                          frame of the surface (tangent along eta, normal)
+// One thread per surface point; every input is the k = nk2 plane [ny][nx] of its array. Products and sums are rounded one by
+// one in the reference's order (no FMA contraction: gcc does not contract on x86-64), so the matrices come out bit-identical.
+// The VTI expressions of the reference are the general anisotropic ones with the vanishing Cij left out (adding an exact zero
+// changes nothing), so both go through one routine over the 21 Cij.
+__device__ __forceinline__ float mul_(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add_(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub_(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ void invert3x3_rn(float m[3][3])   // fdlib_math_invert3x3, lib/fdlib_math.c:7-35
+{
+  float inv[3][3];
+  inv[0][0] = sub_(mul_(m[1][1], m[2][2]), mul_(m[2][1], m[1][2]));
+  inv[0][1] = sub_(mul_(m[2][1], m[0][2]), mul_(m[0][1], m[2][2]));
+  inv[0][2] = sub_(mul_(m[0][1], m[1][2]), mul_(m[0][2], m[1][1]));
+  inv[1][0] = sub_(mul_(m[1][2], m[2][0]), mul_(m[1][0], m[2][2]));
+  inv[1][1] = sub_(mul_(m[0][0], m[2][2]), mul_(m[2][0], m[0][2]));
+  inv[1][2] = sub_(mul_(m[1][0], m[0][2]), mul_(m[0][0], m[1][2]));
+  inv[2][0] = sub_(mul_(m[1][0], m[2][1]), mul_(m[1][1], m[2][0]));
+  inv[2][1] = sub_(mul_(m[2][0], m[0][1]), mul_(m[0][0], m[2][1]));
+  inv[2][2] = sub_(mul_(m[0][0], m[1][1]), mul_(m[0][1], m[1][0]));
+  float det = add_(add_(mul_(inv[0][0], m[0][0]), mul_(inv[0][1], m[1][0])), mul_(inv[0][2], m[2][0]));
+  det = __fdiv_rn(1.0f, det);
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) m[i][j] = mul_(inv[i][j], det);
+}
+__device__ __forceinline__ void matmul3x3_rn(const float A[3][3], const float B[3][3], float C[3][3])   // lib/fdlib_math.c:37-49
+{
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+    float c = 0.0f;
+    for (int k = 0; k < 3; k++) c = add_(c, mul_(A[i][k], B[k][j]));
+    C[i][j] = c;
+  }
+}
+// isotropic: M = sgn * [ l2m a_i b_i + mu (a_p b_p + a_q b_q) on the diagonal ; lam a_i b_j + mu a_j b_i off it ], a = zeta row
+__device__ __forceinline__ void iso_mat(const float *a, const float *b, float lam, float mu, float l2m, bool neg, float M[3][3])
+{
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+    if (i == j) {
+      const int p = (i + 1) % 3 < (i + 2) % 3 ? (i + 1) % 3 : (i + 2) % 3, q = (i + 1) % 3 < (i + 2) % 3 ? (i + 2) % 3 : (i + 1) % 3;
+      const float t1 = mul_(mul_(neg ? -l2m : l2m, a[i]), b[i]);
+      const float t2 = mul_(mu, add_(mul_(a[p], b[p]), mul_(a[q], b[q])));
+      M[i][j] = neg ? sub_(t1, t2) : add_(t1, t2);
+    } else {
+      const float t1 = mul_(mul_(neg ? -lam : lam, a[i]), b[j]);
+      const float t2 = mul_(mul_(mu, a[j]), b[i]);
+      M[i][j] = neg ? sub_(t1, t2) : add_(t1, t2);
+    }
+  }
+}
+// general anisotropic: M[i][j] = sum_p ( sum_q C[V(i,p)][V(j,q)] in_q ) out_p, V = Voigt index of a tensor index pair
+__device__ __forceinline__ void aniso_mat(const float (&C)[6][6], const float *in, const float *out, float M[3][3])
+{
+  const int V[3][3] = {{0, 5, 4}, {5, 1, 3}, {4, 3, 2}};
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+    float acc = 0.0f;
+    for (int p = 0; p < 3; p++) {
+      const float *c = C[V[i][p]];
+      const float s = add_(add_(mul_(c[V[j][0]], in[0]), mul_(c[V[j][1]], in[1])), mul_(c[V[j][2]], in[2]));
+      const float t = mul_(s, out[p]);
+      acc = (p == 0) ? t : add_(acc, t);
+    }
+    M[i][j] = acc;
+  }
+}
+__global__ void k_dvh2dvz(DvhArgs a)
+{
+  const int i = a.ni1 + blockIdx.x * blockDim.x + threadIdx.x, j = a.nj1 + blockIdx.y;
+  if (i > a.ni2 || j > a.nj2) return;
+  const size_t p = (size_t)j * a.nx + i;
+  const float xi[3] = {a.metric[1][p], a.metric[2][p], a.metric[3][p]}, et[3] = {a.metric[4][p], a.metric[5][p], a.metric[6][p]},
+              zt[3] = {a.metric[7][p], a.metric[8][p], a.metric[9][p]};
+  float A[3][3], B[3][3], Cm[3][3], AB[3][3], AC[3][3];
+  const bool iso = (a.med == 0 || a.med == 3);
+  if (iso) {
+    const float lam = a.media[0][p], mu = a.media[1][p], l2m = add_(lam, mul_(2.0f, mu));
+    iso_mat(zt, zt, lam, mu, l2m, false, A);
+    iso_mat(zt, xi, lam, mu, l2m, true, B);
+    iso_mat(zt, et, lam, mu, l2m, true, Cm);
+  } else {
+    float C[6][6];
+    for (int r = 0; r < 6; r++) for (int c = 0; c < 6; c++) C[r][c] = 0.0f;
+    if (a.med == 1) {   // VTI: c11 c13 c33 c55 c66 (forward/sv_curv_col_el_vti.c:1147-1152), c12 = c11 - 2.0 * c66 in double
+      const float c11 = a.media[0][p], c13 = a.media[1][p], c33 = a.media[2][p], c55 = a.media[3][p], c66 = a.media[4][p];
+      const float c12 = (float)((double)c11 - 2.0 * (double)c66);
+      C[0][0] = c11; C[1][1] = c11; C[2][2] = c33; C[3][3] = c55; C[4][4] = c55; C[5][5] = c66;
+      C[0][1] = C[1][0] = c12; C[0][2] = C[2][0] = c13; C[1][2] = C[2][1] = c13;
+    } else {            // the 21 Cij, upper triangle row by row
+      int n = 0;
+      for (int r = 0; r < 6; r++) for (int c = r; c < 6; c++) { C[r][c] = C[c][r] = a.media[n][p]; n++; }
+    }
+    aniso_mat(C, zt, zt, A);
+    aniso_mat(C, xi, zt, B);
+    aniso_mat(C, et, zt, Cm);
+  }
+  invert3x3_rn(A);
+  matmul3x3_rn(A, B, AB);
+  matmul3x3_rn(A, Cm, AC);
+  for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) {
+    a.matVx2Vz[p * 9 + r * 3 + c] = iso ? AB[r][c] : mul_(-1.0f, AB[r][c]);
+    a.matVy2Vz[p * 9 + r * 3 + c] = iso ? AC[r][c] : mul_(-1.0f, AC[r][c]);
+    if (a.med == 0) a.matF2Vz[p * 9 + r * 3 + c] = A[r][c];
+  }
+  if (a.med == 3) {
+    // rotation into the local frame of the surface: tangent along eta (centred difference of the coordinates), normal = zeta row
+    const float xet = fd_shift(a.x, p, a.nx, a.fd_len, a.fd_indx, a.fd_coef), yet = fd_shift(a.y, p, a.nx, a.fd_len, a.fd_indx, a.fd_coef),
+                zet = fd_shift(a.z, p, a.nx, a.fd_len, a.fd_indx, a.fd_coef);
+    const float e_n = (float)(1.0 / sqrt((double)add_(add_(mul_(xet, xet), mul_(yet, yet)), mul_(zet, zet))));
+    const float e_m = (float)(1.0 / sqrt((double)add_(add_(mul_(zt[0], zt[0]), mul_(zt[1], zt[1])), mul_(zt[2], zt[2]))));
+    const float e_nm = mul_(e_n, e_m);
+    float *D = a.matD + p * 9;
+    D[0] = mul_(sub_(mul_(yet, zt[2]), mul_(zet, zt[1])), e_nm);
+    D[1] = mul_(sub_(mul_(zet, zt[0]), mul_(xet, zt[2])), e_nm);
+    D[2] = mul_(sub_(mul_(xet, zt[1]), mul_(yet, zt[0])), e_nm);
+    D[3] = mul_(xet, e_n); D[4] = mul_(yet, e_n); D[5] = mul_(zet, e_n);
+    D[6] = mul_(zt[0], e_m); D[7] = mul_(zt[1], e_m); D[8] = mul_(zt[2], e_m);
+  }
+}
+
 // rows of nx floats between the unpadded host order and the padded device rows (pitch PX; `pad` is already shifted)
 __global__ void k_repitch(float *pad, float *flat, int nx, int pitch, size_t rows, int to_padded)
 {

@@ -39,6 +39,18 @@ __global__ void k_vis_free(float *w, size_t V, int pitch, int nx, int ny, int ni
 __global__ void k_ablexp(float *w, size_t V, int ncmp, int nx, int ny, int i1, int i2, int j1, int j2, int k1, int k2,
                          const float *Ex, const float *Ey, const float *Ez);
 struct MetricOut { float *a[10]; };
+// inputs / outputs of k_dvh2dvz: the k = nk2 planes [ny][nx] of the metric (reference order jac, xi_x .. zeta_z), of the media
+// arrays (order of include/cgfd3d_b200.h) and, for the visco-elastic medium, of the coordinates; matrices [ny][nx][9]
+struct DvhArgs {
+  int med;                      // MED_* (0 iso, 1 vti, 2 aniso, 3 visco)
+  int nx, ni1, ni2, nj1, nj2;
+  const float *metric[10];
+  const float *media[24];
+  const float *x, *y, *z;
+  int fd_len; const int *fd_indx; const float *fd_coef;
+  float *matVx2Vz, *matVy2Vz, *matF2Vz, *matD;
+};
+__global__ void k_dvh2dvz(DvhArgs a);
 __global__ void k_metric_cal(const float *x, const float *y, const float *z, int nx, int ny, int ni1, int ni2, int nj1, int nk1,
                              int fd_len, const int *fd_indx, const float *fd_coef, MetricOut out);
 __global__ void k_metric_mirror(MetricOut out, int axis, int nx, int ny, int nz, int n1, int n2);

@@ -90,6 +90,7 @@ struct StageArgs {
   const float *metric[NMETRIC];
   const float *media[MAX_MEDIA];
   int nmaxwell;
+  int vis_staged;               // visco-elastic interior kernel: memory variables and Y arrays staged by TMA (nmaxwell <= VIS_MAX_STAGED)
   float wl[MAX_MAXWELL];
   const float *qatt;            // Graves' attenuation factor exp(-pi f0 dt / Qs) per point, applied to w_end by the last stage; or nullptr
   PmlFaceDev pml[3][2];
@@ -110,7 +111,11 @@ struct TmaMaps {
   // store maps: the PHYSICAL x-y range only (origin (ni1,nj1), extents ni x nj), so that the parts of a tile that hang
   // over the physical range are clipped by the TMA unit and ghosts are never written
   CUtensorMap out_tmp, out_end;
+  // visco-elastic medium, staged variant: the 6N memory variables of the three levels read (box (TX, TY, 1, 6N) of a tensor
+  // that starts at component 9 of the level), the 2N Ylam / Ymu arrays (tensor = media arrays 3 ..), and the store maps
+  CUtensorMap jcur, jpre, jend, ymed, jout_tmp, jout_end;
 };
+constexpr int VIS_MAX_STAGED = 3;   // Maxwell bodies the staged variant has shared memory for (218 KB per block at 3)
 
 // launchers, one explicit instantiation per medium (kernels_{iso,vti,aniso,vis}.cu); dir = direction index per axis of
 // this stage's operator; MED = MED_* of physics.cuh

@@ -49,11 +49,15 @@ constexpr int OFF_END = OFF_PRE + 9 * CEN_BYTES;
 constexpr int OFF_MED = OFF_END + 9 * CEN_BYTES;
 template <int MED> struct Lay {   // the media tiles come last: their number depends on the medium
   static constexpr int NMT = Med<MED>::NTILE;
-  static constexpr int STAGE_BYTES = OFF_MED + NMT * CEN_BYTES;
+  // visco-elastic medium: tiles of the memory variables (cur | pre -> tmp | end, 6 per Maxwell body each) and of Ylam, Ymu
+  static constexpr int NJT = (MED == MED_VIS) ? 6 * VIS_MAX_STAGED : 0, NYT = (MED == MED_VIS) ? 2 * VIS_MAX_STAGED : 0;
+  static constexpr int OFF_JC = OFF_MED + NMT * CEN_BYTES, OFF_JP = OFF_JC + NJT * CEN_BYTES, OFF_JE = OFF_JP + NJT * CEN_BYTES,
+                       OFF_Y = OFF_JE + NJT * CEN_BYTES;
+  static constexpr int STAGE_BYTES = OFF_Y + NYT * CEN_BYTES;
   static constexpr int SMEM_BYTES = NST * STAGE_BYTES + 128 /*alignment slack*/ + 64 /*barriers*/;
   // blocks per SM the shared memory allows (227 KB usable, 1 KB reserved per block)
   static constexpr int BY_SMEM = 233472 / (SMEM_BYTES + 1024);
-  static constexpr int BY_REGS = 65536 / (TILE_X * TILE_Y * 128);   // 128 registers per thread
+  static constexpr int BY_REGS = (MED == MED_VIS) ? 1 : 65536 / (TILE_X * TILE_Y * 128);   // 128 registers per thread (visco: one block)
   static constexpr int BLOCKS = BY_SMEM < BY_REGS ? (BY_SMEM < 1 ? 1 : BY_SMEM) : BY_REGS;
 };
 
@@ -61,12 +65,18 @@ template <int KIND, int MED, bool GZ> __device__ __forceinline__ constexpr uint3
 {
   return CUR_BYTES + ((GZ ? 5 : 9) + Lay<MED>::NMT) * CEN_BYTES + (KIND != KIND_FIRST ? 9 * CEN_BYTES : 0) + (KIND == KIND_LAST ? 9 * CEN_BYTES : 0);
 }
+// bytes of the staged memory-variable / Y tiles of one plane (visco-elastic medium, nj = 6 N tiles per level, 2 N Y tiles)
+template <int KIND> __device__ __forceinline__ uint32_t vis_tx_bytes(int nmx)
+{
+  return (uint32_t)(nmx * CEN_BYTES) * (6 + 2 + (KIND != KIND_FIRST ? 6 : 0) + (KIND == KIND_LAST ? 6 : 0));
+}
 
 struct TmaCtx {
   unsigned char *ring;
   uint64_t *full;
   int tx, ty, t, i, j, i0, j0, k1;
   int pf;              // L2 prefetch distance in planes beyond the ring (0 = off)
+  int nmx;             // visco-elastic medium: Maxwell bodies staged by TMA (0 = none: atten_update reads them with plain loads)
   bool active, inarr;
   size_t pij;
   const float *qptr;   // w_cur + pij: this thread's column of component 0
@@ -82,11 +92,19 @@ __device__ __forceinline__ void tma_issue_a(const StageArgs &P, const TmaMaps &M
   constexpr int YL = Ofs<DY>::left;
   unsigned char *b = C.ring + s * Lay<MED>::STAGE_BYTES;
   uint64_t *bar = C.full + s;
-  mbar_expect_tx(bar, stage_tx_bytes<KIND, MED, GZ>());
+  uint32_t txb = stage_tx_bytes<KIND, MED, GZ>();
+  if constexpr (MED == MED_VIS) txb += vis_tx_bytes<KIND>(C.nmx);
+  mbar_expect_tx(bar, txb);
   // the wavefield tiles overlap their neighbours' (x-y halo): keep them in L2; everything else is touched once per stage
   tma_load_4d_hint(b + OFF_CUR, &M.cur, bar, C.i0 - HX + P.shift, C.j0 - YL, kk, 0, C.pol_keep);
   tma_load_4d_hint(b + OFF_MET, GZ ? &M.met5 : &M.met, bar, C.i0 + P.shift, C.j0, kk, 0, C.pol_stream);
   tma_load_4d_hint(b + OFF_MED, &M.med, bar, C.i0 + P.shift, C.j0, kk, 0, C.pol_stream);
+  if constexpr (MED == MED_VIS) {
+    if (C.nmx > 0) {
+      tma_load_4d_hint(b + Lay<MED>::OFF_JC, &M.jcur, bar, C.i0 + P.shift, C.j0, kk, 0, C.pol_stream);
+      tma_load_4d_hint(b + Lay<MED>::OFF_Y, &M.ymed, bar, C.i0 + P.shift, C.j0, kk, 0, C.pol_stream);
+    }
+  }
 }
 template <int DX, int DY, int KIND, int MED>
 __device__ __forceinline__ void tma_issue_b(const StageArgs &P, const TmaMaps &M, const TmaCtx &C, int kk, int s)
@@ -95,6 +113,12 @@ __device__ __forceinline__ void tma_issue_b(const StageArgs &P, const TmaMaps &M
   uint64_t *bar = C.full + s;
   if (KIND != KIND_FIRST) tma_load_4d_hint(b + OFF_PRE, &M.pre, bar, C.i0 + P.shift, C.j0, kk, 0, C.pol_stream);
   if (KIND == KIND_LAST) tma_load_4d_hint(b + OFF_END, &M.end, bar, C.i0 + P.shift, C.j0, kk, 0, C.pol_stream);
+  if constexpr (MED == MED_VIS) {
+    if (C.nmx > 0) {
+      if (KIND != KIND_FIRST) tma_load_4d_hint(b + Lay<MED>::OFF_JP, &M.jpre, bar, C.i0 + P.shift, C.j0, kk, 0, C.pol_stream);
+      if (KIND == KIND_LAST) tma_load_4d_hint(b + Lay<MED>::OFF_JE, &M.jend, bar, C.i0 + P.shift, C.j0, kk, 0, C.pol_stream);
+    }
+  }
 }
 // every operand of plane kk into L2 (thread 0, PF planes ahead of the ring refill): the ring holds only NST planes per block,
 // too few bytes in flight to cover DRAM latency; the L2 has room for several more
@@ -139,25 +163,6 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
     for (int c = 0; c < 9; c++) qn[c] = __ldg(w + c * P.siz_vol);
   }
   if (PML && C.active && it + 1 < nplanes) pml_prefetch<KIND>(P, C.i, C.j, k + DIR);
-#if CGFD_VIS_PREFETCH
-  // EXPERIMENT (build switch, off by default, not yet validated on the GPU): the memory variables and Y arrays of the next
-  // plane requested into L2 by the first lane of every warp (one 128-byte line = the warp's 32 points per array and level)
-  if constexpr (MED == MED_VIS) {
-    if (C.active && C.tx == 0 && it + 1 < nplanes) {
-      const size_t pn = (size_t)(k + DIR) * P.siz_slice + C.pij;
-      for (int n = 0; n < P.nmaxwell; n++) {
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.media[3 + n] + pn));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.media[3 + P.nmaxwell + n] + pn));
-        for (int q = 0; q < 6; q++) {
-          const size_t o = (size_t)(9 + 6 * n + q) * P.siz_vol + pn;
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(P.cur + o));
-          if (KIND != KIND_FIRST) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.pre + o));
-          if (KIND == KIND_LAST) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.end + o));
-        }
-      }
-    }
-  }
-#endif
   // Graves' attenuation factor of this point (last stage only; requested before the wait below so that it is there in time)
   float qatt = 1.0f;
   if (KIND == KIND_LAST && P.qatt && C.active) qatt = __ldg(P.qatt + (size_t)k * P.siz_slice + C.pij);
@@ -190,7 +195,12 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
     }
     hooke<MED, GZ>(d, m, md, h);
     if (PML) pml_all<KIND, 0, MED>(P, C.i, C.j, k, d, m, md, h);
-    if constexpr (MED == MED_VIS) atten_update<KIND>(P, (size_t)k * P.siz_slice + C.pij, md.lam, md.mu, h);
+    if constexpr (MED == MED_VIS) {
+      if (C.nmx > 0)
+        atten_smem<KIND>((const float *)(b + Lay<MED>::OFF_JC) + C.t, (float *)(b + Lay<MED>::OFF_JP) + C.t, (float *)(b + Lay<MED>::OFF_JE) + C.t,
+                         (const float *)(b + Lay<MED>::OFF_Y) + C.t, NT, C.nmx, P.wl, md.lam, md.mu, h, P.a, P.b, P.c);
+      else atten_update<KIND>(P, (size_t)k * P.siz_slice + C.pij, md.lam, md.mu, h);
+    }
 #pragma unroll
     for (int c = 3; c < 9; c++) rk_smem<KIND>(sp + c * NT, se + c * NT, qz[c], h[c], P.a, P.b, P.c, qatt);
     // ---- velocity half: needs the stress derivatives only
@@ -218,6 +228,13 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
       if (KIND != KIND_LAST) sp[c * NT] = 0.0f;
       if (KIND == KIND_MID || KIND == KIND_LAST) se[c * NT] = 0.0f;
     }
+    if constexpr (MED == MED_VIS) {
+      float *jp = (float *)(b + Lay<MED>::OFF_JP) + C.t, *je = (float *)(b + Lay<MED>::OFF_JE) + C.t;
+      for (int c = 0; c < 6 * C.nmx; c++) {
+        if (KIND != KIND_LAST) jp[c * NT] = 0.0f;
+        if (KIND == KIND_MID || KIND == KIND_LAST) je[c * NT] = 0.0f;
+      }
+    }
     fence_proxy_async_smem();
   }
   __syncthreads();   // every thread is done with ring slot s; its PRE / END tiles now hold w_tmp / w_end of this plane
@@ -228,6 +245,12 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
     if (C.pf > 0 && it + NST + C.pf < nplanes) tma_prefetch_plane<DX, DY, KIND, MED, GZ>(P, M, C, k + (NST + C.pf) * DIR);
     if (KIND != KIND_LAST) tma_store_4d_hint(&M.out_tmp, b + OFF_PRE, tx0, ty0, k, 0, C.pol_stream);
     if (KIND == KIND_MID || KIND == KIND_LAST) tma_store_4d_hint(&M.out_end, b + OFF_END, tx0, ty0, k, 0, C.pol_stream);
+    if constexpr (MED == MED_VIS) {
+      if (C.nmx > 0) {
+        if (KIND != KIND_LAST) tma_store_4d_hint(&M.jout_tmp, b + Lay<MED>::OFF_JP, tx0, ty0, k, 0, C.pol_stream);
+        if (KIND == KIND_MID || KIND == KIND_LAST) tma_store_4d_hint(&M.jout_end, b + Lay<MED>::OFF_JE, tx0, ty0, k, 0, C.pol_stream);
+      }
+    }
     tma_store_commit();
     if (P.l2mode & 8) tma_store_wait_all();   // debugging switch: synchronous stores
     if (refill) {
@@ -259,6 +282,7 @@ __global__ void __launch_bounds__(TX *TY, Lay<MED>::BLOCKS) k_main_tma(const Sta
   C.active = (C.i <= P.ni2) && (C.j <= P.nj2);
   C.pij = (size_t)C.j * P.siz_line + C.i;
   C.qptr = P.cur + C.pij;
+  C.nmx = (MED == MED_VIS && P.vis_staged) ? P.nmaxwell : 0;
   C.pol_keep = (P.l2mode & 1) ? l2_policy_evict_last() : l2_policy_evict_normal();
   C.pol_stream = (P.l2mode & 2) ? l2_policy_evict_first() : l2_policy_evict_normal();
 
@@ -323,9 +347,6 @@ __global__ void __launch_bounds__(TX *TY, Lay<MED>::BLOCKS) k_main_tma(const Sta
 // launch (blockIdx.z = row * 2 + half): twice the parallelism at ~half the registers of a thread that does both (168 registers,
 // 12 warps per SM: latency bound, ncu r1x: long-scoreboard 4.5 per issue, 30 % of the DRAM rate, 6 % of a step for 2 % of the points).
 // =============================================================================================
-#ifndef CGFD_VIS_PREFETCH
-#define CGFD_VIS_PREFETCH 0
-#endif
 template <int DX, int DY, int DZ, int KIND, int MED, int HALF>
 __device__ __forceinline__ void top_half(const StageArgs &P, int k)
 {

@@ -409,4 +409,43 @@ __device__ __forceinline__ void atten_update(const StageArgs &P, size_t p, float
   h[TXY] -= 2.0f * mu * sum[5];
 }
 
+// The same attenuation step on tiles staged in shared memory by TMA (interior kernel, nmaxwell <= VIS_MAX_STAGED): jc = memory
+// variables of the level this stage reads, jp = level n (in) -> w_tmp (out), je = accumulating level (in / out), y = Ylam[0..N-1],
+// Ymu[0..N-1]; every pointer is this thread's entry of tile 0, tiles are nt floats apart; component 6 n + q of body n.
+template <int KIND>
+__device__ __forceinline__ void atten_smem(const float *jc, float *jp, float *je, const float *y, int nt, int N, const float *wl,
+                                           float lam, float mu, float *h, float a, float b, float c)
+{
+  const float sum_hxyz = (h[TXX] + h[TYY] + h[TZZ]) / (3.0f * lam + 2.0f * mu);
+  float EV[6];
+  EV[0] = ((2.0f * h[TXX] - h[TYY] - h[TZZ]) / (2.0f * mu) + sum_hxyz) / 3.0f;
+  EV[1] = ((2.0f * h[TYY] - h[TXX] - h[TZZ]) / (2.0f * mu) + sum_hxyz) / 3.0f;
+  EV[2] = ((2.0f * h[TZZ] - h[TXX] - h[TYY]) / (2.0f * mu) + sum_hxyz) / 3.0f;
+  EV[3] = h[TYZ] / mu * 0.5f;
+  EV[4] = h[TXZ] / mu * 0.5f;
+  EV[5] = h[TXY] / mu * 0.5f;
+  float sum_tr = 0.0f, sum[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+  for (int n = 0; n < VIS_MAX_STAGED; n++) {
+    if (n < N) {
+      const float ylam = y[n * nt], ymu = y[(N + n) * nt], w = wl[n];
+      float J[6];
+#pragma unroll
+      for (int q = 0; q < 6; q++) J[q] = jc[(6 * n + q) * nt];
+      sum_tr += ylam * (J[0] + J[1] + J[2]);
+#pragma unroll
+      for (int q = 0; q < 6; q++) {
+        sum[q] += ymu * J[q];
+        rk_smem<KIND>(jp + (6 * n + q) * nt, je + (6 * n + q) * nt, J[q], w * (EV[q] - J[q]), a, b, c);
+      }
+    }
+  }
+  h[TXX] -= lam * sum_tr + 2.0f * mu * sum[0];
+  h[TYY] -= lam * sum_tr + 2.0f * mu * sum[1];
+  h[TZZ] -= lam * sum_tr + 2.0f * mu * sum[2];
+  h[TYZ] -= 2.0f * mu * sum[3];
+  h[TXZ] -= 2.0f * mu * sum[4];
+  h[TXY] -= 2.0f * mu * sum[5];
+}
+
 }  // namespace cgfd

@@ -25,7 +25,7 @@ SYMBOLS = [
     "cgfd_b200_comm_unique_id", "cgfd_b200_comm_init", "cgfd_b200_halo_plan", "cgfd_b200_set_profiling", "cgfd_b200_get_profile",
     "cgfd_b200_last_run_ms", "cgfd_b200_set_variant", "cgfd_b200_grid_class",
     "cgfd_b200_add_snapshot", "cgfd_b200_snapshot_frames", "cgfd_b200_dd_set_points", "cgfd_b200_dd_load_block",
-    "cgfd_b200_metric_from_coords", "cgfd_b200_launch_plan",
+    "cgfd_b200_metric_from_coords", "cgfd_b200_launch_plan", "cgfd_b200_dvh2dvz",
 ]
 
 _lib = None
@@ -76,6 +76,7 @@ def load_library():
     L.cgfd_b200_dd_load_block.argtypes = [vp, ci, ci, fp, fp]
     L.cgfd_b200_launch_plan.argtypes = [C.POINTER(abi.Grid), C.POINTER((ci * 2) * 3), ci, ci, ci, C.POINTER(ci * 4), C.POINTER(ci), C.POINTER(ci), ci]
     L.cgfd_b200_metric_from_coords.argtypes = [ci, C.POINTER(abi.Grid), fp, fp, fp, ci, C.POINTER(ci), fp, C.POINTER(fp * 10)]
+    L.cgfd_b200_dvh2dvz.argtypes = [ci, C.POINTER(abi.Problem), fp, fp, fp, ci, C.POINTER(ci), fp, fp, fp, fp, fp]
     _lib = L
     return L
 
@@ -250,6 +251,35 @@ def metric_from_coords(grid: dict, x, y, z, fd_indx=None, fd_coef=None, device=0
     ii = (C.c_int * len(fd_indx))(*fd_indx)
     cc = np.asarray(fd_coef, np.float32)
     if L.cgfd_b200_metric_from_coords(device, C.byref(g), _f(x), _f(y), _f(z), len(fd_indx), ii, _f(cc), C.byref(po)) != 0:
+        raise CgfdError(L.cgfd_b200_last_error().decode())
+    return out
+
+
+def dvh2dvz(prob, device=0):
+    """The free-surface conversion matrices of `prob` (a hostsetup.HostProblem) computed by the library on the GPU
+    (*_dvh2dvz of the four constitutive laws, include/cgfd3d_b200.h): dict(matVx2Vz, matVy2Vz, matF2Vz, matD) of flat
+    [ny*nx*9] arrays, ready for prob.mats. The visco-elastic medium needs prob.coords."""
+    from . import hostsetup
+    L = load_library()
+    n = prob.nx * prob.ny * 9
+    out = {k: np.zeros(n, np.float32) for k in ("matVx2Vz", "matVy2Vz", "matF2Vz", "matD")}
+    saved, prob.mats = prob.mats, {}
+    try:
+        c = prob.to_c()
+    finally:
+        prob.mats = saved
+    null = abi.fptr()
+    vis = prob.medium_type == abi.MEDIUM_VISCOELASTIC_ISO
+    if vis:
+        x, y, z = (np.ascontiguousarray(a, np.float32) for a in prob.coords)
+        xyz = (_f(x), _f(y), _f(z))
+    else:
+        xyz = (null, null, null)
+    ii = (C.c_int * len(hostsetup.FDC_INDX))(*hostsetup.FDC_INDX)
+    cc = np.asarray(hostsetup.FDC_COEF, np.float32)
+    rc = L.cgfd_b200_dvh2dvz(device, C.byref(c), xyz[0], xyz[1], xyz[2], len(hostsetup.FDC_INDX), ii, _f(cc),
+                             _f(out["matVx2Vz"]), _f(out["matVy2Vz"]), _f(out["matF2Vz"]), _f(out["matD"]))
+    if rc != 0:
         raise CgfdError(L.cgfd_b200_last_error().decode())
     return out
 

@@ -217,6 +217,17 @@ int  cgfd_b200_halo_plan(const cgfd_grid_t *grid, int dirx, int diry, int side, 
 int  cgfd_b200_metric_from_coords(int device, const cgfd_grid_t *grid, const float *x, const float *y, const float *z, int fd_len,
                                   const int *fd_indx, const float *fd_coef, float *const metric_out[10]);
 
+/* The free-surface conversion matrices of the four constitutive laws: sv_curv_col_el_iso_dvh2dvz (forward/sv_curv_col_el_iso.c:
+ * 1258-1375), _vti_ (forward/sv_curv_col_el_vti.c:1085-1205), _aniso_ (forward/sv_curv_col_el_aniso.c:1267-1422) and
+ * sv_curv_col_vis_iso_dvh2dvz (forward/sv_curv_col_vis_iso.c:353-507), called by the reference driver at
+ * forward/drv_rk_curv_col.c:132-159. Reads medium_type, grid, metric[] and media[] of `prob` (host or device pointers, whole
+ * arrays [nz][ny][nx]; only the k = nk2 plane is touched) and writes matVx2Vz, matVy2Vz [ny][nx][9] (host or device), matF2Vz
+ * (isotropic medium only; zero otherwise, may be NULL) and matD (visco-elastic medium only; may be NULL otherwise). The
+ * visco-elastic medium also needs the coordinate arrays x, y, z [nz][ny][nx] and the centred operator fd->fdc_indx / fdc_coef
+ * (surface tangent for matD). Bit-identical to the reference functions (no FMA contraction, same order of operations). */
+int  cgfd_b200_dvh2dvz(int device, const cgfd_problem_t *prob, const float *x, const float *y, const float *z, int fd_len,
+                       const int *fd_indx, const float *fd_coef, float *matVx2Vz, float *matVy2Vz, float *matF2Vz, float *matD);
+
 /* ---- distributed (finite-fault) sources ------------------------------------------------------- */
 /* src_t dd_* (forward/src_t.h:94-126): `n` grid points indx[] = src->dd_indx (flat host index i + j*nx + k*nx*ny) that receive a
  * velocity source vi and / or a moment-rate source mij at every stage of every step, added at the point

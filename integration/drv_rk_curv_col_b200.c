@@ -6,10 +6,10 @@
  * stay the reference's own.
  *
  * What runs where:
- *   host (reference code, unchanged): nc file creation, free-surface matrix set-up (*_dvh2dvz),
+ *   host (reference code, unchanged): nc file creation,
  *        io_recv_keep / io_line_keep / io_slice_nc_put / io_snap_nc_put / PG_slice_output;
  *   GPU (libcgfd3d_b200.so through the C ABI of include/cgfd3d_b200.h): the whole RK4 stage loop --
- *        RHS, CFS-PML, free surface, sources, RK update, halo exchange, PGV/PGA/PGD maps.
+ *        RHS, CFS-PML, free surface, sources, RK update, halo exchange, PGV/PGA/PGD maps; the free-surface matrices (*_dvh2dvz).
  * After every step only the samples the output taps need are copied back: the receiver / line points
  * (recorded on the device) and, on the steps a slice or snapshot is due, its strided sub-boxes. They are
  * written into the host wavefield level the reference functions read (w_end), so those run unmodified.
@@ -26,11 +26,6 @@
 #include "fdlib_math.h"
 #include "blk_t.h"
 #include "drv_rk_curv_col.h"
-#include "sv_curv_col_el.h"
-#include "sv_curv_col_el_iso.h"
-#include "sv_curv_col_el_vti.h"
-#include "sv_curv_col_el_aniso.h"
-#include "sv_curv_col_vis_iso.h"
 
 #include "cgfd3d_b200.h"
 
@@ -116,16 +111,6 @@ drv_rk_curv_col_allstep(
   iosnap_nc_t iosnap_nc;
   io_snap_nc_create(iosnap, &iosnap_nc, topoid);
 
-  /* free-surface conversion matrices: one-shot host set-up, reference code (drv_rk_curv_col.c:132-159) */
-  if (bdry->is_sides_free[CONST_NDIM - 1][1] == 1) {
-    if (md->medium_type == CONST_MEDIUM_ELASTIC_ISO) sv_curv_col_el_iso_dvh2dvz(gd, metric, md, bdry, verbose);
-    else if (md->medium_type == CONST_MEDIUM_ELASTIC_VTI) sv_curv_col_el_vti_dvh2dvz(gd, metric, md, bdry, verbose);
-    else if (md->medium_type == CONST_MEDIUM_ELASTIC_ANISO) sv_curv_col_el_aniso_dvh2dvz(gd, metric, md, bdry, verbose);
-    else if (md->medium_type == CONST_MEDIUM_VISCOELASTIC_ISO && md->visco_type == CONST_VISCO_GMB)
-      sv_curv_col_vis_iso_dvh2dvz(gd, metric, md, bdry, fd->fdc_len, fd->fdc_indx, fd->fdc_coef, verbose);
-    else DIE("conversion matrix for medium_type=%d is not implemented", md->medium_type);
-  }
-
   /* ---- flatten the reference structs into the C ABI problem description ---------------------------- */
   cgfd_problem_t P;
   memset(&P, 0, sizeof(P));
@@ -162,7 +147,17 @@ drv_rk_curv_col_allstep(
     P.pml[d][s].enabled = 1; P.pml[d][s].nlay = bdry->num_of_layers[d][s];
     P.pml[d][s].A = bdry->A[d][s]; P.pml[d][s].B = bdry->B[d][s]; P.pml[d][s].D = bdry->D[d][s];
   }
-  if (P.free_top) { P.matVx2Vz = bdry->matVx2Vz2; P.matVy2Vz = bdry->matVy2Vz2; P.matF2Vz = bdry->matF2Vz2; P.matD = bdry->matD; }
+  if (P.free_top) {
+    /* free-surface conversion matrices: the *_dvh2dvz call of forward/drv_rk_curv_col.c:132-159, computed on the device by the
+     * library (bit-identical to the reference functions) into the arrays bdry_free_set allocated */
+    if (md->medium_type == CONST_MEDIUM_VISCOELASTIC_ISO && md->visco_type != CONST_VISCO_GMB)
+      DIE("conversion matrix for visco_type=%d is not implemented (neither is it in the reference, forward/drv_rk_curv_col.c:150-157)", md->visco_type);
+    int ndev0 = cgfd_b200_device_count();
+    if (ndev0 <= 0) DIE("no CUDA device visible (this driver has no CPU fallback)");
+    GPU(cgfd_b200_dvh2dvz(myid % ndev0, &P, gd->x3d, gd->y3d, gd->z3d, fd->fdc_len, fd->fdc_indx, fd->fdc_coef,
+                          bdry->matVx2Vz2, bdry->matVy2Vz2, bdry->matF2Vz2, bdry->matD));
+    P.matVx2Vz = bdry->matVx2Vz2; P.matVy2Vz = bdry->matVy2Vz2; P.matF2Vz = bdry->matF2Vz2; P.matD = bdry->matD;
+  }
   if (bdry->is_enable_ablexp == 1) {
     P.ablexp_enabled = 1;
     for (int n = 0; n < CONST_NDIM_2; n++) {

@@ -185,3 +185,26 @@ def test_distributed_sources(case):
     assert float(np.abs(wr[0]).max()) > 0 and np.isfinite(wg).all()
     bad = [(util.CMP[c], util.rel_l2(wg[c], wr[c])) for c in range(9) if not util.rel_l2(wg[c], wr[c]) <= TOL_RUN]
     assert not bad, bad
+
+
+@pytest.mark.parametrize("medium", ["iso", "vti", "aniso", "visco"])
+def test_dvh2dvz_on_device(medium):
+    """cgfd_b200_dvh2dvz = the reference's *_dvh2dvz of the four constitutive laws (iso.c:1258-1375, vti.c:1085-1205,
+    aniso.c:1267-1422, vis_iso.c:353-507) on the GPU: bit-identical matrices on a hill grid with heterogeneous media and
+    perturbed x-y grid lines (every metric array matters)."""
+    _need()
+    from cgfd3d_b200 import hostsetup as hs
+    prob = util.small_problem(ni=37, nj=29, nk=23, seed=4, medium=medium)
+    x, y, z = (a.copy() for a in prob.coords)
+    rng = np.random.default_rng(2)
+    x += rng.uniform(-8, 8, x.shape).astype(np.float32)
+    y += rng.uniform(-8, 8, y.shape).astype(np.float32)
+    prob.coords = (x, y, z)
+    prob.metric = hs.metric_from_coords(x, y, z)
+    ref = ref_flat.RefSolver(prob).dvh2dvz()
+    got = solver.dvh2dvz(prob)
+    assert float(np.abs(ref["matVx2Vz"]).max()) > 0
+    names = ["matVx2Vz", "matVy2Vz"] + (["matF2Vz"] if medium == "iso" else []) + (["matD"] if medium == "visco" else [])
+    for k in names:
+        assert float(np.abs(ref[k]).max()) > 0, k
+        np.testing.assert_array_equal(got[k], ref[k], err_msg=k)
