@@ -90,6 +90,7 @@ struct SnapTap {
   int ncmp = 0; int cmps[32];
   int box[9];                    // i1, ni, di, j1, nj, dj, k1, nk, dk (local indices incl. ghosts)
   int it1 = 0, tinv = 1, max_frames = 0, nframes = 0;
+  long nissued = 0;              // frames ever issued (ring slot = nissued % SNAP_RING; nframes restarts with every output buffer)
   size_t cmp_elems = 0;          // ni*nj*nk
   float *host = nullptr;         // [max_frames][ncmp][nk][nj][ni]
   float *ring[SNAP_RING];
@@ -169,7 +170,9 @@ struct cgfd_b200_ctx {
   std::vector<cudaEvent_t> ev;   // pairs around the main kernel
   size_t ev_used = 0;
   double main_ms = 0; int64_t main_launches = 0, total_launches = 0;
-  cudaEvent_t run0 = nullptr, run1 = nullptr; double last_run_ms = 0;
+  cudaEvent_t run0 = nullptr, run1 = nullptr, ev_rec = nullptr; double last_run_ms = 0;
+  struct { int it_last = -1; cudaEvent_t done = nullptr; } blk[4];   // completion of the last asynchronous blocks (run_async / wait_block)
+  int blk_next = 0;
   int variant = 0;
   int neigh[4] = {-1, -1, -1, -1};
   HaloComm *halo = nullptr;
@@ -642,6 +645,8 @@ extern "C" void cgfd_b200_destroy(cgfd_b200_ctx *c)
   for (auto e : c->ev) cudaEventDestroy(e);
   if (c->run0) cudaEventDestroy(c->run0);
   if (c->run1) cudaEventDestroy(c->run1);
+  if (c->ev_rec) cudaEventDestroy(c->ev_rec);
+  for (auto &b : c->blk) if (b.done) cudaEventDestroy(b.done);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
   for (SnapTap *t : c->snaps) {
@@ -1030,7 +1035,8 @@ static int drain_profile(cgfd_b200_ctx *c)
   return 0;
 }
 
-extern "C" int cgfd_b200_run(cgfd_b200_ctx *c, int it0, int nsteps)
+// enqueue nsteps RK4 steps (no host synchronisation except when a snapshot ring is full)
+static int run_enqueue(cgfd_b200_ctx *c, int it0, int nsteps)
 {
   CK(cudaSetDevice(c->device));
   StageArgs P;
@@ -1085,8 +1091,8 @@ extern "C" int cgfd_b200_run(cgfd_b200_ctx *c, int it0, int nsteps)
     for (SnapTap *t : c->snaps) {
       // io_snap_nc_put / io_slice_nc_put (forward/io_funcs.c:991-1268): frame of w_end every tinv steps from it1 on
       if (it < t->it1 || (it - t->it1) % t->tinv != 0 || t->nframes >= t->max_frames) continue;
-      const int r = t->nframes % SNAP_RING;
-      if (t->nframes >= SNAP_RING) CK(cudaEventSynchronize(t->copied[r]));   // the slot's previous frame has left the device
+      const int r = (int)(t->nissued % SNAP_RING);
+      if (t->nissued >= SNAP_RING) CK(cudaEventSynchronize(t->copied[r]));   // the slot's previous frame has left the device
       const size_t tot = t->cmp_elems;
       for (int m = 0; m < t->ncmp; m++)
         k_pack_box<<<(unsigned)((tot + 255) / 256), 256, 0, c->st>>>(wnew + (size_t)t->cmps[m] * c->V, c->PX, g.ny, t->box[0], t->box[1], t->box[2],
@@ -1098,22 +1104,74 @@ extern "C" int cgfd_b200_run(cgfd_b200_ctx *c, int it0, int nsteps)
       CK(cudaMemcpyAsync(t->host + (size_t)t->nframes * t->ncmp * tot, t->ring[r], (size_t)t->ncmp * tot * sizeof(float),
                          cudaMemcpyDeviceToHost, c->st_io));
       CK(cudaEventRecord(t->copied[r], c->st_io));
-      t->nframes++;
+      t->nframes++; t->nissued++;
     }
     // swap levels n <-> n+1 (forward/drv_rk_curv_col.c:530-542)
     int t = c->ipre; c->ipre = c->iend; c->iend = t;
     if (c->profiling && c->ev_used > 4096) { if (drain_profile(c)) return 1; }
   }
   CK(cudaEventRecord(c->run1, c->st));
+  CK(cudaGetLastError());
+  return 0;
+}
+extern "C" int cgfd_b200_sync(cgfd_b200_ctx *c)
+{
+  CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->st));
-  if (!c->snaps.empty()) CK(cudaStreamSynchronize(c->st_io));   // every frame of these steps is in host memory on return
+  CK(cudaStreamSynchronize(c->st_io));   // every snapshot frame / record copy of the enqueued steps is in host memory on return
   CK(cudaGetLastError());
   float ms = 0;
-  CK(cudaEventElapsedTime(&ms, c->run0, c->run1));
-  c->last_run_ms = ms;
+  if (cudaEventElapsedTime(&ms, c->run0, c->run1) == cudaSuccess) c->last_run_ms = ms; else cudaGetLastError();
   if (drain_profile(c)) return 1;
   return 0;
 }
+extern "C" int cgfd_b200_run(cgfd_b200_ctx *c, int it0, int nsteps)
+{
+  if (run_enqueue(c, it0, nsteps)) return 1;
+  return cgfd_b200_sync(c);
+}
+extern "C" int cgfd_b200_run_async(cgfd_b200_ctx *c, int it0, int nsteps, float *rec_out)
+{
+  const int first = c->rec_count;
+  if (run_enqueue(c, it0, nsteps)) return 1;
+  // everything these steps produce for the host (snapshot frames: already on the I/O stream; record samples: below) is complete
+  // when the block's event on the I/O stream is
+  if (!c->ev_rec) CK(cudaEventCreateWithFlags(&c->ev_rec, cudaEventDisableTiming));
+  CK(cudaEventRecord(c->ev_rec, c->st));
+  CK(cudaStreamWaitEvent(c->st_io, c->ev_rec, 0));
+  if (rec_out && c->nrec > 0 && c->rec_count > first) {
+    const size_t row = (size_t)c->ncmp * c->nrec;
+    CK(cudaMemcpyAsync(rec_out, c->rec + (size_t)first * row, (size_t)(c->rec_count - first) * row * sizeof(float), cudaMemcpyDeviceToHost, c->st_io));
+  }
+  auto &b = c->blk[c->blk_next];
+  c->blk_next = (c->blk_next + 1) % 4;
+  if (!b.done) CK(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming | cudaEventBlockingSync));
+  CK(cudaEventRecord(b.done, c->st_io));
+  b.it_last = it0 + nsteps - 1;
+  return 0;
+}
+extern "C" int cgfd_b200_wait_block(cgfd_b200_ctx *c, int it_last)
+{
+  CK(cudaSetDevice(c->device));
+  for (auto &b : c->blk)
+    if (b.done && b.it_last == it_last) { CK(cudaEventSynchronize(b.done)); return 0; }
+  return fail("wait_block: no asynchronous block in flight ends at step " + std::to_string(it_last));
+}
+extern "C" int cgfd_b200_snapshot_set_output(cgfd_b200_ctx *c, int id, float *host_out, int max_frames)
+{
+  if (id < 0 || id >= (int)c->snaps.size() || !host_out || max_frames <= 0) return fail("snapshot_set_output: bad arguments");
+  SnapTap *t = c->snaps[id];
+  // frames already enqueued keep the destination they were enqueued with
+  t->host = host_out; t->max_frames = max_frames; t->nframes = 0;
+  return 0;
+}
+extern "C" int cgfd_b200_host_alloc(size_t bytes, void **out)
+{
+  *out = nullptr;
+  CK(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+  return 0;
+}
+extern "C" void cgfd_b200_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 extern "C" int cgfd_b200_onestage(cgfd_b200_ctx *c, int it, int ipair, int istage, const float *w_cur, float *rhs)
 {

@@ -26,6 +26,7 @@ SYMBOLS = [
     "cgfd_b200_last_run_ms", "cgfd_b200_set_variant", "cgfd_b200_grid_class",
     "cgfd_b200_add_snapshot", "cgfd_b200_snapshot_frames", "cgfd_b200_dd_set_points", "cgfd_b200_dd_load_block",
     "cgfd_b200_metric_from_coords", "cgfd_b200_launch_plan", "cgfd_b200_dvh2dvz",
+    "cgfd_b200_run_async", "cgfd_b200_sync", "cgfd_b200_wait_block", "cgfd_b200_snapshot_set_output", "cgfd_b200_host_alloc", "cgfd_b200_host_free",
 ]
 
 _lib = None
@@ -76,6 +77,13 @@ def load_library():
     L.cgfd_b200_dd_load_block.argtypes = [vp, ci, ci, fp, fp]
     L.cgfd_b200_launch_plan.argtypes = [C.POINTER(abi.Grid), C.POINTER((ci * 2) * 3), ci, ci, ci, C.POINTER(ci * 4), C.POINTER(ci), C.POINTER(ci), ci]
     L.cgfd_b200_metric_from_coords.argtypes = [ci, C.POINTER(abi.Grid), fp, fp, fp, ci, C.POINTER(ci), fp, C.POINTER(fp * 10)]
+    L.cgfd_b200_run_async.argtypes = [vp, ci, ci, fp]
+    L.cgfd_b200_sync.argtypes = [vp]
+    L.cgfd_b200_wait_block.argtypes = [vp, ci]
+    L.cgfd_b200_snapshot_set_output.argtypes = [vp, ci, fp, ci]
+    L.cgfd_b200_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.cgfd_b200_host_free.argtypes = [vp]
+    L.cgfd_b200_host_free.restype = None
     L.cgfd_b200_dvh2dvz.argtypes = [ci, C.POINTER(abi.Problem), fp, fp, fp, ci, C.POINTER(ci), fp, fp, fp, fp, fp]
     _lib = L
     return L
@@ -158,6 +166,21 @@ class Solver:
 
     def run(self, nsteps, it0=0):
         self._chk(self.L.cgfd_b200_run(self.h, it0, nsteps))
+
+    def run_async(self, nsteps, it0=0, rec_out=None):
+        """enqueue nsteps steps and return; rec_out [nsteps][ncmp][nrec] receives their record samples (see sync())"""
+        self._chk(self.L.cgfd_b200_run_async(self.h, it0, nsteps, abi.fptr() if rec_out is None else _f(rec_out)))
+
+    def sync(self):
+        self._chk(self.L.cgfd_b200_sync(self.h))
+
+    def wait_block(self, it_last):
+        self._chk(self.L.cgfd_b200_wait_block(self.h, it_last))
+
+    def snapshot_set_output(self, sid, out):
+        assert out.dtype == np.float32 and out.flags["C_CONTIGUOUS"]
+        self._chk(self.L.cgfd_b200_snapshot_set_output(self.h, sid, _f(out), out.shape[0]))
+        self._snap_keep = getattr(self, "_snap_keep", []) + [out]
 
     # -- taps
     def set_record_points(self, iptr, max_nt):

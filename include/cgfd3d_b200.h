@@ -253,6 +253,21 @@ int  cgfd_b200_add_snapshot(cgfd_b200_ctx *ctx, int ncmps, const int *cmps, cons
 /* frames written so far for snapshot `id` (-1: unknown id) */
 int  cgfd_b200_snapshot_frames(cgfd_b200_ctx *ctx, int id);
 
+/* Asynchronous time stepping for a host program that post-processes the outputs of one block of steps while the GPU runs the next:
+ * cgfd_b200_run_async enqueues the steps and returns; rec_out (may be NULL; pinned memory for a true asynchronous copy) receives
+ * the record samples of these steps as [nsteps][ncmp][npoints] once they exist. cgfd_b200_sync waits for everything enqueued: steps,
+ * snapshot frames, record copies. cgfd_b200_snapshot_set_output points snapshot `id` at another host buffer for the frames that
+ * follow (frame counter restarts at 0; frames already enqueued keep their destination), so that two buffers can alternate between blocks. cgfd_b200_host_alloc / _free give
+ * page-locked host memory to a C program that does not link the CUDA runtime itself. */
+int  cgfd_b200_run_async(cgfd_b200_ctx *ctx, int it0, int nsteps, float *rec_out);
+int  cgfd_b200_sync(cgfd_b200_ctx *ctx);
+/* wait for the block of steps a cgfd_b200_run_async call enqueued (identified by its last step) and for its outputs; blocks
+ * enqueued after it keep running. The last four blocks can be waited for. */
+int  cgfd_b200_wait_block(cgfd_b200_ctx *ctx, int it_last);
+int  cgfd_b200_snapshot_set_output(cgfd_b200_ctx *ctx, int id, float *host_out, int max_frames);
+int  cgfd_b200_host_alloc(size_t bytes, void **out);
+void cgfd_b200_host_free(void *p);
+
 /* The launch plan of the interior kernel for the tile rectangle rect = {bx0, bx1, by0, by1} (tiles of 32 x 8 points counted from
  * (ni1, nj1)); pure host logic, no GPU needed. pml_nlay[idim][iside] = layers of the CFS-PML on that face (0 = none). Returns the
  * number of blocks, *zchunk = rows per z chunk, order[b] = (chunk * ntiles_y + tile_y) * ntiles_x + tile_x of the b-th block:

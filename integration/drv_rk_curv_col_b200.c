@@ -59,18 +59,34 @@ static void flatten_fd(const fd_t *fd, cgfd_fd_t *o)
   }
 }
 
-/* copy a strided box of component icmp from the device into the host level `w` at the same indices */
-static void fetch_box(cgfd_b200_ctx *ctx, float *w, size_t siz_icmp, size_t siz_line, size_t siz_slice, int icmp,
-                      int i1, int ni, int di, int j1, int nj, int dj, int k1, int nk, int dk, float **buf, size_t *cap)
+/* one streaming output (slice or snapshot): components c1 .. c1+ncmp-1 of the strided box, every tinv steps from it1 on */
+typedef struct {
+  int id, c1, ncmp, box[9], it1, tinv, cap, frame;
+  size_t elems;
+  float *buf[2];
+} tap_t;
+static void tap_set(tap_t *T, int c1, int c2, int i1, int ni, int di, int j1, int nj, int dj, int k1, int nk, int dk, int it1, int tinv)
 {
-  size_t tot = (size_t)ni * nj * nk;
-  if (tot == 0) return;
-  if (tot > *cap) { *buf = (float *)realloc(*buf, tot * sizeof(float)); *cap = tot; }
-  GPU(cgfd_b200_get_box(ctx, icmp, i1, ni, di, j1, nj, dj, k1, nk, dk, *buf));
-  float *var = w + (size_t)icmp * siz_icmp;
-  size_t n = 0;
-  for (int kk = 0; kk < nk; kk++) for (int jj = 0; jj < nj; jj++) for (int ii = 0; ii < ni; ii++)
-    var[(size_t)(i1 + ii * di) + (size_t)(j1 + jj * dj) * siz_line + (size_t)(k1 + kk * dk) * siz_slice] = (*buf)[n++];
+  int b[9] = { i1, ni, di, j1, nj, dj, k1, nk, dk };
+  memcpy(T->box, b, sizeof(b));
+  T->c1 = c1; T->ncmp = c2 - c1 + 1; T->it1 = it1; T->tinv = tinv > 0 ? tinv : 1;
+  T->elems = (size_t)ni * nj * nk;
+}
+/* if a frame of this tap is due at step `it`: copy it from the block's host buffer into the host level `w` at the box's own indices */
+static void tap_scatter(tap_t *T, int set, int it, float *w, size_t siz_icmp, size_t siz_line, size_t siz_slice)
+{
+  if (it < T->it1 || (it - T->it1) % T->tinv != 0 || T->elems == 0) return;
+  const int *b = T->box;
+  const float *f = T->buf[set] + (size_t)T->frame * T->ncmp * T->elems;
+  for (int c = 0; c < T->ncmp; c++) {
+    float *var = w + (size_t)(T->c1 + c) * siz_icmp;
+    size_t n = (size_t)c * T->elems;
+    for (int kk = 0; kk < b[7]; kk++) for (int jj = 0; jj < b[4]; jj++) {
+      float *row = var + (size_t)(b[3] + jj * b[5]) * siz_line + (size_t)(b[6] + kk * b[8]) * siz_slice + b[0];
+      for (int ii = 0; ii < b[1]; ii++) row[(size_t)ii * b[2]] = f[n++];
+    }
+  }
+  T->frame++;
 }
 
 void
@@ -215,7 +231,12 @@ drv_rk_curv_col_allstep(
     free(dd_indx);
   }
 
-  /* ---- output taps: every grid point io_recv_keep / io_line_keep will read ------------------------- */
+  /* ---- output taps ---------------------------------------------------------------------------------------
+   * Every grid point io_recv_keep / io_line_keep will read is a record point (sampled on the device after every step); every slice
+   * and snapshot is a streaming tap (cgfd_b200_add_snapshot: frames packed on the device and copied to pinned host memory on an
+   * I/O stream while the steps run). The time loop advances in BLOCKS of steps: while the GPU runs block b+1, the host feeds the
+   * samples and frames of block b, step by step, into the host wavefield level the reference's own io_recv_keep / io_line_keep /
+   * io_slice_nc_put / io_snap_nc_put read (w_end), so those functions run unmodified and the files come out as the reference's. */
   int nrec = iorecv->total_number * CONST_2_NDIM;
   for (int n = 0; n < ioline->num_of_lines; n++) nrec += ioline->line_nr[n];
   int64_t *rec_iptr = (int64_t *)malloc(sizeof(int64_t) * (nrec > 0 ? nrec : 1));
@@ -223,66 +244,106 @@ drv_rk_curv_col_allstep(
   for (int n = 0; n < iorecv->total_number; n++) for (int q = 0; q < CONST_2_NDIM; q++) rec_iptr[ir++] = iorecv->recvone[n].indx1d[q];
   for (int n = 0; n < ioline->num_of_lines; n++) for (int q = 0; q < ioline->line_nr[n]; q++) rec_iptr[ir++] = ioline->recv_iptr[n][q];
   if (nrec > 0) GPU(cgfd_b200_set_record_points(ctx, nrec, rec_iptr, nt_total));
-  float *rec_step = (float *)malloc(sizeof(float) * (size_t)(nrec > 0 ? nrec : 1) * ncmp);
-  float *boxbuf = NULL; size_t boxcap = 0;
-  const int any_slice = ioslice_nc.num_of_slice_x + ioslice_nc.num_of_slice_y + ioslice_nc.num_of_slice_z;
 
-  if (myid == 0 && verbose > 0) fprintf(stdout, "start time loop (GPU) ...\n");
-  struct timespec ts0, ts1;
-  clock_gettime(CLOCK_MONOTONIC, &ts0);
-  for (int it = 0; it < nt_total; it++)
+  int BLK = 32;   /* steps per block */
+  if (getenv("CGFD_DRV_BLOCK")) BLK = atoi(getenv("CGFD_DRV_BLOCK"));
+  if (BLK < 1 || output_all == 1) BLK = 1;
+
+  /* taps: slices x, y, z first, then the snapshots */
+  const int nslice = ioslice_nc.num_of_slice_x + ioslice_nc.num_of_slice_y + ioslice_nc.num_of_slice_z;
+  const int ntap = nslice + iosnap->num_of_snap;
+  tap_t *tap = (tap_t *)calloc(ntap > 0 ? ntap : 1, sizeof(tap_t));
   {
-    float t_cur = it * dt + t0;
-    float t_end = t_cur + dt;
-    if (myid == 0 && verbose > 10) fprintf(stdout, "-> it=%d, t=%f\n", it, t_cur);
-
-    if (src->dd_is_valid == 1) {
-      src_dd_accit_loadstf(src, it, myid);
-      /* a new block was read when the counter wrapped to 0 (forward/src_t.c:1952-2003) */
-      if (src->dd_is_valid == 1 && it > 0 && src->dd_it_here == 0)
-        GPU(cgfd_b200_dd_load_block(ctx, it, src->dd_nt_this_read, src->dd_vi, src->dd_mij));
-    }
-    GPU(cgfd_b200_run(ctx, it, 1));
-
-    /* receivers and lines: device record -> host w_end at the sampled indices -> reference functions */
-    if (nrec > 0) {
-      GPU(cgfd_b200_get_record(ctx, it, 1, rec_step));
-      for (int c = 0; c < ncmp; c++) for (int q = 0; q < nrec; q++) w_end[(size_t)c * siz_icmp + rec_iptr[q]] = rec_step[(size_t)c * nrec + q];
-      io_recv_keep(iorecv, w_end, it, ncmp, siz_icmp);
-      io_line_keep(ioline, w_end, it, ncmp, siz_icmp);
-    }
-    /* slices: planes through the physical range */
-    if (any_slice > 0) {
-      int c2 = (wav->visco_type == CONST_VISCO_GMB) ? 8 : ncmp - 1;
-      for (int c = 0; c <= c2; c++) {
-        for (int n = 0; n < ioslice_nc.num_of_slice_x; n++)
-          fetch_box(ctx, w_end, siz_icmp, gd->siz_iy, gd->siz_iz, c, ioslice->slice_x_indx[n], 1, 1, gd->nj1, gd->nj, 1, gd->nk1, gd->nk, 1, &boxbuf, &boxcap);
-        for (int n = 0; n < ioslice_nc.num_of_slice_y; n++)
-          fetch_box(ctx, w_end, siz_icmp, gd->siz_iy, gd->siz_iz, c, gd->ni1, gd->ni, 1, ioslice->slice_y_indx[n], 1, 1, gd->nk1, gd->nk, 1, &boxbuf, &boxcap);
-        for (int n = 0; n < ioslice_nc.num_of_slice_z; n++)
-          fetch_box(ctx, w_end, siz_icmp, gd->siz_iy, gd->siz_iz, c, gd->ni1, gd->ni, 1, gd->nj1, gd->nj, 1, ioslice->slice_z_indx[n], 1, 1, &boxbuf, &boxcap);
-      }
-      io_slice_nc_put(ioslice, &ioslice_nc, gd, w_end, w_rhs, it, t_end, 0, ncmp - 1, wav->visco_type);
-    }
-    /* snapshots due at this step (condition of io_snap_nc_put, forward/io_funcs.c:1152-1158) */
-    for (int n = 0; n < iosnap->num_of_snap; n++) {
-      int it1 = iosnap->it1[n], dit = iosnap->dit[n];
-      if (!(it >= it1 && (it - it1) / dit <= (nt_total - it1) / dit && (it - it1) % dit == 0)) continue;
+    int t = 0;
+    const int c2s = (wav->visco_type == CONST_VISCO_GMB) ? 8 : ncmp - 1;   /* io_slice_nc_put writes components 0 .. c2s */
+    for (int n = 0; n < ioslice_nc.num_of_slice_x; n++, t++)
+      tap_set(&tap[t], 0, c2s, ioslice->slice_x_indx[n], 1, 1, gd->nj1, gd->nj, 1, gd->nk1, gd->nk, 1, 0, 1);
+    for (int n = 0; n < ioslice_nc.num_of_slice_y; n++, t++)
+      tap_set(&tap[t], 0, c2s, gd->ni1, gd->ni, 1, ioslice->slice_y_indx[n], 1, 1, gd->nk1, gd->nk, 1, 0, 1);
+    for (int n = 0; n < ioslice_nc.num_of_slice_z; n++, t++)
+      tap_set(&tap[t], 0, c2s, gd->ni1, gd->ni, 1, gd->nj1, gd->nj, 1, ioslice->slice_z_indx[n], 1, 1, 0, 1);
+    for (int n = 0; n < iosnap->num_of_snap; n++, t++) {
       int c1 = (iosnap->out_vel[n] == 1) ? 0 : 3;
       int c2 = (iosnap->out_stress[n] == 1 || iosnap->out_strain[n] == 1) ? 8 : 2;
-      for (int c = c1; c <= c2; c++)
-        fetch_box(ctx, w_end, siz_icmp, gd->siz_iy, gd->siz_iz, c, iosnap->i1[n], iosnap->ni[n], iosnap->di[n], iosnap->j1[n], iosnap->nj[n],
-                  iosnap->dj[n], iosnap->k1[n], iosnap->nk[n], iosnap->dk[n], &boxbuf, &boxcap);
+      tap_set(&tap[t], c1, c2, iosnap->i1[n], iosnap->ni[n], iosnap->di[n], iosnap->j1[n], iosnap->nj[n], iosnap->dj[n],
+              iosnap->k1[n], iosnap->nk[n], iosnap->dk[n], iosnap->it1[n], iosnap->dit[n]);
     }
-    io_snap_nc_put(iosnap, &iosnap_nc, gd, md, wav, w_end, w_rhs, nt_total, it, t_end, 1, 1, 1);
-
-    if (output_all == 1) {
-      char ou_file[CONST_MAX_STRLEN];
-      GPU(cgfd_b200_get_wavefield(ctx, w_end));
-      io_build_fname_time(output_dir, "w3d", ".nc", topoid, it, ou_file);
-      io_var3d_export_nc(ou_file, w_end, wav->cmp_pos, wav->cmp_name, wav->ncmp, gd->index_name, gd->nx, gd->ny, gd->nz);
+    for (t = 0; t < ntap; t++) {
+      tap_t *T = &tap[t];
+      T->cap = BLK / T->tinv + 2;   /* frames one block can produce */
+      size_t bytes = (size_t)T->cap * T->ncmp * T->elems * sizeof(float);
+      for (int b = 0; b < 2; b++) { void *q = NULL; GPU(cgfd_b200_host_alloc(bytes, &q)); T->buf[b] = (float *)q; }
+      int cm[32]; for (int c = 0; c < T->ncmp; c++) cm[c] = T->c1 + c;
+      T->id = cgfd_b200_add_snapshot(ctx, T->ncmp, cm, T->box, T->it1, T->tinv, T->cap, T->buf[0]);
+      if (T->id < 0) DIE("cgfd_b200_add_snapshot failed: %s", cgfd_b200_last_error());
     }
   }
+  float *rec_blk[2] = { NULL, NULL };
+  if (nrec > 0) for (int b = 0; b < 2; b++) { void *q = NULL; GPU(cgfd_b200_host_alloc((size_t)BLK * ncmp * nrec * sizeof(float), &q)); rec_blk[b] = (float *)q; }
+
+  if (myid == 0 && verbose > 0) fprintf(stdout, "start time loop (GPU, blocks of %d steps) ...\n", BLK);
+  struct timespec ts0, ts1;
+  clock_gettime(CLOCK_MONOTONIC, &ts0);
+  int it_enq = 0;                 /* next step to enqueue */
+  int blk_first[2] = { 0, 0 }, blk_n[2] = { 0, 0 };
+  int cur = 0;                    /* buffer set of the block being enqueued */
+  /* enqueue the first block, then: wait for block b, enqueue block b+1, post-process block b on the host while b+1 runs */
+  while (it_enq < nt_total || blk_n[1 - cur] > 0)
+  {
+    if (it_enq < nt_total) {
+      int n = nt_total - it_enq < BLK ? nt_total - it_enq : BLK;
+      if (src->dd_is_valid == 1) {
+        /* distributed sources: the reference reloads their time functions from file every dd_nt_per_read steps
+         * (src_dd_accit_loadstf, forward/drv_rk_curv_col.c:179-181); a block never crosses a reload, and the reloaded block goes
+         * to the device (two blocks resident) before the steps that use it are enqueued */
+        src_dd_accit_loadstf(src, it_enq, myid);
+        if (src->dd_is_valid == 1 && it_enq > 0 && src->dd_it_here == 0)
+          GPU(cgfd_b200_dd_load_block(ctx, it_enq, src->dd_nt_this_read, src->dd_vi, src->dd_mij));
+        int m = 1;
+        while (m < n && src->dd_is_valid == 1 && src->dd_it_here + 1 < src->dd_nt_per_read && it_enq + m < src->dd_max_nt) {
+          src_dd_accit_loadstf(src, it_enq + m, myid);   /* only advances the counter: no reload inside this range */
+          m++;
+        }
+        n = m;
+      }
+      for (int t = 0; t < ntap; t++) GPU(cgfd_b200_snapshot_set_output(ctx, tap[t].id, tap[t].buf[cur], tap[t].cap));
+      GPU(cgfd_b200_run_async(ctx, it_enq, n, rec_blk[cur]));
+      blk_first[cur] = it_enq; blk_n[cur] = n;
+      it_enq += n;
+    } else {
+      blk_n[cur] = 0;
+    }
+    /* post-process the PREVIOUS block while the one just enqueued runs (output_all = 1 dumps the whole device state after every
+     * step: no look-ahead then, the block just enqueued is waited for and processed at once) */
+    const int prev = (output_all == 1) ? cur : 1 - cur;
+    if (blk_n[prev] > 0) {
+      GPU(cgfd_b200_wait_block(ctx, blk_first[prev] + blk_n[prev] - 1));
+      for (int t = 0; t < ntap; t++) tap[t].frame = 0;
+      for (int q = 0; q < blk_n[prev]; q++) {
+        const int it = blk_first[prev] + q;
+        const float t_end = it * dt + t0 + dt;
+        if (myid == 0 && verbose > 10) fprintf(stdout, "-> it=%d, t=%f\n", it, it * dt + t0);
+        if (nrec > 0) {
+          const float *r = rec_blk[prev] + (size_t)q * ncmp * nrec;
+          for (int c = 0; c < ncmp; c++) for (int p = 0; p < nrec; p++) w_end[(size_t)c * siz_icmp + rec_iptr[p]] = r[(size_t)c * nrec + p];
+          io_recv_keep(iorecv, w_end, it, ncmp, siz_icmp);
+          io_line_keep(ioline, w_end, it, ncmp, siz_icmp);
+        }
+        for (int t = 0; t < ntap; t++) tap_scatter(&tap[t], prev, it, w_end, siz_icmp, gd->siz_iy, gd->siz_iz);
+        if (nslice > 0) io_slice_nc_put(ioslice, &ioslice_nc, gd, w_end, w_rhs, it, t_end, 0, ncmp - 1, wav->visco_type);
+        io_snap_nc_put(iosnap, &iosnap_nc, gd, md, wav, w_end, w_rhs, nt_total, it, t_end, 1, 1, 1);
+        if (output_all == 1) {
+          char ou_file[CONST_MAX_STRLEN];
+          GPU(cgfd_b200_get_wavefield(ctx, w_end));
+          io_build_fname_time(output_dir, "w3d", ".nc", topoid, it, ou_file);
+          io_var3d_export_nc(ou_file, w_end, wav->cmp_pos, wav->cmp_name, wav->ncmp, gd->index_name, gd->nx, gd->ny, gd->nz);
+        }
+      }
+      blk_n[prev] = 0;
+    }
+    cur = 1 - cur;
+  }
+  GPU(cgfd_b200_sync(ctx));
   clock_gettime(CLOCK_MONOTONIC, &ts1);
   if (myid == 0 && verbose > 0) {
     double sec = (ts1.tv_sec - ts0.tv_sec) + 1e-9 * (ts1.tv_nsec - ts0.tv_nsec);
@@ -301,7 +362,10 @@ drv_rk_curv_col_allstep(
   io_slice_nc_close(&ioslice_nc);
   io_snap_nc_close(&iosnap_nc);
   cgfd_b200_destroy(ctx);
-  free(rec_iptr); free(rec_step); free(boxbuf);
+  free(rec_iptr);
+  for (int t = 0; t < ntap; t++) for (int b = 0; b < 2; b++) cgfd_b200_host_free(tap[t].buf[b]);
+  for (int b = 0; b < 2; b++) cgfd_b200_host_free(rec_blk[b]);
+  free(tap);
   (void)qc_check_nan_num_of_step;
   return;
 }

@@ -253,3 +253,47 @@ def test_metric_from_coords_on_device():
     assert float(np.abs(ref[2]).max()) > 0
     for m in range(10):
         np.testing.assert_array_equal(got[m], ref[m])
+
+
+def test_async_blocks_match_plain_run():
+    """run_async / wait_block / snapshot_set_output (the calls the drop-in driver advances with: block b+1 enqueued before block b is
+    waited for, two host buffers alternating): frames, record samples and the final wavefield equal those of one plain run()."""
+    _need()
+    nt, B = 29, 8
+    prob = util.small_problem(ni=45, nj=28, nk=24, pml_layers=5, nt_total=nt)
+    rec = [prob.iptr(10 + 5 * n, 6 + 3 * n, prob.nk - 1) for n in range(5)]
+    box = (3, prob.ni // 2, 2, 3, prob.nj // 2, 2, prob.nz - 4, 1, 1)
+    G = solver.Solver(prob)
+    G.set_record_points(rec, nt)
+    sid, frames = G.add_snapshot((0, 1, 2), box, max_frames=nt, it1=2, tinv=3)
+    G.run(nt)
+    w_ref, rec_ref, nfr = G.get_wavefield(), G.get_record(0, nt), G.snapshot_frames(sid)
+    G.close()
+    G = solver.Solver(prob)
+    G.set_record_points(rec, nt)
+    bufs = [np.zeros((B // 3 + 2,) + frames.shape[1:], np.float32) for _ in range(2)]
+    recb = [np.zeros((B, 9, len(rec)), np.float32) for _ in range(2)]
+    sid, _ = G.add_snapshot((0, 1, 2), box, max_frames=bufs[0].shape[0], it1=2, tinv=3, out=bufs[0])
+    got_frames, got_rec, blocks = [], [], []
+    it = 0
+    while it < nt or blocks:
+        if it < nt:
+            n = min(B, nt - it)
+            cur = (it // B) % 2
+            G.snapshot_set_output(sid, bufs[cur])
+            G.run_async(n, it0=it, rec_out=recb[cur])
+            blocks.append((it, n, cur))
+            it += n
+        if len(blocks) == 2 or it >= nt:
+            b0, n0, c0 = blocks.pop(0)
+            G.wait_block(b0 + n0 - 1)
+            nf = sum(1 for q in range(b0, b0 + n0) if q >= 2 and (q - 2) % 3 == 0)
+            got_frames.append(bufs[c0][:nf].copy())
+            got_rec.append(recb[c0][:n0].copy())
+    G.sync()
+    w = G.get_wavefield()
+    G.close()
+    np.testing.assert_array_equal(w, w_ref)
+    np.testing.assert_array_equal(np.concatenate(got_rec), rec_ref)
+    np.testing.assert_array_equal(np.concatenate(got_frames), frames[:nfr])
+    assert nfr == 9 and float(np.abs(frames).max()) > 0
