@@ -59,6 +59,12 @@ template <int MED> struct Lay {   // the media tiles come last: their number dep
   static constexpr int BY_SMEM = 233472 / (SMEM_BYTES + 1024);
   static constexpr int BY_REGS = (MED == MED_VIS) ? 1 : 65536 / (TILE_X * TILE_Y * 128);   // 128 registers per thread (visco: one block)
   static constexpr int BLOCKS = BY_SMEM < BY_REGS ? (BY_SMEM < 1 ? 1 : BY_SMEM) : BY_REGS;
+  // one resident block only: two thread groups per tile (stress half / velocity half of the RHS), 512 threads
+#ifndef CGFD_NO_SPLIT
+  static constexpr bool SPLIT = (BLOCKS == 1);
+#else
+  static constexpr bool SPLIT = false;
+#endif
 };
 
 template <int KIND, int MED, bool GZ> __device__ __forceinline__ constexpr uint32_t stage_tx_bytes()
@@ -143,26 +149,38 @@ __device__ __forceinline__ void tma_issue(const StageArgs &P, const TmaMaps &M, 
 // offsets {-3..1}, downwards for {-1..3}), so that three of its neighbours are planes already visited and only one
 // lies ahead: q0,q1,q2 = planes k-3d, k-2d, k-d (d = march direction), q3 = plane k, q4 receives plane k+d, which was
 // requested one iteration earlier (qn) -- at the same time as the TMA of that plane, so it is one DRAM read.
-template <int DX, int DY, int DZ, int KIND, int MED, bool GZ, bool PML>
+//
+// PART: which half of the RHS this thread forms. 0 = both (one thread per column: media with two resident blocks per SM);
+// 1 = the stress half (velocity derivatives -> Hooke -> PML part 0 -> attenuation -> RK update of the six stress components),
+// 2 = the velocity half (stress derivatives -> momentum -> PML part 1 -> RK update of the three velocity components).
+// The halves share nothing but the read-only tiles of the ring slot and write disjoint components, so media whose shared-memory
+// footprint leaves room for ONE block per SM (general anisotropic: 22 media tiles; visco-elastic: the staged memory variables) run
+// blocks of two thread groups on the same tile -- 16 warps per SM instead of 8, each with a zeta queue of its own 3 / 6 components.
+template <int PART> struct Part {
+  static constexpr int QB = (PART == 2) ? 3 : 0;                          // first component of the zeta queue
+  static constexpr int QN = (PART == 0) ? 9 : (PART == 1) ? 3 : 6;        // components in the queue = components differentiated
+};
+template <int DX, int DY, int DZ, int KIND, int MED, bool GZ, bool PML, int PART>
 __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, const TmaCtx &C, int k, int it, int nplanes,
-                                          const float (&q0)[9], const float (&q1)[9], const float (&q2)[9],
-                                          const float (&q3)[9], float (&q4)[9], float (&qn)[9])
+                                          const float (&q0)[Part<PART>::QN], const float (&q1)[Part<PART>::QN], const float (&q2)[Part<PART>::QN],
+                                          const float (&q3)[Part<PART>::QN], float (&q4)[Part<PART>::QN], float (&qn)[Part<PART>::QN])
 {
   constexpr int YL = Ofs<DY>::left;
   constexpr int FX = Ofs<DX>::first, FY = Ofs<DY>::first;
   constexpr int DIR = DZ ? 1 : -1;
   constexpr int NT = TX * TY;
+  constexpr int QB = Part<PART>::QB, QN = Part<PART>::QN;
   const int s = it % NST;
   const uint32_t parity = (it / NST) & 1;
   const float *cx = c_fd.coef[DX], *cy = c_fd.coef[DY], *cz = c_fd.coef[DZ];
 #pragma unroll
-  for (int c = 0; c < 9; c++) q4[c] = qn[c];
+  for (int c = 0; c < QN; c++) q4[c] = qn[c];
   if (C.inarr && it + 1 < nplanes && !(P.l2mode & 128)) {   // bit 7: DIAGNOSTIC (wrong results): no z-ahead loads
     const float *w = C.qptr + (long)(k + 2 * DIR) * (long)P.siz_slice;
 #pragma unroll
-    for (int c = 0; c < 9; c++) qn[c] = __ldg(w + c * P.siz_vol);
+    for (int c = 0; c < QN; c++) qn[c] = __ldg(w + (QB + c) * P.siz_vol);
   }
-  if (PML && C.active && it + 1 < nplanes) pml_prefetch<KIND>(P, C.i, C.j, k + DIR);
+  if (PML && PART != 2 && C.active && it + 1 < nplanes) pml_prefetch<KIND>(P, C.i, C.j, k + DIR);
   // Graves' attenuation factor of this point (last stage only; requested before the wait below so that it is there in time)
   float qatt = 1.0f;
   if (KIND == KIND_LAST && P.qatt && C.active) qatt = __ldg(P.qatt + (size_t)k * P.siz_slice + C.pij);
@@ -174,48 +192,51 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
     const float *sd = (const float *)(b + OFF_MED) + C.t;
     float *sp = (float *)(b + OFF_PRE) + C.t;   // w_pre in, w_tmp out
     float *se = (float *)(b + OFF_END) + C.t;   // w_end in, w_end out
-    const float(&qz)[9] = q3;   // centre plane of the queue
     Met m;   // tiles in device order (metric_dev_slot)
     m.xix = sm[0 * NT]; m.ety = sm[1 * NT]; m.ztx = sm[2 * NT]; m.zty = sm[3 * NT]; m.ztz = sm[4 * NT];
     if (GZ) { m.xiy = 0.0f; m.xiz = 0.0f; m.etx = 0.0f; m.etz = 0.0f; }
     else { m.xiy = sm[5 * NT]; m.xiz = sm[6 * NT]; m.etx = sm[7 * NT]; m.etz = sm[8 * NT]; }
     Med<MED> md;
-    md.load([&](int n) { return sd[n * NT]; });
+    if (PART == 2) md.load_slw([&](int n) { return sd[n * NT]; });   // the velocity half needs 1/rho only
+    else md.load([&](int n) { return sd[n * NT]; });
     const float slw = md.slw;
     Deriv d;
     float h[9];
-    // ---- stress half: needs the velocity derivatives only
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-      const float *r = sc + c * SY * SXT;
-      d.x[c] = cx[0] * r[FX] + cx[1] * r[FX + 1] + cx[2] * r[FX + 2] + cx[3] * r[FX + 3] + cx[4] * r[FX + 4];
-      d.y[c] = cy[0] * r[FY * SXT] + cy[1] * r[(FY + 1) * SXT] + cy[2] * r[(FY + 2) * SXT] + cy[3] * r[(FY + 3) * SXT] + cy[4] * r[(FY + 4) * SXT];
-      d.z[c] = DZ ? cz[0] * q0[c] + cz[1] * q1[c] + cz[2] * q2[c] + cz[3] * q3[c] + cz[4] * q4[c]
-                  : cz[0] * q4[c] + cz[1] * q3[c] + cz[2] * q2[c] + cz[3] * q1[c] + cz[4] * q0[c];
+    // derivatives of the components this thread differentiates (queue entry c - QB holds component c)
+#define CGFD_DERIV(c)                                                                                                             \
+    {                                                                                                                             \
+      const float *r = sc + (c) * SY * SXT;                                                                                       \
+      d.x[c] = cx[0] * r[FX] + cx[1] * r[FX + 1] + cx[2] * r[FX + 2] + cx[3] * r[FX + 3] + cx[4] * r[FX + 4];                     \
+      d.y[c] = cy[0] * r[FY * SXT] + cy[1] * r[(FY + 1) * SXT] + cy[2] * r[(FY + 2) * SXT] + cy[3] * r[(FY + 3) * SXT] + cy[4] * r[(FY + 4) * SXT]; \
+      d.z[c] = DZ ? cz[0] * q0[(c) - QB] + cz[1] * q1[(c) - QB] + cz[2] * q2[(c) - QB] + cz[3] * q3[(c) - QB] + cz[4] * q4[(c) - QB]  \
+                  : cz[0] * q4[(c) - QB] + cz[1] * q3[(c) - QB] + cz[2] * q2[(c) - QB] + cz[3] * q1[(c) - QB] + cz[4] * q0[(c) - QB]; \
     }
-    hooke<MED, GZ>(d, m, md, h);
-    if (PML) pml_all<KIND, 0, MED>(P, C.i, C.j, k, d, m, md, h);
-    if constexpr (MED == MED_VIS) {
-      if (C.nmx > 0)
-        atten_smem<KIND>((const float *)(b + Lay<MED>::OFF_JC) + C.t, (float *)(b + Lay<MED>::OFF_JP) + C.t, (float *)(b + Lay<MED>::OFF_JE) + C.t,
-                         (const float *)(b + Lay<MED>::OFF_Y) + C.t, NT, C.nmx, P.wl, md.lam, md.mu, h, P.a, P.b, P.c);
-      else atten_update<KIND>(P, (size_t)k * P.siz_slice + C.pij, md.lam, md.mu, h);
+    if (PART != 2) {
+      // ---- stress half: needs the velocity derivatives only
+#pragma unroll
+      for (int c = 0; c < 3; c++) CGFD_DERIV(c)
+      hooke<MED, GZ>(d, m, md, h);
+      if (PML) pml_all<KIND, 0, MED>(P, C.i, C.j, k, d, m, md, h);
+      if constexpr (MED == MED_VIS) {
+        if (C.nmx > 0)
+          atten_smem<KIND>((const float *)(b + Lay<MED>::OFF_JC) + C.t, (float *)(b + Lay<MED>::OFF_JP) + C.t, (float *)(b + Lay<MED>::OFF_JE) + C.t,
+                           (const float *)(b + Lay<MED>::OFF_Y) + C.t, NT, C.nmx, P.wl, md.lam, md.mu, h, P.a, P.b, P.c);
+        else atten_update<KIND>(P, (size_t)k * P.siz_slice + C.pij, md.lam, md.mu, h);
+      }
+      // the centre value of a stress component: in the queue of a thread that differentiates it, else in the halo tile
+#pragma unroll
+      for (int c = 3; c < 9; c++) rk_smem<KIND>(sp + c * NT, se + c * NT, PART == 0 ? q3[c - QB] : sc[c * SY * SXT], h[c], P.a, P.b, P.c, qatt);
     }
+    if (PART != 1) {
+      // ---- velocity half: needs the stress derivatives only
 #pragma unroll
-    for (int c = 3; c < 9; c++) rk_smem<KIND>(sp + c * NT, se + c * NT, qz[c], h[c], P.a, P.b, P.c, qatt);
-    // ---- velocity half: needs the stress derivatives only
+      for (int c = 3; c < 9; c++) CGFD_DERIV(c)
+      if (GZ) momentum_gz(d, m, slw, h); else momentum(d, m, slw, h);
+      if (PML) pml_all<KIND, 1, MED>(P, C.i, C.j, k, d, m, md, h);
 #pragma unroll
-    for (int c = 3; c < 9; c++) {
-      const float *r = sc + c * SY * SXT;
-      d.x[c] = cx[0] * r[FX] + cx[1] * r[FX + 1] + cx[2] * r[FX + 2] + cx[3] * r[FX + 3] + cx[4] * r[FX + 4];
-      d.y[c] = cy[0] * r[FY * SXT] + cy[1] * r[(FY + 1) * SXT] + cy[2] * r[(FY + 2) * SXT] + cy[3] * r[(FY + 3) * SXT] + cy[4] * r[(FY + 4) * SXT];
-      d.z[c] = DZ ? cz[0] * q0[c] + cz[1] * q1[c] + cz[2] * q2[c] + cz[3] * q3[c] + cz[4] * q4[c]
-                  : cz[0] * q4[c] + cz[1] * q3[c] + cz[2] * q2[c] + cz[3] * q1[c] + cz[4] * q0[c];
+      for (int c = 0; c < 3; c++) rk_smem<KIND>(sp + c * NT, se + c * NT, PART == 0 ? q3[c - QB] : sc[c * SY * SXT], h[c], P.a, P.b, P.c, qatt);
     }
-    if (GZ) momentum_gz(d, m, slw, h); else momentum(d, m, slw, h);
-    if (PML) pml_all<KIND, 1, MED>(P, C.i, C.j, k, d, m, md, h);
-#pragma unroll
-    for (int c = 0; c < 3; c++) rk_smem<KIND>(sp + c * NT, se + c * NT, qz[c], h[c], P.a, P.b, P.c, qatt);
+#undef CGFD_DERIV
     fence_proxy_async_smem();   // the results written above are read by the TMA store below
   } else {
     // Columns / rows of the tile beyond the physical range. The TMA store clips at the tensor extent, but in units of 16 bytes:
@@ -223,22 +244,25 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
     // written). Ghost values of the result must be zero here (physical face) or are overwritten by the halo exchange that
     // follows (inter-rank face), so these threads clear their tile entries instead of leaving stale shared memory in them.
     float *sp = (float *)(b + OFF_PRE) + C.t, *se = (float *)(b + OFF_END) + C.t;
+    constexpr int CB = (PART == 1) ? 3 : 0, CE = (PART == 2) ? 3 : 9;   // the components this thread's half writes
 #pragma unroll
-    for (int c = 0; c < 9; c++) {
+    for (int c = CB; c < CE; c++) {
       if (KIND != KIND_LAST) sp[c * NT] = 0.0f;
       if (KIND == KIND_MID || KIND == KIND_LAST) se[c * NT] = 0.0f;
     }
     if constexpr (MED == MED_VIS) {
-      float *jp = (float *)(b + Lay<MED>::OFF_JP) + C.t, *je = (float *)(b + Lay<MED>::OFF_JE) + C.t;
-      for (int c = 0; c < 6 * C.nmx; c++) {
-        if (KIND != KIND_LAST) jp[c * NT] = 0.0f;
-        if (KIND == KIND_MID || KIND == KIND_LAST) je[c * NT] = 0.0f;
+      if (PART != 2) {
+        float *jp = (float *)(b + Lay<MED>::OFF_JP) + C.t, *je = (float *)(b + Lay<MED>::OFF_JE) + C.t;
+        for (int c = 0; c < 6 * C.nmx; c++) {
+          if (KIND != KIND_LAST) jp[c * NT] = 0.0f;
+          if (KIND == KIND_MID || KIND == KIND_LAST) je[c * NT] = 0.0f;
+        }
       }
     }
     fence_proxy_async_smem();
   }
   __syncthreads();   // every thread is done with ring slot s; its PRE / END tiles now hold w_tmp / w_end of this plane
-  if (C.t == 0) {
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
     const int tx0 = C.i0 - P.ni1, ty0 = C.j0 - P.nj1;
     const bool refill = it + NST < nplanes;
     if (refill) tma_issue_a<DX, DY, KIND, MED, GZ>(P, M, C, k + NST * DIR, s);   // most of the next plane's bytes: requested at once
@@ -262,14 +286,44 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
   }
 }
 
+// the march of one thread (group) through the planes of its z chunk
+template <int DX, int DY, int DZ, int KIND, int MED, bool GZ, int PART>
+__device__ __forceinline__ void march(const StageArgs &P, const TmaMaps &M, const TmaCtx &C, int kf, int nplanes, bool pml_xy, int zk1, int zk2)
+{
+  constexpr int DIR = DZ ? 1 : -1;
+  constexpr int QB = Part<PART>::QB, QN = Part<PART>::QN;
+  float q0[QN], q1[QN], q2[QN], q3[QN], q4[QN], qn[QN];
+#pragma unroll
+  for (int c = 0; c < QN; c++) { q0[c] = q1[c] = q2[c] = q3[c] = q4[c] = qn[c] = 0.0f; }
+  if (C.inarr && !(P.l2mode & 256)) {   // bit 8: DIAGNOSTIC (wrong results): no queue priming
+    const long sd = (long)DIR * (long)P.siz_slice;
+#pragma unroll
+    for (int c = 0; c < QN; c++) {
+      const float *w = P.cur + (QB + c) * P.siz_vol + (size_t)kf * P.siz_slice + C.pij;
+      q0[c] = __ldg(w - 3 * sd); q1[c] = __ldg(w - 2 * sd); q2[c] = __ldg(w - sd); q3[c] = __ldg(w);
+      qn[c] = __ldg(w + sd);
+    }
+  }
+  for (int it = 0; it < nplanes; it++) {
+    const int k = kf + it * DIR;
+    if (pml_xy || k <= zk1 || k >= zk2 || (P.l2mode & 4)) tma_plane<DX, DY, DZ, KIND, MED, GZ, true, PART>(P, M, C, k, it, nplanes, q0, q1, q2, q3, q4, qn);
+    else tma_plane<DX, DY, DZ, KIND, MED, GZ, false, PART>(P, M, C, k, it, nplanes, q0, q1, q2, q3, q4, qn);
+    // rotate the zeta queue (register moves; unrolling by 5 instead makes the loop body outgrow the
+    // instruction cache and the kernel instruction-fetch bound -- profiles/r1d_summary.txt)
+#pragma unroll
+    for (int c = 0; c < QN; c++) { q0[c] = q1[c]; q1[c] = q2[c]; q2[c] = q3[c]; q3[c] = q4[c]; }
+  }
+}
+
 template <int DX, int DY, int DZ, int KIND, int MED, bool GZ>
-__global__ void __launch_bounds__(TX *TY, Lay<MED>::BLOCKS) k_main_tma(const StageArgs P, const __grid_constant__ TmaMaps M)
+__global__ void __launch_bounds__(TX *TY *(Lay<MED>::SPLIT ? 2 : 1), Lay<MED>::BLOCKS) k_main_tma(const StageArgs P, const __grid_constant__ TmaMaps M)
 {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
+  constexpr bool SPLIT = Lay<MED>::SPLIT;   // two thread groups per tile: threadIdx.y < TY forms the stress half, the rest the velocity half
   TmaCtx C;
   C.ring = smem_raw;
   C.full = (uint64_t *)(C.ring + NST * Lay<MED>::STAGE_BYTES);
-  C.tx = threadIdx.x; C.ty = threadIdx.y; C.t = C.ty * TX + C.tx;
+  C.tx = threadIdx.x; C.ty = SPLIT ? threadIdx.y % TY : threadIdx.y; C.t = C.ty * TX + C.tx;
   // 1-D grid; the optional order table puts the tiles that meet an x / y PML slab first: they take ~3x as long per plane,
   // and started last they would be the tail of the launch
   const int bid = P.order ? __ldg(P.order + blockIdx.x) : (int)blockIdx.x;
@@ -285,8 +339,9 @@ __global__ void __launch_bounds__(TX *TY, Lay<MED>::BLOCKS) k_main_tma(const Sta
   C.nmx = (MED == MED_VIS && P.vis_staged) ? P.nmaxwell : 0;
   C.pol_keep = (P.l2mode & 1) ? l2_policy_evict_last() : l2_policy_evict_normal();
   C.pol_stream = (P.l2mode & 2) ? l2_policy_evict_first() : l2_policy_evict_normal();
+  const bool t0 = threadIdx.x == 0 && threadIdx.y == 0;
 
-  if (C.t == 0) {
+  if (t0) {
 #pragma unroll
     for (int s = 0; s < NST; s++) mbar_init(C.full + s, 1);
     mbar_fence_init();
@@ -296,7 +351,7 @@ __global__ void __launch_bounds__(TX *TY, Lay<MED>::BLOCKS) k_main_tma(const Sta
   const int nplanes = C.k1 - k0 + 1;
   const int kf = DZ ? k0 : C.k1;   // first plane of the march
   C.pf = (P.l2mode >> 5) & 3;
-  if (C.t == 0) {
+  if (t0) {
 #pragma unroll
     for (int s = 0; s < NST; s++)
       if (s < nplanes) tma_issue<DX, DY, KIND, MED, GZ>(P, M, C, kf + s * DIR, s);
@@ -314,28 +369,15 @@ __global__ void __launch_bounds__(TX *TY, Lay<MED>::BLOCKS) k_main_tma(const Sta
   const int zk1 = P.pml[2][0].on ? P.pml[2][0].k2 : -1;            // planes k <= zk1 lie in the bottom slab
   const int zk2 = P.pml[2][1].on ? P.pml[2][1].k1 : (1 << 30);     // planes k >= zk2 lie in the top slab
 
-  float q0[9], q1[9], q2[9], q3[9], q4[9], qn[9];
-#pragma unroll
-  for (int c = 0; c < 9; c++) { q0[c] = q1[c] = q2[c] = q3[c] = q4[c] = qn[c] = 0.0f; }
-  if (C.inarr && !(P.l2mode & 256)) {   // bit 8: DIAGNOSTIC (wrong results): no queue priming
-    const long sd = (long)DIR * (long)P.siz_slice;
-#pragma unroll
-    for (int c = 0; c < 9; c++) {
-      const float *w = P.cur + c * P.siz_vol + (size_t)kf * P.siz_slice + C.pij;
-      q0[c] = __ldg(w - 3 * sd); q1[c] = __ldg(w - 2 * sd); q2[c] = __ldg(w - sd); q3[c] = __ldg(w);
-      qn[c] = __ldg(w + sd);
-    }
+  if constexpr (SPLIT) {
+    // warp-uniform: rows 0 .. TY-1 of the block are the stress group, rows TY .. 2 TY-1 the velocity group; both execute one
+    // __syncthreads per plane (barrier 0 counts arrivals of the whole block whatever the call site)
+    if (threadIdx.y < TY) march<DX, DY, DZ, KIND, MED, GZ, 1>(P, M, C, kf, nplanes, pml_xy, zk1, zk2);
+    else march<DX, DY, DZ, KIND, MED, GZ, 2>(P, M, C, kf, nplanes, pml_xy, zk1, zk2);
+  } else {
+    march<DX, DY, DZ, KIND, MED, GZ, 0>(P, M, C, kf, nplanes, pml_xy, zk1, zk2);
   }
-  for (int it = 0; it < nplanes; it++) {
-    const int k = kf + it * DIR;
-    if (pml_xy || k <= zk1 || k >= zk2 || (P.l2mode & 4)) tma_plane<DX, DY, DZ, KIND, MED, GZ, true>(P, M, C, k, it, nplanes, q0, q1, q2, q3, q4, qn);
-    else tma_plane<DX, DY, DZ, KIND, MED, GZ, false>(P, M, C, k, it, nplanes, q0, q1, q2, q3, q4, qn);
-    // rotate the zeta queue (register moves; unrolling by 5 instead makes the loop body outgrow the
-    // instruction cache and the kernel instruction-fetch bound -- profiles/r1d_summary.txt)
-#pragma unroll
-    for (int c = 0; c < 9; c++) { q0[c] = q1[c]; q1[c] = q2[c]; q2[c] = q3[c]; q3[c] = q4[c]; }
-  }
-  if (C.t == 0) tma_store_wait_all();
+  if (t0) tma_store_wait_all();
   if (P.l2mode & 16) __syncthreads();   // debugging switch: no thread leaves before the stores are complete
 }
 
@@ -547,7 +589,7 @@ static void launch_main_t(const StageArgs &P0, const TmaMaps *maps, int zchunk, 
   P.zchunk = (nk + nzc - 1) / nzc;
   nzc = (nk + P.zchunk - 1) / P.zchunk;
   P.nbx = bx; P.nby = by;
-  dim3 grid(bx * by * nzc), block(TX, TY);
+  dim3 grid(bx * by * nzc), block(TX, Lay<MED>::SPLIT ? 2 * TY : TY);
   if (ev0) cudaEventRecord(ev0, st);
   k_main_tma<DX, DY, DZ, KIND, MED, GZ><<<grid, block, Lay<MED>::SMEM_BYTES, st>>>(P, *maps);
   if (ev1) cudaEventRecord(ev1, st);

@@ -126,6 +126,7 @@ template <> struct Med<MED_ISO> {
   static constexpr int NTILE = 3;
   float lam, mu, lam2mu, slw;
   template <class F> __device__ __forceinline__ void load(F g) { lam = g(0); mu = g(1); slw = g(2); lam2mu = lam + 2.0f * mu; }
+  template <class F> __device__ __forceinline__ void load_slw(F g) { lam = mu = lam2mu = 0.0f; slw = g(2); }
 };
 template <> struct Med<MED_VIS> : Med<MED_ISO> {};
 template <> struct Med<MED_VTI> {
@@ -135,6 +136,7 @@ template <> struct Med<MED_VTI> {
   {
     c11 = g(0); c13 = g(1); c33 = g(2); c55 = g(3); c66 = g(4); slw = g(5); c12 = c11 - 2.0f * c66;
   }
+  template <class F> __device__ __forceinline__ void load_slw(F g) { c11 = c13 = c33 = c55 = c66 = c12 = 0.0f; slw = g(5); }
 };
 template <> struct Med<MED_ANISO> {
   static constexpr int NTILE = 22;
@@ -143,6 +145,12 @@ template <> struct Med<MED_ANISO> {
   {
 #pragma unroll
     for (int n = 0; n < 21; n++) c[n] = g(n);
+    slw = g(21);
+  }
+  template <class F> __device__ __forceinline__ void load_slw(F g)
+  {
+#pragma unroll
+    for (int n = 0; n < 21; n++) c[n] = 0.0f;
     slw = g(21);
   }
 };
@@ -416,14 +424,18 @@ template <int KIND>
 __device__ __forceinline__ void atten_smem(const float *jc, float *jp, float *je, const float *y, int nt, int N, const float *wl,
                                            float lam, float mu, float *h, float a, float b, float c)
 {
+  // strain rate from the stress RHS. The reference divides seven times per point (forward/sv_curv_col_vis_iso.c:299-309); here
+  // the two reciprocals are formed once and multiplied (each quotient differs by <= 1 ulp: far inside the tolerance, and a
+  // float division costs ~10 issue slots in a kernel that is issue bound)
+  const float r2mu = 1.0f / (2.0f * mu), third = 1.0f / 3.0f;
   const float sum_hxyz = (h[TXX] + h[TYY] + h[TZZ]) / (3.0f * lam + 2.0f * mu);
   float EV[6];
-  EV[0] = ((2.0f * h[TXX] - h[TYY] - h[TZZ]) / (2.0f * mu) + sum_hxyz) / 3.0f;
-  EV[1] = ((2.0f * h[TYY] - h[TXX] - h[TZZ]) / (2.0f * mu) + sum_hxyz) / 3.0f;
-  EV[2] = ((2.0f * h[TZZ] - h[TXX] - h[TYY]) / (2.0f * mu) + sum_hxyz) / 3.0f;
-  EV[3] = h[TYZ] / mu * 0.5f;
-  EV[4] = h[TXZ] / mu * 0.5f;
-  EV[5] = h[TXY] / mu * 0.5f;
+  EV[0] = ((2.0f * h[TXX] - h[TYY] - h[TZZ]) * r2mu + sum_hxyz) * third;
+  EV[1] = ((2.0f * h[TYY] - h[TXX] - h[TZZ]) * r2mu + sum_hxyz) * third;
+  EV[2] = ((2.0f * h[TZZ] - h[TXX] - h[TYY]) * r2mu + sum_hxyz) * third;
+  EV[3] = h[TYZ] * r2mu;
+  EV[4] = h[TXZ] * r2mu;
+  EV[5] = h[TXY] * r2mu;
   float sum_tr = 0.0f, sum[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
   for (int n = 0; n < VIS_MAX_STAGED; n++) {
