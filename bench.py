@@ -147,16 +147,16 @@ def build_rank_problem(size, rank, nranks, device=None, medium="iso", global_siz
     sigma = 0.1 * max(gni, gnj) * dh[0]
     sub = (gi0, gj0, gni, gnj, neigh)
     # dt below the CFL bound of the stretched grid (estimate_dt on the full array is slow; checked in tests)
-    if medium != "iso":
-        prob = hs.build_problem(ni, nj, nk, dh=dh, topo="hill", hill=(1000.0, sigma), pml_layers=10, free_top=True, dt=0.008, sub=sub, medium=medium)
-        # free-surface matrices of the other constitutive laws: computed by the library on the device (cgfd_b200_dvh2dvz)
-        from cgfd3d_b200 import solver
-        prob.mats = solver.dvh2dvz(prob)
-    elif device is None:
-        prob = hs.build_problem(ni, nj, nk, dh=dh, topo="hill", hill=(1000.0, sigma), pml_layers=10, free_top=True, dt=0.012, sub=sub)
-    else:
+    dt = 0.012 if medium == "iso" else 0.008
+    if device is not None:
         from cgfd3d_b200 import devsetup
-        prob = devsetup.build_problem(ni, nj, nk, device=device, dh=dh, hill=(1000.0, sigma), pml_layers=10, free_top=True, dt=0.012, sub=sub)
+        prob = devsetup.build_problem(ni, nj, nk, device=device, dh=dh, hill=(1000.0, sigma), pml_layers=10, free_top=True, dt=dt, sub=sub, medium=medium)
+    else:
+        prob = hs.build_problem(ni, nj, nk, dh=dh, topo="hill", hill=(1000.0, sigma), pml_layers=10, free_top=True, dt=dt, sub=sub, medium=medium)
+        if medium != "iso":
+            # free-surface matrices of the other constitutive laws: computed by the library on the device (cgfd_b200_dvh2dvz)
+            from cgfd3d_b200 import solver
+            prob.mats = solver.dvh2dvz(prob, device=int(os.environ.get("LOCAL_RANK", "0")))
     # one explosive moment source under the hill top, on the rank that owns it
     gsi, gsj = gni // 2, gnj // 2
     if gi0 <= gsi < gi0 + ni and gj0 <= gsj < gj0 + nj:
@@ -212,7 +212,7 @@ def run_ours(args):
         t0 = time.time()
         gs = global_size
         big = (size[0] * size[1] * size[2] if gs is None else gs[0] * gs[1] * gs[2] / nranks) > 64e6
-        on_device = big and args.medium == "iso"   # big blocks: set-up arrays built on the GPU (devsetup.py)
+        on_device = big or args.medium != "iso"   # big blocks / many media arrays: set-up arrays built on the GPU (devsetup.py)
         prob = build_rank_problem(size, rank, nranks, device=("cuda:%d" % local) if on_device else None, medium=args.medium, global_size=gs)
         t_host = time.time() - t0
         t0 = time.time()

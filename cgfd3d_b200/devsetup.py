@@ -91,7 +91,8 @@ class _Slab:
 
 
 def build_problem(ni, nj, nk, *, device, dh=(100.0, 100.0, 100.0), hill=(1000.0, 2000.0), vp=3000.0, vs=2000.0, rho=1500.0,
-                  pml_layers=10, pml_faces=((0, 0), (0, 1), (1, 0), (1, 1), (2, 0)), free_top=True, dt=0.012, sub=None):
+                  pml_layers=10, pml_faces=((0, 0), (0, 1), (1, 0), (1, 1), (2, 0)), free_top=True, dt=0.012, sub=None, medium="iso",
+                  nmaxwell=3):
     """Device twin of hostsetup.build_problem(topo='hill'): the returned HostProblem holds torch CUDA tensors in
     .metric / .media (float32, contiguous)."""
     if sub is None:
@@ -121,7 +122,35 @@ def build_problem(ni, nj, nk, *, device, dh=(100.0, 100.0, 100.0), hill=(1000.0,
             continue
         A, B, D = hs.pml_profiles(_Slab(x), _Slab(y), _Slab(z), g, idim, iside, pml_layers)
         prob.pml[(idim, iside)] = (pml_layers, A, B, D)
-    if free_top:
+    if medium != "iso":
+        # the homogeneous test media of hostsetup.set_test_medium (values after forward/md_t.c:501-595, 912-952) as device fills
+        slw = float(np.float32(1.0 / rho))
+        def fill(v):
+            return torch.full(shape, float(np.float32(v)), dtype=torch.float32, device=dev)
+        if medium == "vti":
+            prob.medium_type = abi.MEDIUM_ELASTIC_VTI
+            prob.media = [fill(v) for v in (25.2e9, 10.962e9, 18.0e9, 5.12e9, 7.168e9)] + [fill(slw)]
+        elif medium == "aniso":
+            prob.medium_type = abi.MEDIUM_ELASTIC_ANISO
+            c11, c13, c33, c55, c66 = 25.2e9, 10.962e9, 18.0e9, 5.12e9, 7.168e9
+            c12, e = c11 - 2 * c66, 0.15e9
+            C = [c11, c12, c13, e, -e, 0.5 * e, c11, c13, -0.5 * e, e, 0.7 * e, c33, 0.3 * e, -0.6 * e, e, c55, 0.4 * e, -0.2 * e, c55, 0.8 * e, c66]
+            prob.media = [fill(v) for v in C] + [fill(slw)]
+        elif medium == "visco":
+            prob.medium_type = abi.MEDIUM_VISCOELASTIC_ISO
+            prob.nmaxwell = nmaxwell
+            prob.media = prob.media[:2] + [fill(slw)] + [fill(0.03 + 0.01 * n) for n in range(nmaxwell)] + [fill(0.05 + 0.01 * n) for n in range(nmaxwell)]
+            import math
+            prob.visco_wl = tuple(float(np.float32(2.0 * math.pi * 10 ** (-1.0 + 2.0 * n / max(nmaxwell - 1, 1)))) for n in range(nmaxwell))
+        else:
+            raise ValueError(medium)
+        if free_top:
+            # free-surface matrices by the library itself (cgfd_b200_dvh2dvz takes the device arrays as they are)
+            from . import solver
+            prob.coords = (x, y, z)
+            prob.mats = solver.dvh2dvz(prob, device=dev.index or 0)
+            prob.coords = None
+    elif free_top:
         k = g["nk2"]
         # the free-surface matrices need the k = nk2 plane only
         met2 = [None] + [m[k:k + 1].cpu().numpy() for m in metric[1:]]

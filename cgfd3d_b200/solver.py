@@ -294,8 +294,8 @@ def dvh2dvz(prob, device=0):
     null = abi.fptr()
     vis = prob.medium_type == abi.MEDIUM_VISCOELASTIC_ISO
     if vis:
-        x, y, z = (np.ascontiguousarray(a, np.float32) for a in prob.coords)
-        xyz = (_f(x), _f(y), _f(z))
+        keep = [a if hasattr(a, "data_ptr") else np.ascontiguousarray(a, np.float32) for a in prob.coords]   # torch (device) or numpy
+        xyz = tuple(abi.as_f(a) for a in keep)
     else:
         xyz = (null, null, null)
     ii = (C.c_int * len(hostsetup.FDC_INDX))(*hostsetup.FDC_INDX)
