@@ -261,7 +261,11 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
     }
     fence_proxy_async_smem();
   }
-  __syncthreads();   // every thread is done with ring slot s; its PRE / END tiles now hold w_tmp / w_end of this plane
+  // every thread is done with ring slot s; its PRE / END tiles now hold w_tmp / w_end of this plane. The two thread groups of a
+  // split block reach this point through different instantiations of this function: they meet at a NAMED barrier with an explicit
+  // thread count (the producer / consumer idiom: warps may arrive from different program counters), not at __syncthreads()
+  if (PART == 0) __syncthreads();
+  else asm volatile("barrier.sync 1, %0;" ::"r"(2 * TX * TY) : "memory");
   if (threadIdx.x == 0 && threadIdx.y == 0) {
     const int tx0 = C.i0 - P.ni1, ty0 = C.j0 - P.nj1;
     const bool refill = it + NST < nplanes;
@@ -370,8 +374,8 @@ __global__ void __launch_bounds__(TX *TY *(Lay<MED>::SPLIT ? 2 : 1), Lay<MED>::B
   const int zk2 = P.pml[2][1].on ? P.pml[2][1].k1 : (1 << 30);     // planes k >= zk2 lie in the top slab
 
   if constexpr (SPLIT) {
-    // warp-uniform: rows 0 .. TY-1 of the block are the stress group, rows TY .. 2 TY-1 the velocity group; both execute one
-    // __syncthreads per plane (barrier 0 counts arrivals of the whole block whatever the call site)
+    // warp-uniform: rows 0 .. TY-1 of the block are the stress group, rows TY .. 2 TY-1 the velocity group; they meet once per
+    // plane at named barrier 1 (see tma_plane)
     if (threadIdx.y < TY) march<DX, DY, DZ, KIND, MED, GZ, 1>(P, M, C, kf, nplanes, pml_xy, zk1, zk2);
     else march<DX, DY, DZ, KIND, MED, GZ, 2>(P, M, C, kf, nplanes, pml_xy, zk1, zk2);
   } else {
