@@ -287,7 +287,7 @@ def run_ours(args):
     # ---- the measured workload --------------------------------------------------------------------------------------------
     gs = args.global_size
     size = None if gs else (args.size or ((400, 400, 200) if nranks == 1 else (800, 800, 400)))
-    R = measure(size, gs)
+    R = measure(size, gs, e2e=not args.no_e2e)
 
     # ---- weak-scaling base: the per-GPU block of the multi-GPU runs on ONE GPU, so that the efficiency of an N-GPU line can be
     # recomputed from the lines themselves. N = 1: a second problem in this process. N > 1: rank 0 starts a one-GPU bench.py on its
@@ -331,7 +331,7 @@ def run_ours(args):
         ni, nj, nk = R["block"]
         main_pts = ni * nj * (nk - 4 if R["free_top"] else nk)   # the free-surface kernel owns the top 4 rows
         ach = (bpps / 4.0) * main_pts / kb / 1e9 if main_n else None
-        e0 = R["e2e"][0]
+        e0 = R["e2e"][0] if R["e2e"] else None
         workload = "%s, Gaussian-hill topography (curvilinear), " % WORKLOAD[args.medium]
         if gs is None:
             workload += "%dx%dx%d per GPU%s, " % (tuple(size) + (" (weak scaling)" if nranks > 1 else "",))
@@ -346,7 +346,7 @@ def run_ours(args):
             "config": {"workload": workload, "proc_grid": "%dx%d" % (px, py), "l2": "working set >> 126 MB L2 (no flush needed)",
                        "variant": args.variant or "default", "medium": args.medium,
                        "kernels": "vertically-deformed-grid (4 metric arrays identically zero)" if R["gz"] else "general curvilinear"},
-            "e2e": {"value": round(e0["value"], 4), "unit": "Gpoint-updates/s", "h2d_bytes_per_step": int(e0["h2d"]), "d2h_bytes_per_step": int(e0["d2h"]),
+            "e2e": None if e0 is None else {"value": round(e0["value"], 4), "unit": "Gpoint-updates/s", "h2d_bytes_per_step": int(e0["h2d"]), "d2h_bytes_per_step": int(e0["d2h"]),
                     "steps": e0["steps"],
                     "what": "set_wavefield (H2D) + run(steps) with receiver traces and a surface Vx/Vy/Vz snapshot streamed to pinned host "
                             "memory every step + get_wavefield (D2H); the whole-wavefield transfers are a one-off, so the rate grows with "
@@ -505,6 +505,7 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the N-rank-vs-1-rank value check before timing")
     ap.add_argument("--no-weak-base", action="store_true", help="skip the one-GPU measurement of the weak-scaling block")
     ap.add_argument("--short-e2e", action="store_true", help="only the K-step end-to-end leg (not the 100-step one)")
+    ap.add_argument("--no-e2e", action="store_true", help="side measurements of very large blocks: skip the end-to-end leg (no pinned host copy of the state)")
     ap.add_argument("--variant", default="")
     ap.add_argument("--medium", default="iso", choices=["iso", "vti", "aniso", "visco"],
                     help="constitutive law (default iso = the BASELINE.json metric; the others are side measurements)")
