@@ -83,6 +83,7 @@ struct TmaCtx {
   int tx, ty, t, i, j, i0, j0, k1;
   int pf;              // L2 prefetch distance in planes beyond the ring (0 = off)
   int nmx;             // visco-elastic medium: Maxwell bodies staged by TMA (0 = none: atten_update reads them with plain loads)
+  int fmask;           // x / y PML faces this thread's column lies in (pml_mask_xy)
   bool active, inarr;
   size_t pij;
   const float *qptr;   // w_cur + pij: this thread's column of component 0
@@ -181,6 +182,7 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
     for (int c = 0; c < QN; c++) qn[c] = __ldg(w + (QB + c) * P.siz_vol);
   }
   if (PML && PART != 2 && C.active && it + 1 < nplanes) pml_prefetch<KIND>(P, C.i, C.j, k + DIR);
+  const int pmask = PML ? (C.fmask | pml_mask_z(P, k)) : 0;
   // Graves' attenuation factor of this point (last stage only; requested before the wait below so that it is there in time)
   float qatt = 1.0f;
   if (KIND == KIND_LAST && P.qatt && C.active) qatt = __ldg(P.qatt + (size_t)k * P.siz_slice + C.pij);
@@ -216,7 +218,7 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
 #pragma unroll
       for (int c = 0; c < 3; c++) CGFD_DERIV(c)
       hooke<MED, GZ>(d, m, md, h);
-      if (PML) pml_all<KIND, 0, MED>(P, C.i, C.j, k, d, m, md, h);
+      if (PML) pml_masked<KIND, 0, MED>(P, pmask, C.i, C.j, k, d, m, md, h);
       if constexpr (MED == MED_VIS) {
         if (C.nmx > 0)
           atten_smem<KIND>((const float *)(b + Lay<MED>::OFF_JC) + C.t, (float *)(b + Lay<MED>::OFF_JP) + C.t, (float *)(b + Lay<MED>::OFF_JE) + C.t,
@@ -232,7 +234,7 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
 #pragma unroll
       for (int c = 3; c < 9; c++) CGFD_DERIV(c)
       if (GZ) momentum_gz(d, m, slw, h); else momentum(d, m, slw, h);
-      if (PML) pml_all<KIND, 1, MED>(P, C.i, C.j, k, d, m, md, h);
+      if (PML) pml_masked<KIND, 1, MED>(P, pmask, C.i, C.j, k, d, m, md, h);
 #pragma unroll
       for (int c = 0; c < 3; c++) rk_smem<KIND>(sp + c * NT, se + c * NT, PART == 0 ? q3[c - QB] : sc[c * SY * SXT], h[c], P.a, P.b, P.c, qatt);
     }
@@ -341,6 +343,7 @@ __global__ void __launch_bounds__(TX *TY *(Lay<MED>::SPLIT ? 2 : 1), Lay<MED>::B
   C.pij = (size_t)C.j * P.siz_line + C.i;
   C.qptr = P.cur + C.pij;
   C.nmx = (MED == MED_VIS && P.vis_staged) ? P.nmaxwell : 0;
+  C.fmask = pml_mask_xy(P, C.i, C.j);
   C.pol_keep = (P.l2mode & 1) ? l2_policy_evict_last() : l2_policy_evict_normal();
   C.pol_stream = (P.l2mode & 2) ? l2_policy_evict_first() : l2_policy_evict_normal();
   const bool t0 = threadIdx.x == 0 && threadIdx.y == 0;

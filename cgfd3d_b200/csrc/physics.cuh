@@ -354,26 +354,46 @@ template <int KIND> __device__ __forceinline__ void pml_prefetch(const StageArgs
   }
 }
 
-// all PML faces a point belongs to, in the reference's face order x1,x2,y1,y2,z1,z2
+// all PML faces a point belongs to, in the reference's face order x1,x2,y1,y2,z1,z2.
+// mask = membership bits of the point (bit 2*axis + side), see pml_mask: the interior kernel forms the x / y bits once per thread
+// (they do not change along its z march) and the z bits once per plane (uniform over the block), instead of twelve range tests per plane.
+__device__ __forceinline__ int pml_mask_xy(const StageArgs &P, int i, int j)
+{
+  int m = 0;
+#pragma unroll
+  for (int s = 0; s < 2; s++) {
+    const PmlFaceDev &Fx = P.pml[0][s], &Fy = P.pml[1][s];
+    if (Fx.on && i >= Fx.i1 && i <= Fx.i2) m |= 1 << s;
+    if (Fy.on && j >= Fy.j1 && j <= Fy.j2) m |= 4 << s;
+  }
+  return m;
+}
+__device__ __forceinline__ int pml_mask_z(const StageArgs &P, int k)
+{
+  int m = 0;
+#pragma unroll
+  for (int s = 0; s < 2; s++) {
+    const PmlFaceDev &Fz = P.pml[2][s];
+    if (Fz.on && k >= Fz.k1 && k <= Fz.k2) m |= 16 << s;
+  }
+  return m;
+}
+template <int KIND, int PART, int MED>
+__device__ __forceinline__ void pml_masked(const StageArgs &P, int mask, int i, int j, int k, const Deriv &d, const Met &m, const Med<MED> &M,
+                                           float *h)
+{
+  if (mask & 1) pml_face<0, KIND, PART, MED>(P, P.pml[0][0], i, j, k, d, m, M, h);
+  if (mask & 2) pml_face<0, KIND, PART, MED>(P, P.pml[0][1], i, j, k, d, m, M, h);
+  if (mask & 4) pml_face<1, KIND, PART, MED>(P, P.pml[1][0], i, j, k, d, m, M, h);
+  if (mask & 8) pml_face<1, KIND, PART, MED>(P, P.pml[1][1], i, j, k, d, m, M, h);
+  if (mask & 16) pml_face<2, KIND, PART, MED>(P, P.pml[2][0], i, j, k, d, m, M, h);
+  if (mask & 32) pml_face<2, KIND, PART, MED>(P, P.pml[2][1], i, j, k, d, m, M, h);
+}
 template <int KIND, int PART, int MED>
 __device__ __forceinline__ void pml_all(const StageArgs &P, int i, int j, int k, const Deriv &d, const Met &m, const Med<MED> &M,
                                         float *h)
 {
-#pragma unroll
-  for (int s = 0; s < 2; s++) {
-    const PmlFaceDev &F = P.pml[0][s];
-    if (F.on && i >= F.i1 && i <= F.i2) pml_face<0, KIND, PART, MED>(P, F, i, j, k, d, m, M, h);
-  }
-#pragma unroll
-  for (int s = 0; s < 2; s++) {
-    const PmlFaceDev &F = P.pml[1][s];
-    if (F.on && j >= F.j1 && j <= F.j2) pml_face<1, KIND, PART, MED>(P, F, i, j, k, d, m, M, h);
-  }
-#pragma unroll
-  for (int s = 0; s < 2; s++) {
-    const PmlFaceDev &F = P.pml[2][s];
-    if (F.on && k >= F.k1 && k <= F.k2) pml_face<2, KIND, PART, MED>(P, F, i, j, k, d, m, M, h);
-  }
+  pml_masked<KIND, PART, MED>(P, pml_mask_xy(P, i, j) | pml_mask_z(P, k), i, j, k, d, m, M, h);
 }
 
 // Generalised-Maxwell-body attenuation (sv_curv_col_vis_iso_atten, forward/sv_curv_col_vis_iso.c:250-347) fused with the RK
