@@ -80,6 +80,8 @@ struct StageArgs {
   int l2mode;                   // bit 0: wavefield tiles evict_last, bit 1: touch-once operands and results evict_first;
                                 // bit 2: no PML-free fast path (every block-plane runs the PML copy of the loop body)
                                 // bits 5-6: L2 prefetch distance of the interior kernel, planes beyond the ring (0 = off)
+                                // bits 7, 8: traffic DIAGNOSTICS (results are wrong): no z-ahead loads / no priming of the zeta queue
+                                //            (profiles/r2_experiments.txt, r2a: both kinds of loads hit in L2)
   size_t siz_line, siz_slice, siz_vol;   // padded pitch, pitch*ny, pitch*ny*nz
   const float *cur;             // w_cur  [ncmp][nz][ny][nx]
   const float *pre;             // w_pre
