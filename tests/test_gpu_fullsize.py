@@ -73,3 +73,43 @@ def test_domain_of_dependence_400x400x200(big_problem):
     assert float(np.abs(out[0][2]).max()) > 0 and np.isfinite(out[0]).all()
     for c in range(9):
         np.testing.assert_array_equal(out[0][c], out[1][c])
+
+
+def test_onestage_matches_reference_at_full_size(big_problem):
+    """The bench workload itself against the UNMODIFIED reference: one RHS evaluation of sv_curv_col_el_iso_onestage on the
+    400x400x200 hill problem (random wavefield and PML auxiliary state, moment source active), two operator pairs / stages with
+    opposite zeta directions -- every interior tile, every PML face and the free-surface rows at the size the metric is quoted on.
+    Tolerance as everywhere: max|gpu - ref| <= 2e-5 max|ref| per component."""
+    from oracle import ref_flat
+    from tests import util
+    if not ref_flat.available():
+        pytest.fail("oracle/_ref/libcgfd_ref_flat.so is missing")
+    prob = big_problem
+    hs.make_source(prob, NI // 2, NJ // 2, NK - 1 - 20, nt_total=100, kind="moment", mech=(1e16, 0.6e16, 1.3e16, 0.2e16, -0.4e16, 0.3e16),
+                   fc=2.0, t0=0.1, stf_len=1.0)
+    w, aux = util.random_state(prob, seed=2024)
+    R = ref_flat.RefSolver(prob)
+    G = solver.Solver(prob)
+    for key, a in aux.items():
+        R.set_pml_aux(key[0], key[1], a.ravel())
+        G.set_pml_aux(key[0], key[1], a.ravel())
+    bad = []
+    for (it, ipair, istage) in ((5, 1, 1), (6, 6, 2)):
+        rr = R.onestage(it, ipair, istage, w)
+        rg = G.onestage(it, ipair, istage, w)
+        for c in range(9):
+            e = util.rel_max(rg[c], rr[c])
+            if not e <= 2e-5:
+                bad.append((ipair, istage, util.CMP[c], e))
+        for key in aux:
+            ar = R.get_pml_aux_rhs(*key).reshape(9, -1)
+            ag = G.get_pml_aux_rhs(*key).reshape(9, -1)
+            for c in range(9):
+                e = util.rel_max(ag[c], ar[c])
+                if not e <= 2e-5:
+                    bad.append((ipair, istage, "aux%s.%s" % (key, util.CMP[c]), e))
+        assert float(np.abs(rr[0]).max()) > 0 and float(np.abs(rr[5]).max()) > 0
+        del rr, rg
+    G.close()
+    R.close()
+    assert not bad, bad
