@@ -148,11 +148,18 @@ def build_rank_problem(size, rank, nranks, device=None, medium="iso", global_siz
     sub = (gi0, gj0, gni, gnj, neigh)
     # dt below the CFL bound of the stretched grid (estimate_dt on the full array is slow; checked in tests)
     dt = 0.012 if medium == "iso" else 0.008
+    # cost-attribution side runs (scripts/gpu_r2h.sh): BENCH_DIAG="pml=xz,free=0" keeps only the named PML axes / drops the free
+    # surface; the line then says so in config.diag and is not a bench line of the named workload
+    diag = dict(kv.split("=") for kv in os.environ.get("BENCH_DIAG", "").split(",") if "=" in kv)
+    kw = {}
+    if "pml" in diag:
+        kw["pml_faces"] = tuple((ax, sd) for ax, sd in ((0, 0), (0, 1), (1, 0), (1, 1), (2, 0)) if "xyz"[ax] in diag["pml"])
+    free_top = diag.get("free", "1") != "0"
     if device is not None:
         from cgfd3d_b200 import devsetup
-        prob = devsetup.build_problem(ni, nj, nk, device=device, dh=dh, hill=(1000.0, sigma), pml_layers=10, free_top=True, dt=dt, sub=sub, medium=medium)
+        prob = devsetup.build_problem(ni, nj, nk, device=device, dh=dh, hill=(1000.0, sigma), pml_layers=10, free_top=free_top, dt=dt, sub=sub, medium=medium, **kw)
     else:
-        prob = hs.build_problem(ni, nj, nk, dh=dh, topo="hill", hill=(1000.0, sigma), pml_layers=10, free_top=True, dt=dt, sub=sub, medium=medium)
+        prob = hs.build_problem(ni, nj, nk, dh=dh, topo="hill", hill=(1000.0, sigma), pml_layers=10, free_top=free_top, dt=dt, sub=sub, medium=medium, **kw)
         if medium != "iso":
             # free-surface matrices of the other constitutive laws: computed by the library on the device (cgfd_b200_dvh2dvz)
             from cgfd3d_b200 import solver
@@ -246,7 +253,8 @@ def run_ours(args):
         S.set_profiling(False)
         R = {"value": npts_all * K / (ms_max * 1e-3) / 1e9, "ms_per_step": ms_max / K, "main_ms": main_ms, "main_n": main_n,
              "launches": launches, "clocks": clk.summary() if clk else None, "wall": tw1 - tw0, "npts_all": npts_all,
-             "block": (ni, nj, nk), "free_top": prob.free_top, "gz": S.grid_class(), "t_host": t_host, "t_upload": t_upload,
+             "block": (ni, nj, nk), "free_top": prob.free_top, "top_fused": S.top_fused(), "gz": S.grid_class(),
+             "pml_slab_points": sum(int(np.prod(prob.pml_aux_shape(*f)[1:])) for f in prob.pml), "t_host": t_host, "t_upload": t_upload,
              "on_device": on_device, "e2e": []}
         if e2e:
             # ---- end to end from host buffers: the call sequence of a production run -- initial wavefield from pinned host memory,
@@ -329,8 +337,13 @@ def run_ours(args):
         # algorithmic bytes of one interior-kernel launch = (bytes per point-step / 4 stages) x the points it covers
         bpps = BYTES_PER_POINT_STEP[args.medium]
         ni, nj, nk = R["block"]
-        main_pts = ni * nj * (nk - 4 if R["free_top"] else nk)   # the free-surface kernel owns the top 4 rows
+        # a separate free-surface launch (CGFD_FUSE_TOP=0) owns the top 4 rows; by default they are planes of the interior kernel
+        main_pts = ni * nj * (nk - 4 if (R["free_top"] and not R["top_fused"]) else nk)
         ach = (bpps / 4.0) * main_pts / kb / 1e9 if main_n else None
+        # CFS-PML auxiliary variables: 16 x 9 floats per slab point and step, i.e. 144 B per launch on average.
+        # NOT part of `achieved` / `frac` (the survey's interior formula); reported beside them
+        pml_bytes = 144 * R["pml_slab_points"]
+        ach_pml = ((bpps / 4.0) * main_pts + pml_bytes) / kb / 1e9 if main_n else None
         e0 = R["e2e"][0] if R["e2e"] else None
         workload = "%s, Gaussian-hill topography (curvilinear), " % WORKLOAD[args.medium]
         if gs is None:
@@ -345,6 +358,7 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload, "proc_grid": "%dx%d" % (px, py), "l2": "working set >> 126 MB L2 (no flush needed)",
                        "variant": args.variant or "default", "medium": args.medium,
+                       **({"diag": os.environ["BENCH_DIAG"]} if os.environ.get("BENCH_DIAG") else {}),
                        "kernels": "vertically-deformed-grid (4 metric arrays identically zero)" if R["gz"] else "general curvilinear"},
             "e2e": None if e0 is None else {"value": round(e0["value"], 4), "unit": "Gpoint-updates/s", "h2d_bytes_per_step": int(e0["h2d"]), "d2h_bytes_per_step": int(e0["d2h"]),
                     "steps": e0["steps"],
@@ -358,6 +372,8 @@ def run_ours(args):
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                          "launches_timed": int(main_n), "avg_launch_ms": round(main_ms / max(main_n, 1), 4),
                          "algorithmic_bytes_per_launch": int((bpps / 4.0) * main_pts),
+                         "free_surface_rows": "planes of k_main_tma's top z chunk" if R["top_fused"] else ("separate k_top launch" if R["free_top"] else "none"),
+                         "pml_aux_bytes_per_launch": int(pml_bytes), "frac_incl_pml_aux": None if ach_pml is None else round(ach_pml / peak, 4),
                          "whole_step_frac": round(bpps * (R["npts_all"] / nranks) / (R["ms_per_step"] * 1e-3) / 1e9 / peak, 4)},
             "setup_s": {"arrays": round(R["t_host"], 2), "arrays_built_on": "gpu (torch)" if R["on_device"] else "host (numpy)", "upload": round(R["t_upload"], 2)},
             "wall_s_timed": round(R["wall"], 4), "finite": all(e["finite"] for e in R["e2e"]),

@@ -44,10 +44,10 @@ static int kernels_init(int med)
 #undef CALL
   return rc;
 }
-static void launch_main(int med, const StageArgs &P, const TmaMaps *maps, const int *dir, int kind, int gz, int zchunk, const int rect[4],
+static void launch_main(int med, const StageArgs &P, const TmaMaps *maps, const int *dir, int kind, int gz, int topk, int zchunk, const int rect[4],
                         cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, int *nl)
 {
-#define CALL(M) med_launch_main<M>(P, maps, dir[0], dir[1], dir[2], kind, gz, zchunk, rect, st, e0, e1, nl)
+#define CALL(M) med_launch_main<M>(P, maps, dir[0], dir[1], dir[2], kind, gz, topk, zchunk, rect, st, e0, e1, nl)
   MED_SWITCH(med, CALL)
 #undef CALL
 }
@@ -101,16 +101,23 @@ struct SnapTap {
 struct LaunchPlan {
   int zchunk = 0;
   int *order = nullptr;
+  // fused free surface: rows [ktop0, nk2] are ONE chunk per tile, launched with the kernels that carry the free-surface plane
+  // function (TOPK); the launch above covers [nk1, ktop0 - 1]
+  int ktop0 = 0, zchunk_top = 0;
+  int *order_top = nullptr;
 };
 
 struct cgfd_b200_ctx {
   int device = 0;
   cudaStream_t st = nullptr;        // compute stream
   cudaStream_t st2 = nullptr;       // boundary phase: free-surface rows, tiles next to inter-rank faces, halo exchange
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t st3 = nullptr;       // fused free surface: the top-chunk launch of the interior tiles, beside the launch of the chunks below
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork3 = nullptr, ev_join3 = nullptr;
   int nsm = 148;                    // multiprocessors of the device (launch plan: resident blocks per wave)
   int l2mode = 3;                   // L2 eviction hints of the interior kernel (CGFD_L2MODE)
   int overlap = 1;                  // run the boundary phase concurrently with the interior kernel
+  int top_stream = 1;               // fused free surface: top-chunk launch on its own stream (CGFD_TOP_STREAM=0: same stream, before the rest)
+  int fuse_top = 1;                 // free-surface rows as planes of the interior kernel's top z chunk (CGFD_FUSE_TOP=0: separate k_top launch)
   int toppar = 0;                   // single rank: free-surface kernel on the second stream beside the interior kernel (CGFD_TOPPAR)
   int ntx = 0, nty = 0;             // tiles of the interior kernel along x / y
   int src_nb = 0;                   // source footprint points that belong to the boundary phase (first in the list)
@@ -169,6 +176,7 @@ struct cgfd_b200_ctx {
   int profiling = 0;
   std::vector<cudaEvent_t> ev;   // pairs around the main kernel
   size_t ev_used = 0;
+  FILE *prof_dump = nullptr;
   double main_ms = 0; int64_t main_launches = 0, total_launches = 0;
   cudaEvent_t run0 = nullptr, run1 = nullptr, ev_rec = nullptr; double last_run_ms = 0;
   struct { int it_last = -1; cudaEvent_t done = nullptr; } blk[4];   // completion of the last asynchronous blocks (run_async / wait_block)
@@ -360,7 +368,7 @@ static int setup_sources(cgfd_b200_ctx *c, const cgfd_problem_t *p)
   std::vector<int64_t> pt_iptr; std::vector<int> pt_src, pt_bnd; std::vector<float> pt_wV, pt_wM;
   // does point (i,j,k) belong to the boundary phase of a stage (free-surface rows, tiles next to an inter-rank face)?
   auto bnd = [&](int i, int j, int k) -> int {
-    if (c->free_top && k >= g.nk2 - 3) return 1;
+    if (c->free_top && !c->fuse_top && k >= g.nk2 - 3) return 1;   // k_top runs in the boundary phase; fused rows belong to their tile
     const int tx = (i - g.ni1) / TILE_X, ty = (j - g.nj1) / TILE_Y;
     if (tx < 0 || ty < 0 || tx >= c->ntx || ty >= c->nty) return 1;
     return (c->neigh[0] >= 0 && tx == 0) || (c->neigh[1] >= 0 && tx == c->ntx - 1) || (c->neigh[2] >= 0 && ty == 0) ||
@@ -533,11 +541,16 @@ extern "C" int cgfd_b200_create(const cgfd_problem_t *p, int device, cgfd_b200_c
   if (const char *e = getenv("CGFD_OVERLAP")) c->overlap = atoi(e);
   if (const char *e = getenv("CGFD_L2MODE")) c->l2mode = atoi(e);
   if (const char *e = getenv("CGFD_TOPPAR")) c->toppar = atoi(e);
+  if (const char *e = getenv("CGFD_FUSE_TOP")) c->fuse_top = atoi(e) != 0;
+  if (c->fuse_top) c->toppar = 0;
+  if (const char *e = getenv("CGFD_TOP_STREAM")) c->top_stream = atoi(e) != 0;
+  if (const char *e = getenv("CGFD_PROFILE_DUMP")) c->prof_dump = fopen(e, "a");
   {
     int lo = 0, hi = 0;
     CKD(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     CKD(cudaStreamCreateWithPriority(&c->st, cudaStreamNonBlocking, lo));
     CKD(cudaStreamCreateWithPriority(&c->st2, cudaStreamNonBlocking, hi));
+    CKD(cudaStreamCreateWithPriority(&c->st3, cudaStreamNonBlocking, hi));
     CKD(cudaStreamCreateWithFlags(&c->st_io, cudaStreamNonBlocking));
     for (int b = 0; b < 2; b++) {
       CKD(cudaEventCreateWithFlags(&c->stage_full[b], cudaEventDisableTiming));
@@ -545,6 +558,8 @@ extern "C" int cgfd_b200_create(const cgfd_problem_t *p, int device, cgfd_b200_c
     }
     CKD(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CKD(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    CKD(cudaEventCreateWithFlags(&c->ev_join3, cudaEventDisableTiming));
+    CKD(cudaEventCreateWithFlags(&c->ev_fork3, cudaEventDisableTiming));
   }
   {
     cudaDeviceProp prop;
@@ -682,6 +697,8 @@ extern "C" void cgfd_b200_destroy(cgfd_b200_ctx *c)
   for (auto &b : c->blk) if (b.done) cudaEventDestroy(b.done);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->ev_join3) cudaEventDestroy(c->ev_join3);
+  if (c->ev_fork3) cudaEventDestroy(c->ev_fork3);
   for (SnapTap *t : c->snaps) {
     for (int r = 0; r < SNAP_RING; r++) { cudaFree(t->ring[r]); cudaEventDestroy(t->packed[r]); cudaEventDestroy(t->copied[r]); }
     delete t;
@@ -694,7 +711,9 @@ extern "C" void cgfd_b200_destroy(cgfd_b200_ctx *c)
     if (c->stage_free[b]) cudaEventDestroy(c->stage_free[b]);
   }
   if (c->st_io) cudaStreamDestroy(c->st_io);
+  if (c->prof_dump) fclose(c->prof_dump);
   if (c->st2) cudaStreamDestroy(c->st2);
+  if (c->st3) cudaStreamDestroy(c->st3);
   if (c->st) cudaStreamDestroy(c->st);
   delete c;
 }
@@ -807,7 +826,7 @@ static void fill_args(cgfd_b200_ctx *c, StageArgs &P)
   P.nmaxwell = c->nmaxwell; P.vis_staged = c->vis_staged;
   P.qatt = c->qatt ? c->qatt + c->shift : nullptr;
   for (int n = 0; n < MAX_MAXWELL; n++) P.wl[n] = c->wl[n];
-  P.free_top = c->free_top; P.timg_mode = c->timg_mode; P.l2mode = c->l2mode;
+  P.free_top = c->free_top; P.fuse_top = c->free_top && c->fuse_top; P.timg_mode = c->timg_mode; P.l2mode = c->l2mode;
   P.matVx2Vz = c->mats[0]; P.matVy2Vz = c->mats[1]; P.matF2Vz = c->mats[2]; P.matD = c->mats[3];
   if (c->has_surf) {
     P.TxSrc = c->srcslice; P.TySrc = c->srcslice + c->hslice; P.TzSrc = c->srcslice + 2 * c->hslice;
@@ -847,12 +866,11 @@ static int split_tiles(const cgfd_b200_ctx *c, bool split, int bnd[4][4], int in
 // its z chunks in the direction the kernel marches (dz = 1 upwards, 0 downwards) before the next band starts, so that the
 // 4 planes a chunk re-reads for its zeta queue are the ones the previous chunk of the same tile has just fetched (L2 hits
 // instead of a second DRAM read). lpt = 1: chunk-major order.
-static void compute_plan(const cgfd_grid_t &g, const int pml_r[2][2][3], int free_top, int nsm, int blocks_per_sm, int waves, int minchunk,
-                         int zchunk_explicit, int lpt, int dz, const int rect[4], int *zchunk, std::vector<int> *order)
+static void compute_plan(const cgfd_grid_t &g, const int pml_r[2][2][3], int nk /* rows of the launch */, int nsm, int blocks_per_sm, int waves,
+                         int minchunk, int zchunk_explicit, int lpt, int dz, const int rect[4], int *zchunk, std::vector<int> *order)
 {
   *zchunk = 0; order->clear();
   const int bx = rect[1] - rect[0], by = rect[3] - rect[2];
-  const int nk = (free_top ? g.nk2 - 4 : g.nk2) - g.nk1 + 1;
   if (bx <= 0 || by <= 0 || nk <= 0) return;
   int nzc = 1;
   if (zchunk_explicit > 0) nzc = (nk + zchunk_explicit - 1) / zchunk_explicit;
@@ -894,7 +912,25 @@ static const LaunchPlan *plan_for(cgfd_b200_ctx *c, const int rect[4], int dz)
     pml_r[d][sd][0] = f.on; pml_r[d][sd][1] = f.r[2 * d]; pml_r[d][sd][2] = f.r[2 * d + 1];
   }
   std::vector<int> order;
-  compute_plan(c->g, pml_r, c->free_top, c->nsm, blocks_per_sm(c->med), c->plan_waves, c->plan_minchunk, c->zchunk, c->plan_lpt, dz, rect, &pl.zchunk, &order);
+  const cgfd_grid_t &g = c->g;
+  const bool fused = c->free_top && c->fuse_top;
+  const int nk_all = (c->free_top && !fused ? g.nk2 - 4 : g.nk2) - g.nk1 + 1;
+  const int bps = blocks_per_sm(c->med);
+  compute_plan(g, pml_r, nk_all, c->nsm, bps, c->plan_waves, c->plan_minchunk, c->zchunk, c->plan_lpt, dz, rect, &pl.zchunk, &order);
+  if (fused && pl.zchunk > 0) {
+    // The chunking above covers every row. Its top chunk (with the chunk below when it is shorter than 8 rows) becomes the launch
+    // of the TOPK kernels: one chunk per tile, the tiles that meet an x / y PML slab first. The chunks below keep their size.
+    const int nzc = (nk_all + pl.zchunk - 1) / pl.zchunk;
+    int kt0 = g.nk1 + (nzc - 1) * pl.zchunk;
+    if (g.nk2 - kt0 + 1 < 8 && nzc >= 2) kt0 -= pl.zchunk;
+    pl.ktop0 = kt0; pl.zchunk_top = g.nk2 - kt0 + 1;
+    std::vector<int> otop;
+    int zt = 0;
+    compute_plan(g, pml_r, pl.zchunk_top, c->nsm, bps, c->plan_waves, c->plan_minchunk, pl.zchunk_top, c->plan_lpt, dz, rect, &zt, &otop);
+    if (!otop.empty() && upload(c, &pl.order_top, otop.data(), otop.size())) return nullptr;
+    order.clear();
+    if (kt0 > g.nk1) { int zl = 0; compute_plan(g, pml_r, kt0 - g.nk1, c->nsm, bps, c->plan_waves, c->plan_minchunk, pl.zchunk, c->plan_lpt, dz, rect, &zl, &order); }
+  }
   if (!order.empty() && upload(c, &pl.order, order.data(), order.size())) return nullptr;
   return &(c->plans[key] = pl);
 }
@@ -909,7 +945,7 @@ extern "C" int cgfd_b200_launch_plan(const cgfd_grid_t *g, const int pml_nlay[3]
   }
   cgfd_b200_ctx defaults;
   std::vector<int> ord;
-  compute_plan(*g, pml_r, free_top, 148 /* B200; the context itself asks the device */, blocks_per_sm, defaults.plan_waves, defaults.plan_minchunk, 0, defaults.plan_lpt, dz, rect, zchunk, &ord);
+  compute_plan(*g, pml_r, (free_top ? g->nk2 - 4 : g->nk2) - g->nk1 + 1, 148 /* B200; the context itself asks the device */, blocks_per_sm, defaults.plan_waves, defaults.plan_minchunk, 0, defaults.plan_lpt, dz, rect, zchunk, &ord);
   if (order) for (size_t n = 0; n < ord.size() && (int)n < capacity; n++) order[n] = ord[n];
   return (int)ord.size();
 }
@@ -931,6 +967,27 @@ static int launch_dd(cgfd_b200_ctx *c, int bf, int it, int istage, int first, in
   k_srcdd_inject<<<(count + 127) / 128, 128, 0, s>>>(count, c->dd.sel + first, c->dd.iptr, c->dd.wV, c->dd.rjac,
       c->dd.vi_on ? c->dd.vi[bf] + row * 3 : nullptr, c->dd.mij_on ? c->dd.mij[bf] + row * 6 : nullptr,
       c->lev[itmp] + c->shift, c->lev[iend] + c->shift, a, b, c->V, kind, qatt);
+  return 0;
+}
+
+// The interior kernel on one tile rectangle. With the fused free surface these are two launches: the top chunk of every tile (rows
+// [ktop0, nk2], TOPK kernels, on s_top -- first: its blocks are the long ones) and the chunks below it (on s_lean); they touch
+// disjoint rows and may run side by side. Otherwise one launch of the rows below the free-surface kernel's.
+static int launch_rect(cgfd_b200_ctx *c, StageArgs &P, const TmaMaps *mp, const int *dir, int kind, const int rect[4], cudaStream_t s_lean,
+                       cudaStream_t s_top, int *nl)
+{
+  const LaunchPlan *pl = plan_for(c, rect, dir[2]);
+  if (!pl) return 1;
+  const int nk1 = c->g.nk1, nk2 = c->g.nk2;
+  if (P.fuse_top) {
+    P.kbeg = pl->ktop0; P.kend = nk2; P.order = pl->order_top;
+    launch_main(c->med, P, mp, dir, kind, c->gz, 1, pl->zchunk_top, rect, s_top, nullptr, nullptr, nl);
+    P.kbeg = nk1; P.kend = pl->ktop0 - 1; P.order = pl->order;
+    launch_main(c->med, P, mp, dir, kind, c->gz, 0, pl->zchunk, rect, s_lean, nullptr, nullptr, nl);
+  } else {
+    P.kbeg = nk1; P.kend = P.free_top ? nk2 - 4 : nk2; P.order = pl->order;
+    launch_main(c->med, P, mp, dir, kind, c->gz, 0, pl->zchunk, rect, s_lean, nullptr, nullptr, nl);
+  }
   return 0;
 }
 
@@ -990,12 +1047,8 @@ static int run_stage(cgfd_b200_ctx *c, StageArgs &P, int it, int ipair, int ista
   if (two) { CK(cudaEventRecord(c->ev_fork, c->st)); CK(cudaStreamWaitEvent(c->st2, c->ev_fork, 0)); }
   // ---- boundary phase
   if (!top_late) launch_top(c->med, P, dir, kind, sb, &nl);
-  for (int n = 0; n < nb; n++) {
-    const LaunchPlan *pl = plan_for(c, bnd[n], dir[2]);
-    if (!pl) return 1;
-    P.order = pl->order;
-    launch_main(c->med, P, mp, dir, kind, c->gz, pl->zchunk, bnd[n], sb, nullptr, nullptr, &nl);
-  }
+  for (int n = 0; n < nb; n++)
+    if (launch_rect(c, P, mp, dir, kind, bnd[n], sb, sb, &nl)) return 1;
   // Sources are pushed through the RK axpy AFTER the stage kernel of their point has written it (k_src_inject). The points were
   // classified at create time by the declared neighbours (setup_sources); the tiles are only split when an exchange follows.
   // With a split, the boundary-class points go in here, before the ghosts leave; without one, every point waits for the
@@ -1019,12 +1072,15 @@ static int run_stage(cgfd_b200_ctx *c, StageArgs &P, int it, int ipair, int ista
   if (two && !top_late) CK(cudaEventRecord(c->ev_join, c->st2));
   // ---- interior phase
   {
-    const LaunchPlan *pl = plan_for(c, inner, dir[2]);
-    if (!pl) return 1;
-    P.order = pl->order;
     // top_late: the interior kernel takes the high-priority stream, the free-surface kernel follows on the low-priority one
     cudaStream_t sm = top_late ? c->st2 : c->st;
-    launch_main(c->med, P, mp, dir, kind, c->gz, pl->zchunk, inner, sm, e0, e1, &nl);
+    // fused free surface: the top-chunk launch of the interior tiles runs on a stream of its own beside the chunks below it
+    const bool top3 = P.fuse_top && c->top_stream;
+    if (e0) CK(cudaEventRecord(e0, sm));   // the timed region of the dominant kernel: both of its launches
+    if (top3) { CK(cudaEventRecord(c->ev_fork3, sm)); CK(cudaStreamWaitEvent(c->st3, c->ev_fork3, 0)); }
+    if (launch_rect(c, P, mp, dir, kind, inner, sm, top3 ? c->st3 : sm, &nl)) return 1;
+    if (top3) { CK(cudaEventRecord(c->ev_join3, c->st3)); CK(cudaStreamWaitEvent(sm, c->ev_join3, 0)); }
+    if (e1) CK(cudaEventRecord(e1, sm));
     if (top_late) {
       CK(cudaEventRecord(c->ev_join, c->st2));
       launch_top(c->med, P, dir, kind, c->st, &nl);
@@ -1063,7 +1119,9 @@ static int drain_profile(cgfd_b200_ctx *c)
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, c->ev[n], c->ev[n + 1]));
     c->main_ms += ms; c->main_launches++;
+    if (c->prof_dump) fprintf(c->prof_dump, "%.4f\n", ms);   // CGFD_PROFILE_DUMP: one line per timed launch, in launch order
   }
+  if (c->prof_dump) fflush(c->prof_dump);
   c->ev_used = 0;
   return 0;
 }
@@ -1259,12 +1317,7 @@ extern "C" int cgfd_b200_onestage(cgfd_b200_ctx *c, int it, int ipair, int istag
   const int *dir = c->fd.dir[ipair][istage];
   const int whole[4] = {0, c->ntx, 0, c->nty};
   launch_top(c->med, P, dir, KIND_THIRD, c->st, &nl);
-  {
-    const LaunchPlan *pl = plan_for(c, whole, dir[2]);
-    if (!pl) return 1;
-    P.order = pl->order;
-    launch_main(c->med, P, &maps, dir, KIND_THIRD, c->gz, pl->zchunk, whole, c->st, nullptr, nullptr, &nl);
-  }
+  if (launch_rect(c, P, &maps, dir, KIND_THIRD, whole, c->st, c->st, &nl)) return 1;
   if (c->has_src)
     k_src_inject<<<(c->src.npts + 127) / 128, 128, 0, c->st>>>(c->src, 0, c->src.npts, it, istage, c->lev[iout] + sh, c->lev[izero] + sh, 1.0f, 0.0f, c->V, KIND_THIRD, nullptr);
   CK(cudaGetLastError());
@@ -1428,7 +1481,7 @@ extern "C" int cgfd_b200_dd_set_points(cgfd_b200_ctx *c, int n, const int64_t *i
     for (int q = 0; q < n; q++) {
       const int i = (int)(indx[q] % g.nx), j = (int)((indx[q] / g.nx) % g.ny), k = (int)(indx[q] / ((int64_t)g.nx * g.ny));
       const int tx = (i - g.ni1) / TILE_X, ty = (j - g.nj1) / TILE_Y;
-      const bool bnd = (c->free_top && k >= g.nk2 - 3) || i < g.ni1 || j < g.nj1 || tx >= c->ntx || ty >= c->nty ||
+      const bool bnd = (c->free_top && !c->fuse_top && k >= g.nk2 - 3) || i < g.ni1 || j < g.nj1 || tx >= c->ntx || ty >= c->nty ||
                        (c->neigh[0] >= 0 && tx == 0) || (c->neigh[1] >= 0 && tx == c->ntx - 1) ||
                        (c->neigh[2] >= 0 && ty == 0) || (c->neigh[3] >= 0 && ty == c->nty - 1);
       (bnd ? sel : rest).push_back(q);
@@ -1547,6 +1600,7 @@ extern "C" int cgfd_b200_get_profile(cgfd_b200_ctx *c, double *ms, int64_t *nmai
   return 0;
 }
 extern "C" int cgfd_b200_grid_class(cgfd_b200_ctx *c) { return c->gz; }
+extern "C" int cgfd_b200_top_fused(cgfd_b200_ctx *c) { return c->free_top && c->fuse_top; }
 extern "C" int cgfd_b200_last_run_ms(cgfd_b200_ctx *c, double *ms) { *ms = c->last_run_ms; return 0; }
 extern "C" int cgfd_b200_set_variant(cgfd_b200_ctx *c, const char *name)
 {

@@ -97,6 +97,8 @@ struct StageArgs {
   const float *qatt;            // Graves' attenuation factor exp(-pi f0 dt / Qs) per point, applied to w_end by the last stage; or nullptr
   PmlFaceDev pml[3][2];
   int free_top;
+  int fuse_top;                 // the free-surface rows k >= nk2 - 3 are planes of the interior kernel's top z chunk (a launch of its
+                                // TOPK instantiations; no k_top launch)
   int timg_mode;
   const float *matVx2Vz, *matVy2Vz, *matF2Vz, *matD;
   const float *TxSrc, *TySrc, *TzSrc, *VxSrc, *VySrc, *VzSrc;  // [ny][nx] or nullptr (== 0)
@@ -125,8 +127,9 @@ template <int MED> int med_kernels_init();   // one-time function attributes (dy
 template <int MED> int med_blocks_per_sm();  // resident blocks of the interior kernel per SM
 // interior rows of the tile rectangle rect = {bx0, bx1, by0, by1} (tiles of TILE_X x TILE_Y points from (ni1, nj1))
 // gz = 1: the grid has xi_y = xi_z = eta_x = eta_z == 0 (checked by the caller): kernels that never read those arrays
+// rows [P.kbeg, P.kend]; topk = 1: the launch holds the free-surface rows k >= nk2 - 3 (kernels with the free-surface plane function)
 template <int MED>
-void med_launch_main(const StageArgs &P, const TmaMaps *maps, int dx, int dy, int dz, int kind, int gz, int zchunk, const int rect[4],
+void med_launch_main(const StageArgs &P, const TmaMaps *maps, int dx, int dy, int dz, int kind, int gz, int topk, int zchunk, const int rect[4],
                      cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1, int *nlaunch);
 // the four free-surface rows, whole x-y range (no-op without a free top)
 template <int MED> void med_launch_top(const StageArgs &P, int dx, int dy, int dz, int kind, cudaStream_t st, int *nlaunch);

@@ -16,6 +16,7 @@
 //                stress RHS (*_rhs_vlow_z2, iso.c:451-634, vti.c:407-582, aniso.c:507-707), PML with its
 //                free-surface terms, attenuation, RK update.
 #pragma once
+#include <cstdlib>
 #include "physics.cuh"
 #include "tma.cuh"
 
@@ -146,6 +147,133 @@ __device__ __forceinline__ void tma_issue(const StageArgs &P, const TmaMaps &M, 
   tma_issue_b<DX, DY, KIND, MED>(P, M, C, kk, s);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Free-surface rows inside the interior kernel (StageArgs::fuse_top): the planes k >= nk2 - 3 of the top z chunk run the plane
+// function with TOP = true. Everything a plane needs arrives through the same TMA ring; what differs from a row below:
+//   * stress half: the zeta derivative of the velocity comes from the surface matrices (k = nk2), the 2-point (nk2 - 1) or the
+//     3-point operator (nk2 - 2) -- *_rhs_vlow_z2, forward/sv_curv_col_el_iso.c:503-593 -- all of whose rows sit in the zeta queue;
+//   * velocity half, rows whose zeta stencil reaches the surface: the momentum RHS in conservative form with the anti-symmetric
+//     traction image (sv_curv_col_el_rhs_timg_z2, forward/sv_curv_col_el.c:84-304). The stress values of the fluxes come from
+//     the halo tile (xi, eta) and the zeta queue, the metric of the neighbour points through L1 (40 - 52 loads per point on 2 - 4
+//     of the ~200 planes of a column).
+template <int DZ, int MED, int QN>
+__device__ __forceinline__ void top_vlow(const StageArgs &P, int i, int j, int k, Deriv &d, const float (&q1)[QN], const float (&q2)[QN],
+                                         const float (&q3)[QN])
+{
+  const int nsurf = P.nk2 - k;   // 0 at the surface
+  if (nsurf == 0) {
+    // the surface point-force term exists in the isotropic operator only (iso.c:583-592)
+    constexpr bool FSRC = (MED == MED_ISO || MED == MED_VIS);
+    const size_t p2 = (size_t)j * P.nx + i;
+    const float *A = P.matVx2Vz + p2 * 9, *B = P.matVy2Vz + p2 * 9, *F = P.matF2Vz + p2 * 9;
+    float sx = (FSRC && P.VxSrc) ? __ldg(P.VxSrc + p2) : 0.0f, sy = (FSRC && P.VySrc) ? __ldg(P.VySrc + p2) : 0.0f,
+          sz = (FSRC && P.VzSrc) ? __ldg(P.VzSrc + p2) : 0.0f;
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      float v = __ldg(A + 3 * r + 0) * d.x[VX] + __ldg(A + 3 * r + 1) * d.x[VY] + __ldg(A + 3 * r + 2) * d.x[VZ]
+              + __ldg(B + 3 * r + 0) * d.y[VX] + __ldg(B + 3 * r + 1) * d.y[VY] + __ldg(B + 3 * r + 2) * d.y[VZ];
+      if (FSRC) v += __ldg(F + 3 * r + 0) * sx + __ldg(F + 3 * r + 1) * sy + __ldg(F + 3 * r + 2) * sz;
+      d.z[r] = v;
+    }
+  } else if (nsurf == 1) {
+    // rows (k-1, k) for the backward operator, (k, k+1) for the forward one: q2 is the plane just visited, q3 this plane
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+      d.z[c] = DZ ? c_fd.lay2[1][0] * q2[c] + c_fd.lay2[1][1] * q3[c] : c_fd.lay2[0][0] * q3[c] + c_fd.lay2[0][1] * q2[c];
+  } else if (nsurf == 2) {
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+      d.z[c] = DZ ? c_fd.lay3[1][0] * q1[c] + c_fd.lay3[1][1] * q2[c] + c_fd.lay3[1][2] * q3[c]
+                  : c_fd.lay3[0][0] * q3[c] + c_fd.lay3[0][1] * q2[c] + c_fd.lay3[0][2] * q1[c];
+  }
+}
+
+// sc = this thread's centre entry of component 0 in the halo tile of plane k; the queue entries hold components QB .. QB+QN-1
+// (QB <= TXX); p = offset of the point in a 3-D array
+template <int DX, int DY, int DZ, int QB, int QN>
+__device__ __forceinline__ void timg_smem(const StageArgs &P, size_t p, int i, int j, int k, const float *sc, float slw,
+                                          const float (&q0)[QN], const float (&q1)[QN], const float (&q2)[QN], const float (&q3)[QN],
+                                          const float (&q4)[QN], float *h)
+{
+  constexpr int FX = Ofs<DX>::first, FY = Ofs<DY>::first, FZ = Ofs<DZ>::first;
+  const float *cx = c_fd.coef[DX], *cy = c_fd.coef[DY], *cz = c_fd.coef[DZ];
+  const long L = (long)P.siz_line, S = (long)P.siz_slice;
+  const size_t V = P.siz_vol;
+  const int n_free = P.nk2 - k - FZ;
+  const float jac = __ldg(P.metric[M_JAC] + p);
+  const float slwjac = slw / jac;
+  // component triplets (T1,T2,T3) with flux_n = J*(e_x T1 + e_y T2 + e_z T3)
+  constexpr int T1[3] = {TXX, TXY, TXZ}, T2[3] = {TXY, TYY, TYZ}, T3[3] = {TXZ, TYZ, TZZ};
+  const float *Ts[3] = {P.TxSrc, P.TySrc, P.TzSrc};
+  const size_t p2 = (size_t)j * P.nx + i;
+  // stencil row n of the zeta operator is the plane k + FZ + n: queue entry n when the march runs upwards, 4 - n downwards
+  auto zq = [&](int n, int c) -> float {
+    const int m = DZ ? n : 4 - n;
+    return m == 0 ? q0[c - QB] : m == 1 ? q1[c - QB] : m == 2 ? q2[c - QB] : m == 3 ? q3[c - QB] : q4[c - QB];
+  };
+  // the xi / eta flux derivatives are accumulated term by term (left to right, like M_FD_NOINDX, forward/fd_t.h:33-38);
+  // only the zeta fluxes are kept, because the image terms refer back to them
+  float Dxf[3], Dyf[3], fz[3][5];
+#pragma unroll
+  for (int n = 0; n < 5; n++) {
+    {
+      const size_t pp = p + (FX + n);
+      const float jn = __ldg(P.metric[M_JAC] + pp), ex = __ldg(P.metric[M_XIX] + pp), ey = __ldg(P.metric[M_XIY] + pp),
+                  ez = __ldg(P.metric[M_XIZ] + pp);
+#pragma unroll
+      for (int v = 0; v < 3; v++) {
+        const float f = jn * (ex * sc[T1[v] * SY * SXT + FX + n] + ey * sc[T2[v] * SY * SXT + FX + n] + ez * sc[T3[v] * SY * SXT + FX + n]);
+        if (n == 0) Dxf[v] = cx[0] * f; else Dxf[v] += cx[n] * f;
+      }
+    }
+    {
+      const size_t pp = p + (long)(FY + n) * L;
+      const float jn = __ldg(P.metric[M_JAC] + pp), ex = __ldg(P.metric[M_ETX] + pp), ey = __ldg(P.metric[M_ETY] + pp),
+                  ez = __ldg(P.metric[M_ETZ] + pp);
+#pragma unroll
+      for (int v = 0; v < 3; v++) {
+        const float f = jn * (ex * sc[T1[v] * SY * SXT + (FY + n) * SXT] + ey * sc[T2[v] * SY * SXT + (FY + n) * SXT]
+                            + ez * sc[T3[v] * SY * SXT + (FY + n) * SXT]);
+        if (n == 0) Dyf[v] = cy[0] * f; else Dyf[v] += cy[n] * f;
+      }
+    }
+    if (n < n_free) {
+      const size_t pp = p + (long)(FZ + n) * S;
+      const float jn = __ldg(P.metric[M_JAC] + pp), ex = __ldg(P.metric[M_ZTX] + pp), ey = __ldg(P.metric[M_ZTY] + pp),
+                  ez = __ldg(P.metric[M_ZTZ] + pp);
+#pragma unroll
+      for (int v = 0; v < 3; v++) fz[v][n] = jn * (ex * zq(n, T1[v]) + ey * zq(n, T2[v]) + ez * zq(n, T3[v]));
+    } else {
+#pragma unroll
+      for (int v = 0; v < 3; v++) fz[v][n] = 0.0f;
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < 3; v++) {
+    const float ts = Ts[v] ? __ldg(Ts[v] + p2) : 0.0f;
+#pragma unroll
+    for (int n = 0; n < 5; n++) {
+      if (n == n_free) fz[v][n] = ts;
+      else if (n > n_free) {
+        const int im = 2 * n_free - n;    // mirror index inside the window
+        float below;
+        if (im >= 0) below = (im == 0) ? fz[v][0] : (im == 1) ? fz[v][1] : fz[v][2];   // im <= 2 (n_free = 3, n = 4); no dynamic indexing
+        else if (P.timg_mode == 0) below = 0.0f;
+        else {
+          // image row k + indx[n] - 2(n - n_free) (sv_curv_col_el.c:154-159): below the window, hence outside the queue
+          const size_t pp = p + (long)(FZ + n - 2 * (n - n_free)) * S;
+          const float jn = __ldg(P.metric[M_JAC] + pp), ex = __ldg(P.metric[M_ZTX] + pp), ey = __ldg(P.metric[M_ZTY] + pp),
+                      ez = __ldg(P.metric[M_ZTZ] + pp);
+          below = jn * (ex * __ldg(P.cur + T1[v] * V + pp) + ey * __ldg(P.cur + T2[v] * V + pp) + ez * __ldg(P.cur + T3[v] * V + pp));
+        }
+        fz[v][n] = 2.0f * ts - below;
+      }
+    }
+    float Dz = cz[0] * fz[v][0]; Dz += cz[1] * fz[v][1]; Dz += cz[2] * fz[v][2]; Dz += cz[3] * fz[v][3]; Dz += cz[4] * fz[v][4];
+    h[v] = (Dxf[v] + Dyf[v] + Dz) * slwjac;
+  }
+}
+
 // One plane. The march along z runs TOWARDS the short side of the one-sided zeta operator (upwards for
 // offsets {-3..1}, downwards for {-1..3}), so that three of its neighbours are planes already visited and only one
 // lies ahead: q0,q1,q2 = planes k-3d, k-2d, k-d (d = march direction), q3 = plane k, q4 receives plane k+d, which was
@@ -161,7 +289,7 @@ template <int PART> struct Part {
   static constexpr int QB = (PART == 2) ? 3 : 0;                          // first component of the zeta queue
   static constexpr int QN = (PART == 0) ? 9 : (PART == 1) ? 3 : 6;        // components in the queue = components differentiated
 };
-template <int DX, int DY, int DZ, int KIND, int MED, bool GZ, bool PML, int PART>
+template <int DX, int DY, int DZ, int KIND, int MED, bool GZ, bool PML, int PART, bool TOP = false>
 __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, const TmaCtx &C, int k, int it, int nplanes,
                                           const float (&q0)[Part<PART>::QN], const float (&q1)[Part<PART>::QN], const float (&q2)[Part<PART>::QN],
                                           const float (&q3)[Part<PART>::QN], float (&q4)[Part<PART>::QN], float (&qn)[Part<PART>::QN])
@@ -178,10 +306,15 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
   for (int c = 0; c < QN; c++) q4[c] = qn[c];
   if (C.inarr && it + 1 < nplanes && !(P.l2mode & 128)) {   // bit 7: DIAGNOSTIC (wrong results): no z-ahead loads
     const float *w = C.qptr + (long)(k + 2 * DIR) * (long)P.siz_slice;
+    if (P.l2mode & 2048) {   // touched once by this SM: keep them out of the L1 (which holds the PML aux records, l2mode bit 10)
 #pragma unroll
-    for (int c = 0; c < QN; c++) qn[c] = __ldg(w + (QB + c) * P.siz_vol);
+      for (int c = 0; c < QN; c++) asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(qn[c]) : "l"(w + (QB + c) * P.siz_vol));
+    } else {
+#pragma unroll
+      for (int c = 0; c < QN; c++) qn[c] = __ldg(w + (QB + c) * P.siz_vol);
+    }
   }
-  if (PML && PART != 2 && C.active && it + 1 < nplanes) pml_prefetch<KIND>(P, C.i, C.j, k + DIR);
+  if (PML && PART != 2 && C.active && it + 1 < nplanes && !(P.l2mode & 1024)) pml_prefetch<KIND>(P, C.i, C.j, k + DIR);
   const int pmask = PML ? (C.fmask | pml_mask_z(P, k)) : 0;
   // Graves' attenuation factor of this point (last stage only; requested before the wait below so that it is there in time)
   float qatt = 1.0f;
@@ -217,6 +350,7 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
       // ---- stress half: needs the velocity derivatives only
 #pragma unroll
       for (int c = 0; c < 3; c++) CGFD_DERIV(c)
+      if (TOP) top_vlow<DZ, MED>(P, C.i, C.j, k, d, q1, q2, q3);   // velocity components are queue entries 0..2 of both PART 0 and 1
       hooke<MED, GZ>(d, m, md, h);
       if (PML) pml_masked<KIND, 0, MED>(P, pmask, C.i, C.j, k, d, m, md, h);
       if constexpr (MED == MED_VIS) {
@@ -233,12 +367,18 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
       // ---- velocity half: needs the stress derivatives only
 #pragma unroll
       for (int c = 3; c < 9; c++) CGFD_DERIV(c)
-      if (GZ) momentum_gz(d, m, slw, h); else momentum(d, m, slw, h);
+      // rows whose zeta stencil reaches the free surface (block-uniform): traction image instead of the plain momentum RHS
+      if (TOP && k >= P.nk2 - (Ofs<DZ>::first + 4))
+        timg_smem<DX, DY, DZ, QB, QN>(P, (size_t)k * P.siz_slice + C.pij, C.i, C.j, k, sc, slw, q0, q1, q2, q3, q4, h);
+      else if (GZ) momentum_gz(d, m, slw, h);
+      else momentum(d, m, slw, h);
       if (PML) pml_masked<KIND, 1, MED>(P, pmask, C.i, C.j, k, d, m, md, h);
 #pragma unroll
       for (int c = 0; c < 3; c++) rk_smem<KIND>(sp + c * NT, se + c * NT, PART == 0 ? q3[c - QB] : sc[c * SY * SXT], h[c], P.a, P.b, P.c, qatt);
     }
 #undef CGFD_DERIV
+    // l2mode bit 10: the aux records of the NEXT plane into L1 now (both thread groups of a split block: each asks for its part's lines)
+    if (PML && (P.l2mode & 1024) && it + 1 < nplanes) pml_prefetch_l1<KIND>(P, C.fmask | pml_mask_z(P, k + DIR), C.i, C.j, k + DIR);
     fence_proxy_async_smem();   // the results written above are read by the TMA store below
   } else {
     // Columns / rows of the tile beyond the physical range. The TMA store clips at the tensor extent, but in units of 16 bytes:
@@ -293,8 +433,9 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
 }
 
 // the march of one thread (group) through the planes of its z chunk
-template <int DX, int DY, int DZ, int KIND, int MED, bool GZ, int PART>
-__device__ __forceinline__ void march(const StageArgs &P, const TmaMaps &M, const TmaCtx &C, int kf, int nplanes, bool pml_xy, int zk1, int zk2)
+template <int DX, int DY, int DZ, int KIND, int MED, bool GZ, int PART, bool TOPK>
+__device__ __forceinline__ void march(const StageArgs &P, const TmaMaps &M, const TmaCtx &C, int kf, int nplanes, int ntop, bool pml_xy, int zk1,
+                                      int zk2)
 {
   constexpr int DIR = DZ ? 1 : -1;
   constexpr int QB = Part<PART>::QB, QN = Part<PART>::QN;
@@ -310,18 +451,40 @@ __device__ __forceinline__ void march(const StageArgs &P, const TmaMaps &M, cons
       qn[c] = __ldg(w + sd);
     }
   }
-  for (int it = 0; it < nplanes; it++) {
+  // TOPK kernels (the top z chunk of a free-surface problem): the ntop free-surface planes (k >= nk2 - 3) are the chunk's LAST planes
+  // when the march runs upwards and its FIRST when it runs downwards; DZ is a template parameter, so a kernel holds one copy of
+  // their loop. The kernels of every other chunk (TOPK = false) hold none of this code: the free-surface plane function needs
+  // more registers than the plain one, and inside one kernel its spills reached the hot loop (profiles/r2_experiments.txt, r2j).
+  int it = 0;
+#define CGFD_ROTATE                                                                             \
+  _Pragma("unroll") for (int c = 0; c < QN; c++) { q0[c] = q1[c]; q1[c] = q2[c]; q2[c] = q3[c]; q3[c] = q4[c]; }
+  if (TOPK && !DZ) {
+#pragma unroll 1
+    for (; it < ntop; it++) {
+      tma_plane<DX, DY, DZ, KIND, MED, GZ, true, PART, true>(P, M, C, kf + it * DIR, it, nplanes, q0, q1, q2, q3, q4, qn);
+      CGFD_ROTATE
+    }
+  }
+  const int nlow = (TOPK && DZ) ? nplanes - ntop : nplanes;
+  for (; it < nlow; it++) {
     const int k = kf + it * DIR;
     if (pml_xy || k <= zk1 || k >= zk2 || (P.l2mode & 4)) tma_plane<DX, DY, DZ, KIND, MED, GZ, true, PART>(P, M, C, k, it, nplanes, q0, q1, q2, q3, q4, qn);
     else tma_plane<DX, DY, DZ, KIND, MED, GZ, false, PART>(P, M, C, k, it, nplanes, q0, q1, q2, q3, q4, qn);
     // rotate the zeta queue (register moves; unrolling by 5 instead makes the loop body outgrow the
     // instruction cache and the kernel instruction-fetch bound -- profiles/r1d_summary.txt)
-#pragma unroll
-    for (int c = 0; c < QN; c++) { q0[c] = q1[c]; q1[c] = q2[c]; q2[c] = q3[c]; q3[c] = q4[c]; }
+    CGFD_ROTATE
   }
+  if (TOPK && DZ) {
+#pragma unroll 1
+    for (; it < nplanes; it++) {
+      tma_plane<DX, DY, DZ, KIND, MED, GZ, true, PART, true>(P, M, C, kf + it * DIR, it, nplanes, q0, q1, q2, q3, q4, qn);
+      CGFD_ROTATE
+    }
+  }
+#undef CGFD_ROTATE
 }
 
-template <int DX, int DY, int DZ, int KIND, int MED, bool GZ>
+template <int DX, int DY, int DZ, int KIND, int MED, bool GZ, bool TOPK>
 __global__ void __launch_bounds__(TX *TY *(Lay<MED>::SPLIT ? 2 : 1), Lay<MED>::BLOCKS) k_main_tma(const StageArgs P, const __grid_constant__ TmaMaps M)
 {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -376,13 +539,17 @@ __global__ void __launch_bounds__(TX *TY *(Lay<MED>::SPLIT ? 2 : 1), Lay<MED>::B
   const int zk1 = P.pml[2][0].on ? P.pml[2][0].k2 : -1;            // planes k <= zk1 lie in the bottom slab
   const int zk2 = P.pml[2][1].on ? P.pml[2][1].k1 : (1 << 30);     // planes k >= zk2 lie in the top slab
 
+  // planes of this chunk that are free-surface rows
+  int ntop = 0;
+  if (TOPK) { const int klo = max(k0, P.nk2 - 3); ntop = max(0, C.k1 - klo + 1); }
+
   if constexpr (SPLIT) {
     // warp-uniform: rows 0 .. TY-1 of the block are the stress group, rows TY .. 2 TY-1 the velocity group; they meet once per
     // plane at named barrier 1 (see tma_plane)
-    if (threadIdx.y < TY) march<DX, DY, DZ, KIND, MED, GZ, 1>(P, M, C, kf, nplanes, pml_xy, zk1, zk2);
-    else march<DX, DY, DZ, KIND, MED, GZ, 2>(P, M, C, kf, nplanes, pml_xy, zk1, zk2);
+    if (threadIdx.y < TY) march<DX, DY, DZ, KIND, MED, GZ, 1, TOPK>(P, M, C, kf, nplanes, ntop, pml_xy, zk1, zk2);
+    else march<DX, DY, DZ, KIND, MED, GZ, 2, TOPK>(P, M, C, kf, nplanes, ntop, pml_xy, zk1, zk2);
   } else {
-    march<DX, DY, DZ, KIND, MED, GZ, 0>(P, M, C, kf, nplanes, pml_xy, zk1, zk2);
+    march<DX, DY, DZ, KIND, MED, GZ, 0, TOPK>(P, M, C, kf, nplanes, ntop, pml_xy, zk1, zk2);
   }
   if (t0) tma_store_wait_all();
   if (P.l2mode & 16) __syncthreads();   // debugging switch: no thread leaves before the stores are complete
@@ -574,31 +741,23 @@ __global__ void __launch_bounds__(128, CGFD_TOP_BLOCKS) k_top(const StageArgs P)
 }
 
 // =============================================================================================
-// interior rows of the tile rectangle [bx0,bx1) x [by0,by1) (tiles of TX x TY points counted from (ni1,nj1))
-template <int DX, int DY, int DZ, int KIND, int MED, bool GZ>
+// rows [P.kbeg, P.kend] of the tile rectangle [bx0,bx1) x [by0,by1) (tiles of TX x TY points counted from (ni1,nj1)) in z chunks of
+// `zchunk` rows. TOPK: the launch that holds the free-surface rows (its kernels carry the free-surface plane function).
+template <int DX, int DY, int DZ, int KIND, int MED, bool GZ, bool TOPK>
 static void launch_main_t(const StageArgs &P0, const TmaMaps *maps, int zchunk, const int rect[4], cudaStream_t st,
                           cudaEvent_t ev0, cudaEvent_t ev1, int *nlaunch)
 {
   StageArgs P = P0;
-  const int ktop = P.free_top ? P.nk2 - 3 : P.nk2 + 1;   // first row of the free-surface kernel
-  P.kbeg = P.nk1; P.kend = (P.free_top ? ktop - 1 : P.nk2);
   const int bx = rect[1] - rect[0], by = rect[3] - rect[2];
-  if (P.kend < P.kbeg || bx <= 0 || by <= 0) return;
+  if (P.kend < P.kbeg || bx <= 0 || by <= 0 || zchunk <= 0) return;
   P.bx0 = rect[0]; P.by0 = rect[2];
   const int nk = P.kend - P.kbeg + 1;
-  int nzc;
-  if (zchunk > 0) nzc = (nk + zchunk - 1) / zchunk;
-  else {
-    // z chunks: at least ~8 waves of 148 SMs x 2 resident blocks, chunks no shorter than 24 rows
-    nzc = 1;
-    while (nzc < nk && (long)bx * by * nzc < 148L * Lay<MED>::BLOCKS * 8 && nk / (nzc + 1) >= 24) nzc++;
-  }
-  P.zchunk = (nk + nzc - 1) / nzc;
-  nzc = (nk + P.zchunk - 1) / P.zchunk;
+  P.zchunk = zchunk;
+  const int nzc = (nk + P.zchunk - 1) / P.zchunk;
   P.nbx = bx; P.nby = by;
   dim3 grid(bx * by * nzc), block(TX, Lay<MED>::SPLIT ? 2 * TY : TY);
   if (ev0) cudaEventRecord(ev0, st);
-  k_main_tma<DX, DY, DZ, KIND, MED, GZ><<<grid, block, Lay<MED>::SMEM_BYTES, st>>>(P, *maps);
+  k_main_tma<DX, DY, DZ, KIND, MED, GZ, TOPK><<<grid, block, Lay<MED>::SMEM_BYTES, st>>>(P, *maps);
   if (ev1) cudaEventRecord(ev1, st);
   (*nlaunch)++;
 }
@@ -607,7 +766,7 @@ static void launch_main_t(const StageArgs &P0, const TmaMaps *maps, int zchunk, 
 template <int DX, int DY, int DZ, int KIND, int MED>
 static void launch_top_t(const StageArgs &P0, cudaStream_t st, int *nlaunch)
 {
-  if (!P0.free_top) return;
+  if (!P0.free_top || P0.fuse_top) return;   // fused: the interior kernel's top chunk handles these rows
   StageArgs P = P0;
   const int ni = P.ni2 - P.ni1 + 1, nj = P.nj2 - P.nj1 + 1;
   const int ktop = P.nk2 - 3;
@@ -617,18 +776,22 @@ static void launch_top_t(const StageArgs &P0, cudaStream_t st, int *nlaunch)
   (*nlaunch)++;
 }
 
-template <int DX, int DY, int DZ, int KIND, int MED, bool GZ> static int set_attr_g()
+template <int DX, int DY, int DZ, int KIND, int MED, bool GZ, bool TOPK> static int set_attr_g()
 {
-  cudaError_t e = cudaFuncSetAttribute(k_main_tma<DX, DY, DZ, KIND, MED, GZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<MED>::SMEM_BYTES);
+  cudaError_t e = cudaFuncSetAttribute(k_main_tma<DX, DY, DZ, KIND, MED, GZ, TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<MED>::SMEM_BYTES);
   if (e != cudaSuccess) return 1;
-  e = cudaFuncSetAttribute(k_main_tma<DX, DY, DZ, KIND, MED, GZ>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  // shared-memory carve-out: the smallest configuration that holds the resident blocks (the rest of the 256 KB is L1)
+  int carve = cudaSharedmemCarveoutMaxShared;
+  if (const char *ev = getenv("CGFD_CARVE")) carve = atoi(ev);
+  e = cudaFuncSetAttribute(k_main_tma<DX, DY, DZ, KIND, MED, GZ, TOPK>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
   return e != cudaSuccess;
 }
 template <int DX, int DY, int DZ, int KIND, int MED> static int set_attr_t()
 {
-  return set_attr_g<DX, DY, DZ, KIND, MED, false>() | set_attr_g<DX, DY, DZ, KIND, MED, true>();
+  return set_attr_g<DX, DY, DZ, KIND, MED, false, false>() | set_attr_g<DX, DY, DZ, KIND, MED, true, false>() |
+         set_attr_g<DX, DY, DZ, KIND, MED, false, true>() | set_attr_g<DX, DY, DZ, KIND, MED, true, true>();
 }
-template <int KIND, int MED> static int set_attr_k()
+template <int KIND, int MED> int set_attr_k()
 {
   return set_attr_t<0, 0, 0, KIND, MED>() | set_attr_t<0, 0, 1, KIND, MED>() | set_attr_t<0, 1, 0, KIND, MED>() | set_attr_t<0, 1, 1, KIND, MED>() |
          set_attr_t<1, 0, 0, KIND, MED>() | set_attr_t<1, 0, 1, KIND, MED>() | set_attr_t<1, 1, 0, KIND, MED>() | set_attr_t<1, 1, 1, KIND, MED>();
@@ -647,18 +810,23 @@ template <int MED> int med_kernels_init()
   }
 
 template <int KIND, int MED>
-static void launch_main_k(const StageArgs &P, const TmaMaps *maps, int dx, int dy, int dz, int gz, int zchunk,
-                          const int rect[4], cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, int *n)
+void launch_main_k(const StageArgs &P, const TmaMaps *maps, int dx, int dy, int dz, int gz, int topk, int zchunk,
+                   const int rect[4], cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, int *n)
 {
-#define CALL(a, b, c)                                                                 \
-  do {                                                                                \
-    if (gz) launch_main_t<a, b, c, KIND, MED, true>(P, maps, zchunk, rect, st, e0, e1, n);  \
-    else launch_main_t<a, b, c, KIND, MED, false>(P, maps, zchunk, rect, st, e0, e1, n);    \
+#define CALL(a, b, c)                                                                                \
+  do {                                                                                               \
+    if (topk) {                                                                                      \
+      if (gz) launch_main_t<a, b, c, KIND, MED, true, true>(P, maps, zchunk, rect, st, e0, e1, n);   \
+      else launch_main_t<a, b, c, KIND, MED, false, true>(P, maps, zchunk, rect, st, e0, e1, n);     \
+    } else {                                                                                         \
+      if (gz) launch_main_t<a, b, c, KIND, MED, true, false>(P, maps, zchunk, rect, st, e0, e1, n);  \
+      else launch_main_t<a, b, c, KIND, MED, false, false>(P, maps, zchunk, rect, st, e0, e1, n);    \
+    }                                                                                                \
   } while (0)
   CGFD_DISPATCH_DIR(CALL)
 #undef CALL
 }
-template <int KIND, int MED> static void launch_top_k(const StageArgs &P, int dx, int dy, int dz, cudaStream_t st, int *n)
+template <int KIND, int MED> void launch_top_k(const StageArgs &P, int dx, int dy, int dz, cudaStream_t st, int *n)
 {
 #define CALL(a, b, c) launch_top_t<a, b, c, KIND, MED>(P, st, n)
   CGFD_DISPATCH_DIR(CALL)
@@ -666,13 +834,13 @@ template <int KIND, int MED> static void launch_top_k(const StageArgs &P, int dx
 }
 
 template <int MED>
-void med_launch_main(const StageArgs &P, const TmaMaps *maps, int dx, int dy, int dz, int kind, int gz, int zchunk, const int rect[4],
+void med_launch_main(const StageArgs &P, const TmaMaps *maps, int dx, int dy, int dz, int kind, int gz, int topk, int zchunk, const int rect[4],
                      cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1, int *nlaunch)
 {
-  if (kind == KIND_FIRST) launch_main_k<KIND_FIRST, MED>(P, maps, dx, dy, dz, gz, zchunk, rect, st, ev0, ev1, nlaunch);
-  else if (kind == KIND_MID) launch_main_k<KIND_MID, MED>(P, maps, dx, dy, dz, gz, zchunk, rect, st, ev0, ev1, nlaunch);
-  else if (kind == KIND_THIRD) launch_main_k<KIND_THIRD, MED>(P, maps, dx, dy, dz, gz, zchunk, rect, st, ev0, ev1, nlaunch);
-  else launch_main_k<KIND_LAST, MED>(P, maps, dx, dy, dz, gz, zchunk, rect, st, ev0, ev1, nlaunch);
+  if (kind == KIND_FIRST) launch_main_k<KIND_FIRST, MED>(P, maps, dx, dy, dz, gz, topk, zchunk, rect, st, ev0, ev1, nlaunch);
+  else if (kind == KIND_MID) launch_main_k<KIND_MID, MED>(P, maps, dx, dy, dz, gz, topk, zchunk, rect, st, ev0, ev1, nlaunch);
+  else if (kind == KIND_THIRD) launch_main_k<KIND_THIRD, MED>(P, maps, dx, dy, dz, gz, topk, zchunk, rect, st, ev0, ev1, nlaunch);
+  else launch_main_k<KIND_LAST, MED>(P, maps, dx, dy, dz, gz, topk, zchunk, rect, st, ev0, ev1, nlaunch);
 }
 
 template <int MED> void med_launch_top(const StageArgs &P, int dx, int dy, int dz, int kind, cudaStream_t st, int *nlaunch)
@@ -683,11 +851,24 @@ template <int MED> void med_launch_top(const StageArgs &P, int dx, int dy, int d
   else launch_top_k<KIND_LAST, MED>(P, dx, dy, dz, st, nlaunch);
 }
 
-// one medium per translation unit
+// Translation units: the 64 instantiations of one medium and stage kind (8 operator pairs x general / GZ grid x plane-function
+// copies) are one unit (kernels_kind.cu compiled with -DCGFD_MED=.. -DCGFD_KIND=..); the per-medium units kernels_{iso,..}.cu hold
+// the dispatch over the kinds only. 16 units of similar size build in parallel.
+#define CGFD_INSTANTIATE_KIND(KIND, MED)                                                                               \
+  template int set_attr_k<KIND, MED>();                                                                                 \
+  template void launch_main_k<KIND, MED>(const StageArgs &, const TmaMaps *, int, int, int, int, int, int, const int[4], cudaStream_t, \
+                                         cudaEvent_t, cudaEvent_t, int *);                                              \
+  template void launch_top_k<KIND, MED>(const StageArgs &, int, int, int, cudaStream_t, int *);
+#define CGFD_EXTERN_KIND(KIND, MED)                                                                                    \
+  extern template int set_attr_k<KIND, MED>();                                                                          \
+  extern template void launch_main_k<KIND, MED>(const StageArgs &, const TmaMaps *, int, int, int, int, int, int, const int[4], cudaStream_t, \
+                                                cudaEvent_t, cudaEvent_t, int *);                                       \
+  extern template void launch_top_k<KIND, MED>(const StageArgs &, int, int, int, cudaStream_t, int *);
 #define CGFD_INSTANTIATE_MEDIUM(MED)                                                                                  \
+  CGFD_EXTERN_KIND(KIND_FIRST, MED) CGFD_EXTERN_KIND(KIND_MID, MED) CGFD_EXTERN_KIND(KIND_THIRD, MED) CGFD_EXTERN_KIND(KIND_LAST, MED) \
   template int med_kernels_init<MED>();                                                                                \
   template int med_blocks_per_sm<MED>();                                                                               \
-  template void med_launch_main<MED>(const StageArgs &, const TmaMaps *, int, int, int, int, int, int, const int[4], cudaStream_t, \
+  template void med_launch_main<MED>(const StageArgs &, const TmaMaps *, int, int, int, int, int, int, int, const int[4], cudaStream_t, \
                                      cudaEvent_t, cudaEvent_t, int *);                                                 \
   template void med_launch_top<MED>(const StageArgs &, int, int, int, int, cudaStream_t, int *);
 

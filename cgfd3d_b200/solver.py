@@ -23,7 +23,7 @@ SYMBOLS = [
     "cgfd_b200_pml_aux_size", "cgfd_b200_onestage", "cgfd_b200_get_pml_aux_rhs", "cgfd_b200_run",
     "cgfd_b200_set_record_points", "cgfd_b200_get_record", "cgfd_b200_get_box", "cgfd_b200_get_pg",
     "cgfd_b200_comm_unique_id", "cgfd_b200_comm_init", "cgfd_b200_halo_plan", "cgfd_b200_set_profiling", "cgfd_b200_get_profile",
-    "cgfd_b200_last_run_ms", "cgfd_b200_set_variant", "cgfd_b200_grid_class",
+    "cgfd_b200_last_run_ms", "cgfd_b200_set_variant", "cgfd_b200_grid_class", "cgfd_b200_top_fused",
     "cgfd_b200_add_snapshot", "cgfd_b200_snapshot_frames", "cgfd_b200_dd_set_points", "cgfd_b200_dd_load_block",
     "cgfd_b200_metric_from_coords", "cgfd_b200_launch_plan", "cgfd_b200_dvh2dvz",
     "cgfd_b200_run_async", "cgfd_b200_sync", "cgfd_b200_wait_block", "cgfd_b200_snapshot_set_output", "cgfd_b200_host_alloc", "cgfd_b200_host_free",
@@ -71,6 +71,7 @@ def load_library():
     L.cgfd_b200_last_run_ms.argtypes = [vp, C.POINTER(C.c_double)]
     L.cgfd_b200_set_variant.argtypes = [vp, C.c_char_p]
     L.cgfd_b200_grid_class.argtypes = [vp]
+    L.cgfd_b200_top_fused.argtypes = [vp]
     L.cgfd_b200_add_snapshot.argtypes = [vp, ci, C.POINTER(ci), C.POINTER(ci * 9), ci, ci, ci, fp]
     L.cgfd_b200_snapshot_frames.argtypes = [vp, ci]
     L.cgfd_b200_dd_set_points.argtypes = [vp, ci, C.POINTER(C.c_int64), ci, ci, ci, ci]
@@ -255,6 +256,10 @@ class Solver:
     def grid_class(self) -> int:
         """1: kernels specialised for vertically deformed grids (four metric arrays identically zero) are in use."""
         return int(self.L.cgfd_b200_grid_class(self.h))
+
+    def top_fused(self) -> int:
+        """1: the free-surface rows are planes of the interior kernel (no separate launch)."""
+        return int(self.L.cgfd_b200_top_fused(self.h))
 
     def set_variant(self, name: str):
         self._chk(self.L.cgfd_b200_set_variant(self.h, name.encode()))

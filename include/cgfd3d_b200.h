@@ -273,7 +273,8 @@ void cgfd_b200_host_free(void *p);
  * number of blocks, *zchunk = rows per z chunk, order[b] = (chunk * ntiles_y + tile_y) * ntiles_x + tile_x of the b-th block:
  * tiles that meet an x / y PML slab first (longest job first); within each class bands of one wave of tiles run through their z chunks
  * in the direction of the kernel's march (dz = the zeta direction index of the stage's operator) before the next band starts.
- * -1 on bad arguments. */
+ * free_top != 0: the top four rows are NOT part of the plan (they are left to the separate free-surface launch, CGFD_FUSE_TOP=0);
+ * the default context runs them as planes of the top z chunk, i.e. asks for the plan with free_top = 0. -1 on bad arguments. */
 int  cgfd_b200_launch_plan(const cgfd_grid_t *grid, const int pml_nlay[3][2], int free_top, int blocks_per_sm, int dz, const int rect[4],
                            int *zchunk, int *order, int capacity);
 
@@ -288,6 +289,9 @@ int  cgfd_b200_last_run_ms(cgfd_b200_ctx *ctx, double *ms);
 /* 1 when the context runs the kernels specialised for vertically deformed grids (xi_y = xi_z = eta_x = eta_z == 0 at every
  * physical point, detected at create time; CGFD_GZ=0 in the environment keeps the general kernels), else 0 */
 int  cgfd_b200_grid_class(cgfd_b200_ctx *ctx);
+/* 1 when the free-surface rows (rhs_timg_z2 / rhs_vlow_z2, the top four rows) run as planes of the interior kernel's top z chunk
+ * (the default with a free top), 0 when they are a separate launch (CGFD_FUSE_TOP=0) or the top is not a free surface */
+int  cgfd_b200_top_fused(cgfd_b200_ctx *ctx);
 /* choose a kernel variant by name; NULL/"" = default */
 int  cgfd_b200_set_variant(cgfd_b200_ctx *ctx, const char *name);
 
