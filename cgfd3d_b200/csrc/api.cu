@@ -117,7 +117,8 @@ struct cgfd_b200_ctx {
   int l2mode = 3;                   // L2 eviction hints of the interior kernel (CGFD_L2MODE)
   int overlap = 1;                  // run the boundary phase concurrently with the interior kernel
   int top_stream = 1;               // fused free surface: top-chunk launch on its own stream (CGFD_TOP_STREAM=0: same stream, before the rest)
-  int fuse_top = 1;                 // free-surface rows as planes of the interior kernel's top z chunk (CGFD_FUSE_TOP=0: separate k_top launch)
+  int fuse_top = -1;                // free-surface rows as planes of the top z chunk (TOPK launch of k_main_tma) instead of k_top:
+                                    // the default where it is the faster route (isotropic medium, measured r2l), CGFD_FUSE_TOP=0 / 1
   int toppar = 0;                   // single rank: free-surface kernel on the second stream beside the interior kernel (CGFD_TOPPAR)
   int ntx = 0, nty = 0;             // tiles of the interior kernel along x / y
   int src_nb = 0;                   // source footprint points that belong to the boundary phase (first in the list)
@@ -542,6 +543,7 @@ extern "C" int cgfd_b200_create(const cgfd_problem_t *p, int device, cgfd_b200_c
   if (const char *e = getenv("CGFD_L2MODE")) c->l2mode = atoi(e);
   if (const char *e = getenv("CGFD_TOPPAR")) c->toppar = atoi(e);
   if (const char *e = getenv("CGFD_FUSE_TOP")) c->fuse_top = atoi(e) != 0;
+  if (c->fuse_top < 0) c->fuse_top = (c->med == MED_ISO);
   if (c->fuse_top) c->toppar = 0;
   if (const char *e = getenv("CGFD_TOP_STREAM")) c->top_stream = atoi(e) != 0;
   if (const char *e = getenv("CGFD_PROFILE_DUMP")) c->prof_dump = fopen(e, "a");
@@ -1006,7 +1008,7 @@ static int run_stage(cgfd_b200_ctx *c, StageArgs &P, int it, int ipair, int ista
   P.a = a; P.b = b; P.c = cc;
   TmaMaps maps;
   if (c->have_maps) {
-    maps.cur = c->map_halo[icur]; maps.pre = c->map_cen[ipre]; maps.end = c->map_cen[iend];
+    maps.cur = c->map_halo[icur]; maps.za = c->map_cen[icur]; maps.pre = c->map_cen[ipre]; maps.end = c->map_cen[iend];
     maps.met = c->map_met; maps.met5 = c->map_met5; maps.med = c->map_med;
     maps.out_tmp = c->map_out[itmp]; maps.out_end = c->map_out[iend];
     if (c->vis_staged) {
@@ -1290,7 +1292,7 @@ extern "C" int cgfd_b200_onestage(cgfd_b200_ctx *c, int it, int ipair, int istag
   P.cur = c->lev[icur] + sh; P.pre = c->lev[iz2] + sh; P.tmp = c->lev[iout] + sh; P.end = c->lev[izero] + sh;
   TmaMaps maps;
   if (c->have_maps) {
-    maps.cur = c->map_halo[icur]; maps.pre = c->map_cen[iz2]; maps.end = c->map_cen[izero];
+    maps.cur = c->map_halo[icur]; maps.za = c->map_cen[icur]; maps.pre = c->map_cen[iz2]; maps.end = c->map_cen[izero];
     maps.met = c->map_met; maps.met5 = c->map_met5; maps.med = c->map_med;
     maps.out_tmp = c->map_out[iout]; maps.out_end = c->map_out[izero];
     if (c->vis_staged) {

@@ -111,6 +111,7 @@ struct TmaMaps {
   CUtensorMap met5;  // the same tensor, box (TX, TY, 1, 5): the arrays a vertically deformed grid needs (GZ kernels)
   CUtensorMap med;   // media, box (TX, TY, 1, nmedia)
   CUtensorMap pre;   // w_pre, box (TX, TY, 1, 9)
+  CUtensorMap za;    // w_cur again, box (TX, TY, 1, 9): the centre box of the plane AHEAD of the march (media with ZA tiles)
   CUtensorMap end;   // w_end, box (TX, TY, 1, 9)
   // store maps: the PHYSICAL x-y range only (origin (ni1,nj1), extents ni x nj), so that the parts of a tile that hang
   // over the physical range are clipped by the TMA unit and ghosts are never written

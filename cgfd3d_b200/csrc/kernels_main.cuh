@@ -16,7 +16,6 @@
 //                stress RHS (*_rhs_vlow_z2, iso.c:451-634, vti.c:407-582, aniso.c:507-707), PML with its
 //                free-surface terms, attenuation, RK update.
 #pragma once
-#include <cstdlib>
 #include "physics.cuh"
 #include "tma.cuh"
 
@@ -48,18 +47,32 @@ constexpr int OFF_MET = ((CUR_BYTES + 127) / 128) * 128;
 constexpr int OFF_PRE = OFF_MET + 9 * CEN_BYTES;
 constexpr int OFF_END = OFF_PRE + 9 * CEN_BYTES;
 constexpr int OFF_MED = OFF_END + 9 * CEN_BYTES;
+constexpr int blocks_by_smem(int stage_bytes) { return 233472 / (NST * stage_bytes + 128 /*alignment slack*/ + 64 /*barriers*/ + 1024 /*reserved*/); }
 template <int MED> struct Lay {   // the media tiles come last: their number depends on the medium
   static constexpr int NMT = Med<MED>::NTILE;
   // visco-elastic medium: tiles of the memory variables (cur | pre -> tmp | end, 6 per Maxwell body each) and of Ylam, Ymu
   static constexpr int NJT = (MED == MED_VIS) ? 6 * VIS_MAX_STAGED : 0, NYT = (MED == MED_VIS) ? 2 * VIS_MAX_STAGED : 0;
-  static constexpr int OFF_JC = OFF_MED + NMT * CEN_BYTES, OFF_JP = OFF_JC + NJT * CEN_BYTES, OFF_JE = OFF_JP + NJT * CEN_BYTES,
+  static constexpr int BY_REGS = (MED == MED_VIS) ? 1 : 65536 / (TILE_X * TILE_Y * 128);   // 128 registers per thread (visco: one block)
+  static constexpr int clampb(int by_smem) { return by_smem < BY_REGS ? (by_smem < 1 ? 1 : by_smem) : BY_REGS; }
+  // ZA tiles: the centre box of the NEXT plane of the march (9 components), i.e. the one value per component the one-sided zeta
+  // operator needs from ahead. Staged by TMA with the plane's other operands where that keeps the number of resident blocks
+  // (isotropic: 2 x 112 KB; general anisotropic: 1 block anyway); otherwise (VTI, visco-elastic) each thread fetches its 9 values
+  // with plain loads one plane ahead. With ZA the zeta queue in registers is three planes deep instead of six.
+  static constexpr int BASE_BYTES = OFF_MED + (NMT + 3 * NJT + NYT) * CEN_BYTES;
+#ifndef CGFD_NO_ZA
+  static constexpr bool ZA = blocks_by_smem(BASE_BYTES + 9 * CEN_BYTES) >= 1 && clampb(blocks_by_smem(BASE_BYTES + 9 * CEN_BYTES)) >= clampb(blocks_by_smem(BASE_BYTES));
+#else
+  static constexpr bool ZA = false;
+#endif
+  static constexpr int NZT = ZA ? 9 : 0;
+  static constexpr int OFF_ZA = OFF_MED + NMT * CEN_BYTES;
+  static constexpr int OFF_JC = OFF_ZA + NZT * CEN_BYTES, OFF_JP = OFF_JC + NJT * CEN_BYTES, OFF_JE = OFF_JP + NJT * CEN_BYTES,
                        OFF_Y = OFF_JE + NJT * CEN_BYTES;
   static constexpr int STAGE_BYTES = OFF_Y + NYT * CEN_BYTES;
   static constexpr int SMEM_BYTES = NST * STAGE_BYTES + 128 /*alignment slack*/ + 64 /*barriers*/;
   // blocks per SM the shared memory allows (227 KB usable, 1 KB reserved per block)
   static constexpr int BY_SMEM = 233472 / (SMEM_BYTES + 1024);
-  static constexpr int BY_REGS = (MED == MED_VIS) ? 1 : 65536 / (TILE_X * TILE_Y * 128);   // 128 registers per thread (visco: one block)
-  static constexpr int BLOCKS = BY_SMEM < BY_REGS ? (BY_SMEM < 1 ? 1 : BY_SMEM) : BY_REGS;
+  static constexpr int BLOCKS = clampb(BY_SMEM);
   // one resident block only: two thread groups per tile (stress half / velocity half of the RHS), 512 threads
 #ifndef CGFD_NO_SPLIT
   static constexpr bool SPLIT = (BLOCKS == 1);
@@ -70,7 +83,8 @@ template <int MED> struct Lay {   // the media tiles come last: their number dep
 
 template <int KIND, int MED, bool GZ> __device__ __forceinline__ constexpr uint32_t stage_tx_bytes()
 {
-  return CUR_BYTES + ((GZ ? 5 : 9) + Lay<MED>::NMT) * CEN_BYTES + (KIND != KIND_FIRST ? 9 * CEN_BYTES : 0) + (KIND == KIND_LAST ? 9 * CEN_BYTES : 0);
+  return CUR_BYTES + ((GZ ? 5 : 9) + Lay<MED>::NMT + Lay<MED>::NZT) * CEN_BYTES + (KIND != KIND_FIRST ? 9 * CEN_BYTES : 0) +
+         (KIND == KIND_LAST ? 9 * CEN_BYTES : 0);
 }
 // bytes of the staged memory-variable / Y tiles of one plane (visco-elastic medium, nj = 6 N tiles per level, 2 N Y tiles)
 template <int KIND> __device__ __forceinline__ uint32_t vis_tx_bytes(int nmx)
@@ -94,7 +108,7 @@ struct TmaCtx {
 // Loads of one plane into ring slot s, in two parts: A = the tiles nothing is stored from (wavefield with halo, metric,
 // media; also arms the barrier with the byte count of the whole plane), B = the w_pre / w_end tiles, which double as the
 // sources of the TMA stores of the plane that used the slot before and can only be refilled once those have been read.
-template <int DX, int DY, int KIND, int MED, bool GZ>
+template <int DX, int DY, int DZ, int KIND, int MED, bool GZ>
 __device__ __forceinline__ void tma_issue_a(const StageArgs &P, const TmaMaps &M, const TmaCtx &C, int kk, int s)
 {
   constexpr int YL = Ofs<DY>::left;
@@ -107,6 +121,8 @@ __device__ __forceinline__ void tma_issue_a(const StageArgs &P, const TmaMaps &M
   tma_load_4d_hint(b + OFF_CUR, &M.cur, bar, C.i0 - HX + P.shift, C.j0 - YL, kk, 0, C.pol_keep);
   tma_load_4d_hint(b + OFF_MET, GZ ? &M.met5 : &M.met, bar, C.i0 + P.shift, C.j0, kk, 0, C.pol_stream);
   tma_load_4d_hint(b + OFF_MED, &M.med, bar, C.i0 + P.shift, C.j0, kk, 0, C.pol_stream);
+  // the centre box of the plane ahead (an L2 hit now or for the halo box of that plane one iteration on)
+  if constexpr (Lay<MED>::ZA) tma_load_4d_hint(b + Lay<MED>::OFF_ZA, &M.za, bar, C.i0 + P.shift, C.j0, kk + (DZ ? 1 : -1), 0, C.pol_keep);
   if constexpr (MED == MED_VIS) {
     if (C.nmx > 0) {
       tma_load_4d_hint(b + Lay<MED>::OFF_JC, &M.jcur, bar, C.i0 + P.shift, C.j0, kk, 0, C.pol_stream);
@@ -140,10 +156,10 @@ __device__ __forceinline__ void tma_prefetch_plane(const StageArgs &P, const Tma
   if (KIND != KIND_FIRST) tma_prefetch_4d(&M.pre, C.i0 + P.shift, C.j0, kk, 0);
   if (KIND == KIND_LAST) tma_prefetch_4d(&M.end, C.i0 + P.shift, C.j0, kk, 0);
 }
-template <int DX, int DY, int KIND, int MED, bool GZ>
+template <int DX, int DY, int DZ, int KIND, int MED, bool GZ>
 __device__ __forceinline__ void tma_issue(const StageArgs &P, const TmaMaps &M, const TmaCtx &C, int kk, int s)
 {
-  tma_issue_a<DX, DY, KIND, MED, GZ>(P, M, C, kk, s);
+  tma_issue_a<DX, DY, DZ, KIND, MED, GZ>(P, M, C, kk, s);
   tma_issue_b<DX, DY, KIND, MED>(P, M, C, kk, s);
 }
 
@@ -291,8 +307,8 @@ template <int PART> struct Part {
 };
 template <int DX, int DY, int DZ, int KIND, int MED, bool GZ, bool PML, int PART, bool TOP = false>
 __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, const TmaCtx &C, int k, int it, int nplanes,
-                                          const float (&q0)[Part<PART>::QN], const float (&q1)[Part<PART>::QN], const float (&q2)[Part<PART>::QN],
-                                          const float (&q3)[Part<PART>::QN], float (&q4)[Part<PART>::QN], float (&qn)[Part<PART>::QN])
+                                          float (&q0)[Part<PART>::QN], float (&q1)[Part<PART>::QN], float (&q2)[Part<PART>::QN],
+                                          float (&q3)[Part<PART>::QN], float (&q4)[Part<PART>::QN], float (&qn)[Part<PART>::QN])
 {
   constexpr int YL = Ofs<DY>::left;
   constexpr int FX = Ofs<DX>::first, FY = Ofs<DY>::first;
@@ -302,19 +318,17 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
   const int s = it % NST;
   const uint32_t parity = (it / NST) & 1;
   const float *cx = c_fd.coef[DX], *cy = c_fd.coef[DY], *cz = c_fd.coef[DZ];
+  constexpr bool ZA = Lay<MED>::ZA;   // q3 / q4 of this plane come from shared memory (below, after the wait)
+  if constexpr (!ZA) {
 #pragma unroll
-  for (int c = 0; c < QN; c++) q4[c] = qn[c];
-  if (C.inarr && it + 1 < nplanes && !(P.l2mode & 128)) {   // bit 7: DIAGNOSTIC (wrong results): no z-ahead loads
-    const float *w = C.qptr + (long)(k + 2 * DIR) * (long)P.siz_slice;
-    if (P.l2mode & 2048) {   // touched once by this SM: keep them out of the L1 (which holds the PML aux records, l2mode bit 10)
-#pragma unroll
-      for (int c = 0; c < QN; c++) asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(qn[c]) : "l"(w + (QB + c) * P.siz_vol));
-    } else {
-#pragma unroll
-      for (int c = 0; c < QN; c++) qn[c] = __ldg(w + (QB + c) * P.siz_vol);
-    }
+    for (int c = 0; c < QN; c++) q4[c] = qn[c];
   }
-  if (PML && PART != 2 && C.active && it + 1 < nplanes && !(P.l2mode & 1024)) pml_prefetch<KIND>(P, C.i, C.j, k + DIR);
+  if (!ZA && C.inarr && it + 1 < nplanes && !(P.l2mode & 128)) {   // bit 7: DIAGNOSTIC (wrong results): no z-ahead loads
+    const float *w = C.qptr + (long)(k + 2 * DIR) * (long)P.siz_slice;
+#pragma unroll
+    for (int c = 0; c < QN; c++) qn[c] = __ldg(w + (QB + c) * P.siz_vol);
+  }
+  if (PML && PART != 2 && C.active && it + 1 < nplanes) pml_prefetch<KIND>(P, C.i, C.j, k + DIR);
   const int pmask = PML ? (C.fmask | pml_mask_z(P, k)) : 0;
   // Graves' attenuation factor of this point (last stage only; requested before the wait below so that it is there in time)
   float qatt = 1.0f;
@@ -337,6 +351,13 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
     const float slw = md.slw;
     Deriv d;
     float h[9];
+    if constexpr (ZA) {
+      // this plane's own values and the plane ahead: the centre of the halo tile and the ZA tile (q3 then moves into the register
+      // queue, which holds the three planes behind)
+      const float *za = (const float *)(b + Lay<MED>::OFF_ZA) + C.t;
+#pragma unroll
+      for (int c = 0; c < QN; c++) { q3[c] = sc[(QB + c) * SY * SXT]; q4[c] = za[(QB + c) * NT]; }
+    }
     // derivatives of the components this thread differentiates (queue entry c - QB holds component c)
 #define CGFD_DERIV(c)                                                                                                             \
     {                                                                                                                             \
@@ -377,8 +398,11 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
       for (int c = 0; c < 3; c++) rk_smem<KIND>(sp + c * NT, se + c * NT, PART == 0 ? q3[c - QB] : sc[c * SY * SXT], h[c], P.a, P.b, P.c, qatt);
     }
 #undef CGFD_DERIV
-    // l2mode bit 10: the aux records of the NEXT plane into L1 now (both thread groups of a split block: each asks for its part's lines)
-    if (PML && (P.l2mode & 1024) && it + 1 < nplanes) pml_prefetch_l1<KIND>(P, C.fmask | pml_mask_z(P, k + DIR), C.i, C.j, k + DIR);
+    if constexpr (ZA) {
+      // the register queue moves on here, inside the branch that filled q3: q3 / q4 are dead between planes
+#pragma unroll
+      for (int c = 0; c < QN; c++) { q0[c] = q1[c]; q1[c] = q2[c]; q2[c] = q3[c]; }
+    }
     fence_proxy_async_smem();   // the results written above are read by the TMA store below
   } else {
     // Columns / rows of the tile beyond the physical range. The TMA store clips at the tensor extent, but in units of 16 bytes:
@@ -411,7 +435,7 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
   if (threadIdx.x == 0 && threadIdx.y == 0) {
     const int tx0 = C.i0 - P.ni1, ty0 = C.j0 - P.nj1;
     const bool refill = it + NST < nplanes;
-    if (refill) tma_issue_a<DX, DY, KIND, MED, GZ>(P, M, C, k + NST * DIR, s);   // most of the next plane's bytes: requested at once
+    if (refill) tma_issue_a<DX, DY, DZ, KIND, MED, GZ>(P, M, C, k + NST * DIR, s);   // most of the next plane's bytes: requested at once
     if (C.pf > 0 && it + NST + C.pf < nplanes) tma_prefetch_plane<DX, DY, KIND, MED, GZ>(P, M, C, k + (NST + C.pf) * DIR);
     if (KIND != KIND_LAST) tma_store_4d_hint(&M.out_tmp, b + OFF_PRE, tx0, ty0, k, 0, C.pol_stream);
     if (KIND == KIND_MID || KIND == KIND_LAST) tma_store_4d_hint(&M.out_end, b + OFF_END, tx0, ty0, k, 0, C.pol_stream);
@@ -447,8 +471,8 @@ __device__ __forceinline__ void march(const StageArgs &P, const TmaMaps &M, cons
 #pragma unroll
     for (int c = 0; c < QN; c++) {
       const float *w = P.cur + (QB + c) * P.siz_vol + (size_t)kf * P.siz_slice + C.pij;
-      q0[c] = __ldg(w - 3 * sd); q1[c] = __ldg(w - 2 * sd); q2[c] = __ldg(w - sd); q3[c] = __ldg(w);
-      qn[c] = __ldg(w + sd);
+      q0[c] = __ldg(w - 3 * sd); q1[c] = __ldg(w - 2 * sd); q2[c] = __ldg(w - sd);
+      if constexpr (!Lay<MED>::ZA) { q3[c] = __ldg(w); qn[c] = __ldg(w + sd); }   // ZA: this plane and the one ahead arrive in shared memory
     }
   }
   // TOPK kernels (the top z chunk of a free-surface problem): the ntop free-surface planes (k >= nk2 - 3) are the chunk's LAST planes
@@ -457,7 +481,9 @@ __device__ __forceinline__ void march(const StageArgs &P, const TmaMaps &M, cons
   // more registers than the plain one, and inside one kernel its spills reached the hot loop (profiles/r2_experiments.txt, r2j).
   int it = 0;
 #define CGFD_ROTATE                                                                             \
-  _Pragma("unroll") for (int c = 0; c < QN; c++) { q0[c] = q1[c]; q1[c] = q2[c]; q2[c] = q3[c]; q3[c] = q4[c]; }
+  if constexpr (!Lay<MED>::ZA) {   /* with ZA tiles the plane function rotates its three-deep queue itself */ \
+    _Pragma("unroll") for (int c = 0; c < QN; c++) { q0[c] = q1[c]; q1[c] = q2[c]; q2[c] = q3[c]; q3[c] = q4[c]; } \
+  }
   if (TOPK && !DZ) {
 #pragma unroll 1
     for (; it < ntop; it++) {
@@ -524,7 +550,7 @@ __global__ void __launch_bounds__(TX *TY *(Lay<MED>::SPLIT ? 2 : 1), Lay<MED>::B
   if (t0) {
 #pragma unroll
     for (int s = 0; s < NST; s++)
-      if (s < nplanes) tma_issue<DX, DY, KIND, MED, GZ>(P, M, C, kf + s * DIR, s);
+      if (s < nplanes) tma_issue<DX, DY, DZ, KIND, MED, GZ>(P, M, C, kf + s * DIR, s);
     for (int s = NST; s < NST + C.pf; s++)
       if (s < nplanes) tma_prefetch_plane<DX, DY, KIND, MED, GZ>(P, M, C, kf + s * DIR);
   }
@@ -780,10 +806,7 @@ template <int DX, int DY, int DZ, int KIND, int MED, bool GZ, bool TOPK> static 
 {
   cudaError_t e = cudaFuncSetAttribute(k_main_tma<DX, DY, DZ, KIND, MED, GZ, TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<MED>::SMEM_BYTES);
   if (e != cudaSuccess) return 1;
-  // shared-memory carve-out: the smallest configuration that holds the resident blocks (the rest of the 256 KB is L1)
-  int carve = cudaSharedmemCarveoutMaxShared;
-  if (const char *ev = getenv("CGFD_CARVE")) carve = atoi(ev);
-  e = cudaFuncSetAttribute(k_main_tma<DX, DY, DZ, KIND, MED, GZ, TOPK>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+  e = cudaFuncSetAttribute(k_main_tma<DX, DY, DZ, KIND, MED, GZ, TOPK>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   return e != cudaSuccess;
 }
 template <int DX, int DY, int DZ, int KIND, int MED> static int set_attr_t()

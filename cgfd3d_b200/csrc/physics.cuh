@@ -281,14 +281,9 @@ __device__ __forceinline__ void pml_face(const StageArgs &P, const PmlFaceDev &F
   const float e3 = (AXIS == 0) ? m.xiz : (AXIS == 1) ? m.etz : m.ztz;
   const size_t pa = (((size_t)(k - F.k1) * F.snj + (size_t)(j - F.j1)) * F.sni + (size_t)(i - F.i1)) * AUX_REC + aux_slot(C0);
   float au[N], pv[N], ev[N];
-  if (P.l2mode & 512) {   // DIAGNOSTIC (wrong results): no aux loads -- what the PML planes cost without their load latency
-#pragma unroll
-    for (int n = 0; n < N; n++) { au[n] = 0.0f; pv[n] = 0.0f; ev[n] = 0.0f; }
-  } else {
-    aux_load<N>(F.aux_cur + pa, au);
-    if (KIND != KIND_FIRST) aux_load<N>(F.aux_pre + pa, pv);
-    if (KIND == KIND_LAST) aux_load<N>(F.aux_end + pa, ev);
-  }
+  aux_load<N>(F.aux_cur + pa, au);
+  if (KIND != KIND_FIRST) aux_load<N>(F.aux_pre + pa, pv);
+  if (KIND == KIND_LAST) aux_load<N>(F.aux_end + pa, ev);
   float r[9];
   if (PART) {
     r[VX] = M.slw * (e1 * D_[TXX] + e2 * D_[TXY] + e3 * D_[TXZ]);
@@ -355,33 +350,6 @@ template <int KIND> __device__ __forceinline__ void pml_prefetch(const StageArgs
       asm volatile("prefetch.global.L2 [%0];" ::"l"(F.aux_cur + pa));
       if (KIND != KIND_FIRST) asm volatile("prefetch.global.L2 [%0];" ::"l"(F.aux_pre + pa));
       if (KIND == KIND_LAST) asm volatile("prefetch.global.L2 [%0];" ::"l"(F.aux_end + pa));
-    }
-  }
-}
-
-// the same for the faces in `mask` (pml_mask_xy | pml_mask_z of the point), into L1: issued at the END of the previous plane, so
-// that the records (<= 30 KB per block-plane; the L1 keeps 30 KB per resident block when the shared-memory carve-out is 196 KB)
-// are one L1 hit away when pml_face asks for them, instead of one L2 round trip in the middle of the plane's dependency chain
-template <int KIND> __device__ __forceinline__ void pml_prefetch_l1(const StageArgs &P, int mask, int i, int j, int k)
-{
-#pragma unroll
-  for (int ax = 0; ax < 3; ax++) {
-#pragma unroll
-    for (int s = 0; s < 2; s++) {
-      if (!(mask & (1 << (2 * ax + s)))) continue;
-      const PmlFaceDev &F = P.pml[ax][s];
-      const size_t pa = (((size_t)(k - F.k1) * F.snj + (size_t)(j - F.j1)) * F.sni + (size_t)(i - F.i1)) * AUX_REC;
-      // first and last float of the record: a 40-byte record may straddle two lines
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(F.aux_cur + pa));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(F.aux_cur + pa + 8));
-      if (KIND != KIND_FIRST) {
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(F.aux_pre + pa));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(F.aux_pre + pa + 8));
-      }
-      if (KIND == KIND_LAST) {
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(F.aux_end + pa));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(F.aux_end + pa + 8));
-      }
     }
   }
 }
