@@ -116,6 +116,7 @@ struct cgfd_b200_ctx {
   int nsm = 148;                    // multiprocessors of the device (launch plan: resident blocks per wave)
   int l2mode = 3;                   // L2 eviction hints of the interior kernel (CGFD_L2MODE)
   int overlap = 1;                  // run the boundary phase concurrently with the interior kernel
+  int top_rows = 16;                // fused free surface: rows of the TOPK launch (CGFD_TOP_ROWS)
   int top_stream = 1;               // fused free surface: top-chunk launch on its own stream (CGFD_TOP_STREAM=0: same stream, before the rest)
   int fuse_top = -1;                // free-surface rows as planes of the top z chunk (TOPK launch of k_main_tma) instead of k_top:
                                     // the default where it is the faster route (isotropic medium, measured r2l), CGFD_FUSE_TOP=0 / 1
@@ -546,6 +547,7 @@ extern "C" int cgfd_b200_create(const cgfd_problem_t *p, int device, cgfd_b200_c
   if (c->fuse_top < 0) c->fuse_top = (c->med == MED_ISO);
   if (c->fuse_top) c->toppar = 0;
   if (const char *e = getenv("CGFD_TOP_STREAM")) c->top_stream = atoi(e) != 0;
+  if (const char *e = getenv("CGFD_TOP_ROWS")) { c->top_rows = atoi(e); if (c->top_rows < 4) c->top_rows = 4; }
   if (const char *e = getenv("CGFD_PROFILE_DUMP")) c->prof_dump = fopen(e, "a");
   {
     int lo = 0, hi = 0;
@@ -918,20 +920,22 @@ static const LaunchPlan *plan_for(cgfd_b200_ctx *c, const int rect[4], int dz)
   const bool fused = c->free_top && c->fuse_top;
   const int nk_all = (c->free_top && !fused ? g.nk2 - 4 : g.nk2) - g.nk1 + 1;
   const int bps = blocks_per_sm(c->med);
-  compute_plan(g, pml_r, nk_all, c->nsm, bps, c->plan_waves, c->plan_minchunk, c->zchunk, c->plan_lpt, dz, rect, &pl.zchunk, &order);
-  if (fused && pl.zchunk > 0) {
-    // The chunking above covers every row. Its top chunk (with the chunk below when it is shorter than 8 rows) becomes the launch
-    // of the TOPK kernels: one chunk per tile, the tiles that meet an x / y PML slab first. The chunks below keep their size.
-    const int nzc = (nk_all + pl.zchunk - 1) / pl.zchunk;
-    int kt0 = g.nk1 + (nzc - 1) * pl.zchunk;
-    if (g.nk2 - kt0 + 1 < 8 && nzc >= 2) kt0 -= pl.zchunk;
-    pl.ktop0 = kt0; pl.zchunk_top = g.nk2 - kt0 + 1;
+  if (!fused) {
+    compute_plan(g, pml_r, nk_all, c->nsm, bps, c->plan_waves, c->plan_minchunk, c->zchunk, c->plan_lpt, dz, rect, &pl.zchunk, &order);
+  } else {
+    // The top `top_rows` rows (the four free-surface rows and a few below them, so that a block's start-up is spread over more than
+    // four planes) are the launch of the TOPK kernels: one chunk per tile, the tiles that meet an x / y PML slab first. Kept
+    // short whatever the grid: the TOPK kernels are not the hot loop's best build (section 3.1 of DESIGN.md). The rows below
+    // are chunked as a launch of their own.
+    const int ntop = nk_all < c->top_rows ? nk_all : c->top_rows;
+    const int kt0 = g.nk2 - ntop + 1;
+    pl.ktop0 = kt0; pl.zchunk_top = ntop;
     std::vector<int> otop;
     int zt = 0;
-    compute_plan(g, pml_r, pl.zchunk_top, c->nsm, bps, c->plan_waves, c->plan_minchunk, pl.zchunk_top, c->plan_lpt, dz, rect, &zt, &otop);
+    compute_plan(g, pml_r, ntop, c->nsm, bps, c->plan_waves, c->plan_minchunk, ntop, c->plan_lpt, dz, rect, &zt, &otop);
     if (!otop.empty() && upload(c, &pl.order_top, otop.data(), otop.size())) return nullptr;
-    order.clear();
-    if (kt0 > g.nk1) { int zl = 0; compute_plan(g, pml_r, kt0 - g.nk1, c->nsm, bps, c->plan_waves, c->plan_minchunk, pl.zchunk, c->plan_lpt, dz, rect, &zl, &order); }
+    if (kt0 > g.nk1) compute_plan(g, pml_r, kt0 - g.nk1, c->nsm, bps, c->plan_waves, c->plan_minchunk, c->zchunk, c->plan_lpt, dz, rect, &pl.zchunk, &order);
+    else pl.zchunk = ntop;
   }
   if (!order.empty() && upload(c, &pl.order, order.data(), order.size())) return nullptr;
   return &(c->plans[key] = pl);
