@@ -116,7 +116,7 @@ struct cgfd_b200_ctx {
   int nsm = 148;                    // multiprocessors of the device (launch plan: resident blocks per wave)
   int l2mode = 3;                   // L2 eviction hints of the interior kernel (CGFD_L2MODE)
   int overlap = 1;                  // run the boundary phase concurrently with the interior kernel
-  int top_rows = 16;                // fused free surface: rows of the TOPK launch (CGFD_TOP_ROWS)
+  int top_rows = 24;                // fused free surface: rows of the TOPK launch (CGFD_TOP_ROWS)
   int top_stream = 1;               // fused free surface: top-chunk launch on its own stream (CGFD_TOP_STREAM=0: same stream, before the rest)
   int fuse_top = -1;                // free-surface rows as planes of the top z chunk (TOPK launch of k_main_tma) instead of k_top:
                                     // the default where it is the faster route (isotropic medium, measured r2l), CGFD_FUSE_TOP=0 / 1
@@ -870,13 +870,19 @@ static int split_tiles(const cgfd_b200_ctx *c, bool split, int bnd[4][4], int in
 // its z chunks in the direction the kernel marches (dz = 1 upwards, 0 downwards) before the next band starts, so that the
 // 4 planes a chunk re-reads for its zeta queue are the ones the previous chunk of the same tile has just fetched (L2 hits
 // instead of a second DRAM read). lpt = 1: chunk-major order.
+constexpr int PLAN_CHUNK_ROWS = 25;
 static void compute_plan(const cgfd_grid_t &g, const int pml_r[2][2][3], int nk /* rows of the launch */, int nsm, int blocks_per_sm, int waves,
                          int minchunk, int zchunk_explicit, int lpt, int dz, const int rect[4], int *zchunk, std::vector<int> *order)
 {
   *zchunk = 0; order->clear();
   const int bx = rect[1] - rect[0], by = rect[3] - rect[2];
   if (bx <= 0 || by <= 0 || nk <= 0) return;
-  int nzc = 1;
+  // Chunks of ~25 rows whatever the grid: a band of tiles restarts together at every chunk boundary, which keeps neighbouring tiles
+  // within a few planes of each other, so that the halo lines they share are still in L2 (800x800x400: chunks of 198 rows, which
+  // the wave count alone would allow, run 12 % slower than chunks of 25 -- profiles/r2_experiments.txt r2p). Small rectangles get
+  // more, shorter chunks (never under `minchunk` rows) until they make `waves` waves of resident blocks.
+  int nzc = (nk + PLAN_CHUNK_ROWS / 2) / PLAN_CHUNK_ROWS;
+  if (nzc < 1) nzc = 1;
   if (zchunk_explicit > 0) nzc = (nk + zchunk_explicit - 1) / zchunk_explicit;
   else
     while (nzc < nk && (long)bx * by * nzc < (long)nsm * blocks_per_sm * waves && nk / (nzc + 1) >= minchunk) nzc++;
