@@ -328,7 +328,8 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
 #pragma unroll
     for (int c = 0; c < QN; c++) qn[c] = __ldg(w + (QB + c) * P.siz_vol);
   }
-  if (PML && PART != 2 && C.active && it + 1 < nplanes) pml_prefetch<KIND>(P, C.i, C.j, k + DIR);
+  // l2mode bit 9: no prefetch of the aux records (the loads are not what the PML planes wait for, r2i; the prefetch costs instructions)
+  if (PML && PART != 2 && C.active && it + 1 < nplanes && !(P.l2mode & 512)) pml_prefetch<KIND>(P, C.fmask | pml_mask_z(P, k + DIR), C.i, C.j, k + DIR);
   const int pmask = PML ? (C.fmask | pml_mask_z(P, k)) : 0;
   // Graves' attenuation factor of this point (last stage only; requested before the wait below so that it is there in time)
   float qatt = 1.0f;

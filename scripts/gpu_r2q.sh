@@ -17,6 +17,8 @@ run vti vti A=1
 run aniso aniso A=1
 run visco visco A=1
 run iso_ktop iso CGFD_FUSE_TOP=0
+run iso_b iso A=1
+run iso_nopf iso CGFD_L2MODE=515
 SZ="--size 800x800x400"
 run big_default iso A=1
 run big_z20 iso CGFD_ZCHUNK=20
