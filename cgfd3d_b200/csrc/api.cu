@@ -870,7 +870,7 @@ static int split_tiles(const cgfd_b200_ctx *c, bool split, int bnd[4][4], int in
 // its z chunks in the direction the kernel marches (dz = 1 upwards, 0 downwards) before the next band starts, so that the
 // 4 planes a chunk re-reads for its zeta queue are the ones the previous chunk of the same tile has just fetched (L2 hits
 // instead of a second DRAM read). lpt = 1: chunk-major order.
-constexpr int PLAN_CHUNK_ROWS = 25;
+constexpr int PLAN_CHUNK_ROWS = 25, PLAN_CHUNK_ROWS_2 = 18;
 static void compute_plan(const cgfd_grid_t &g, const int pml_r[2][2][3], int nk /* rows of the launch */, int nsm, int blocks_per_sm, int waves,
                          int minchunk, int zchunk_explicit, int lpt, int dz, const int rect[4], int *zchunk, std::vector<int> *order)
 {
@@ -881,7 +881,10 @@ static void compute_plan(const cgfd_grid_t &g, const int pml_r[2][2][3], int nk 
   // within a few planes of each other, so that the halo lines they share are still in L2 (800x800x400: chunks of 198 rows, which
   // the wave count alone would allow, run 12 % slower than chunks of 25 -- profiles/r2_experiments.txt r2p). Small rectangles get
   // more, shorter chunks (never under `minchunk` rows) until they make `waves` waves of resident blocks.
-  int nzc = (nk + PLAN_CHUNK_ROWS / 2) / PLAN_CHUNK_ROWS;
+  // measured r2r: two resident blocks per SM (iso, VTI) 16 / 18 / 20 / 22 / 25 rows: 4.867 / 4.870 / 4.876 / 4.893 / 4.899 ms per step
+  // at 400x400x200, 7.82 / 7.81 / 7.82 / - / 7.76 Gpt/s at 800x800x400; one resident block (aniso, visco): 25 rows over 20 by 0.6 %
+  const int rows = blocks_per_sm >= 2 ? PLAN_CHUNK_ROWS_2 : PLAN_CHUNK_ROWS;
+  int nzc = (nk + rows / 2) / rows;
   if (nzc < 1) nzc = 1;
   if (zchunk_explicit > 0) nzc = (nk + zchunk_explicit - 1) / zchunk_explicit;
   else
