@@ -493,6 +493,7 @@ static int check_fd(const cgfd_fd_t &fd)
   return 0;
 }
 
+static int stage_alloc(cgfd_b200_ctx *c);
 extern "C" int cgfd_b200_create(const cgfd_problem_t *p, int device, cgfd_b200_ctx **out)
 {
   *out = nullptr;
@@ -679,6 +680,9 @@ extern "C" int cgfd_b200_create(const cgfd_problem_t *p, int device, cgfd_b200_c
   }
   rc |= setup_sources(c, p);
   if (c->has_surf) rc |= upload(c, &c->srcslice, (const float *)nullptr, c->hslice * 6);
+  // the two one-component staging buffers of set_wavefield / get_wavefield: every device allocation of a context happens here, so
+  // that the first whole-wavefield transfer of a run costs what the later ones cost (bench.py e2e: 34 ms against 22 ms)
+  rc |= stage_alloc(c);
   if (rc) { cgfd_b200_destroy(c); return 1; }
   CKD(cudaDeviceSynchronize());
   *out = c;
