@@ -107,6 +107,32 @@ def test_launch_plan_longest_job_first():
     assert order2 == list(range(len(order2)))
 
 
+def test_launch_plan_chunk_length_does_not_grow_with_the_grid():
+    """z chunks stay short whatever the grid (bands of tiles restart together at every chunk boundary, which keeps the halo lines
+    neighbouring tiles share in L2: 800x800x400 ran 12 % slower with the 198-row chunks the wave count alone allows, profiles/
+    r2_experiments.txt r2p): ~18 rows with two resident blocks per SM, ~25 with one; small rectangles get more, shorter chunks,
+    never under 16 rows"""
+    from cgfd3d_b200 import solver
+    nl = 10
+    for (ni, nj, nk) in ((400, 400, 200), (800, 800, 400), (1200, 600, 600), (150, 300, 300)):
+        grid = dict(nx=ni + 6, ny=nj + 6, nz=nk + 6, ni1=3, ni2=ni + 2, nj1=3, nj2=nj + 2, nk1=3, nk2=nk + 2)
+        ntx, nty = (ni + 31) // 32, (nj + 7) // 8
+        for bps, lo, hi in ((2, 16, 19), (1, 16, 26)):
+            for free_top in (0, 1):
+                zc, od = solver.launch_plan(grid, ((nl, nl), (nl, nl), (nl, 0)), free_top, (0, ntx, 0, nty), blocks_per_sm=bps)
+                rows = nk - 4 * free_top
+                assert lo <= zc <= hi, (ni, nj, nk, bps, zc)
+                assert len(od) == ntx * nty * -(-rows // zc)
+    # a one-tile-wide boundary rectangle of a small block: chunks shrink towards 16 rows to make enough blocks, not below
+    grid = dict(nx=106, ny=106, nz=66, ni1=3, ni2=102, nj1=3, nj2=102, nk1=3, nk2=62)
+    zc, od = solver.launch_plan(grid, ((0, nl), (nl, nl), (nl, 0)), 0, (0, 1, 0, 13))
+    assert zc == 20 and len(od) == 13 * 3   # 4 chunks would be 15 rows
+    # fewer rows than one chunk: a single chunk
+    grid = dict(nx=46, ny=46, nz=17, ni1=3, ni2=42, nj1=3, nj2=42, nk1=3, nk2=13)
+    zc, od = solver.launch_plan(grid, ((0, 0), (0, 0), (0, 0)), 0, (0, 2, 0, 5))
+    assert zc == 11 and len(od) == 10
+
+
 def test_bench_rank_problems_for_the_8_gpu_grid():
     """bench.build_rank_problem on the 4x2 process grid of the 8-GPU run (small blocks, numpy set-up): neighbours follow the
     reference's row-major cart (forward/mympi_t.c:32-40), inter-rank faces carry no PML, exactly one rank owns the source, and the
