@@ -431,25 +431,7 @@ __device__ __forceinline__ void tma_plane(const StageArgs &P, const TmaMaps &M, 
   // every thread is done with ring slot s; its PRE / END tiles now hold w_tmp / w_end of this plane. The two thread groups of a
   // split block reach this point through different instantiations of this function: they meet at a NAMED barrier with an explicit
   // thread count (the producer / consumer idiom: warps may arrive from different program counters), not at __syncthreads()
-#ifndef CGFD_PLANE_SYNC
-  if (PART == 0) {
-    // Only the warp that issues the stores and the refill of this slot has to see every warp's results: it WAITS at the plane's
-    // barrier, the other warps only ARRIVE and go straight on to the next plane (whose operands sit in the other slot and are
-    // guarded by that slot's mbarrier). Two barrier ids alternate, so that a warp one plane ahead never meets the plane behind it;
-    // no warp can be two planes ahead, because the slot it would need is refilled by the issuing warp after this barrier.
-    // (ncu r2j: 17 % of the stall samples of the plain planes were warps waiting here for the slowest warp of their block.)
-    // (immediate ids: with an id in a register ptxas reserves all 16 barriers of the block)
-    if (it & 1) {
-      if (threadIdx.y == 0) asm volatile("barrier.sync 3, %0;" ::"n"(TX * TY) : "memory");
-      else asm volatile("barrier.arrive 3, %0;" ::"n"(TX * TY) : "memory");
-    } else {
-      if (threadIdx.y == 0) asm volatile("barrier.sync 2, %0;" ::"n"(TX * TY) : "memory");
-      else asm volatile("barrier.arrive 2, %0;" ::"n"(TX * TY) : "memory");
-    }
-  }
-#else
   if (PART == 0) __syncthreads();
-#endif
   else asm volatile("barrier.sync 1, %0;" ::"r"(2 * TX * TY) : "memory");
   if (threadIdx.x == 0 && threadIdx.y == 0) {
     const int tx0 = C.i0 - P.ni1, ty0 = C.j0 - P.nj1;
