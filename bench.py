@@ -444,17 +444,50 @@ def _ref_program_seconds(size, px, py, nt, hill):
         shutil.rmtree(wd, ignore_errors=True)
 
 
+def _ref_program_step_stamps(size, px, py, nt, hill):
+    """one run of nt steps with the start of every step stamped on arrival of the driver's '-> it=' line (oracle/harness.run_timed);
+    returns (wall, {step: seconds}, outputs finite)"""
+    import shutil
+    import tempfile
+    from oracle import harness as H
+    wd = tempfile.mkdtemp(prefix="cgfd_refarm_")
+    try:
+        H.write_multirank_hill_case(wd, size, px, py, nt, REF_DT, hill=hill, pml_layers=10, src=H.moment_src(size[0] // 2, size[1] // 2, 20))
+        env = dict(os.environ, CGFD_SHIM_NPROCS=str(px * py), CGFD_SHIM_MSG_MB="64")
+        wall, stamps = H.run_timed(H.ref_binary("ref_main_zero"), wd, timeout=3000, env=env)
+        sac = H.read_sac_dir(os.path.join(wd, "OUT"))
+        finite = all(bool(np.isfinite(v).all()) for v in sac.values()) and len(sac) > 0
+        return wall, stamps, finite
+    finally:
+        shutil.rmtree(wd, ignore_errors=True)
+
+
 def cpu_baseline(cores, steps=4, warm=1, size=REF_SIZE, hill=REF_HILL):
-    """Gpoint-updates/s of the reference program on `cores` ranks: (wall of a run of warm + steps steps) - (wall of a run of warm
-    steps), i.e. the time loop alone (the program's own timer has a resolution of one second)."""
+    """Gpoint-updates/s of the reference program on `cores` ranks over `steps` RK4 steps after `warm` untimed ones. One run of
+    warm + steps + 1 steps whose driver reports the start of every step (verbose > 10, forward/drv_rk_curv_col.c:172): the time
+    between the start of step `warm` and the start of step `warm + steps`, i.e. the time loop alone. Where the lines cannot be
+    stamped on arrival: (wall of a run of warm + steps steps) - (wall of a run of warm steps) (the program's own timer has a
+    resolution of one second)."""
     from oracle import harness as H
     if not H.have_ref("ref_main_zero"):
         return {"value": None, "unit": "Gpoint-updates/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}
     px, py = _rank_grid(cores)
+    npts = size[0] * size[1] * size[2]
+    wall, stamps, ok = _ref_program_step_stamps(size, px, py, warm + steps + 1, hill)
+    if warm in stamps and warm + steps in stamps:
+        secs = max(stamps[warm + steps] - stamps[warm], 1e-6)
+        per = sorted(stamps[n + 1] - stamps[n] for n in range(warm, warm + steps))
+        return {"value": round(npts * steps / secs / 1e9, 6), "unit": "Gpoint-updates/s", "cores": cores, "kind": "reference",
+                "ranks": "%dx%d" % (px, py), "seconds_per_step": round(secs / steps, 4), "seconds_per_step_min_max": [round(per[0], 4), round(per[-1], 4)],
+                "setup_s": round(stamps[0], 2), "finite": bool(ok),
+                "sample": "%d RK4 steps of the bench workload itself (isotropic, Gaussian hill %dx%dx%d through gd_curv_coord_import, CFS-PML 10x5, "
+                          "free surface, 1 moment source) by the unmodified reference program on %dx%d ranks with halo exchange "
+                          "(fork/shared-memory MPI stand-in: no MPI in the image); time = start of step %d to start of step %d of one run, "
+                          "from the driver's own per-step lines stamped on arrival"
+                          % ((steps,) + tuple(size) + (px, py, warm, warm + steps))}
     t_w, ok1 = _ref_program_seconds(size, px, py, warm, hill)
     t_wk, ok2 = _ref_program_seconds(size, px, py, warm + steps, hill)
     secs = max(t_wk - t_w, 1e-6)
-    npts = size[0] * size[1] * size[2]
     return {"value": round(npts * steps / secs / 1e9, 6), "unit": "Gpoint-updates/s", "cores": cores, "kind": "reference",
             "ranks": "%dx%d" % (px, py), "seconds_per_step": round(secs / steps, 4), "setup_s": round(t_w, 2), "finite": bool(ok1 and ok2),
             "sample": "%d RK4 steps of the bench workload itself (isotropic, Gaussian hill %dx%dx%d through gd_curv_coord_import, CFS-PML 10x5, "

@@ -168,6 +168,44 @@ def run(binary: str, workdir: str, verbose: int = 1, timeout: float = 3600, env=
     return wall, p.stdout
 
 
+def run_timed(binary: str, workdir: str, timeout: float = 3600, env=None):
+    """Run `<binary> case.json 11` (verbose > 10: the reference driver prints '-> it=<n>, t=...' when a step STARTS,
+    forward/drv_rk_curv_col.c:172) with line-buffered stdout and stamp every such line as it arrives. Returns (wall seconds,
+    {step: seconds since program start}); the dict is empty when the lines could not be stamped (no stdbuf: the pipe is then block
+    buffered and everything arrives at exit)."""
+    import re
+    import shutil
+    stdbuf = shutil.which("stdbuf")
+    cmd = ([stdbuf, "-oL"] if stdbuf else []) + [binary, "case.json", "11"]
+    t0 = time.time()
+    stamps = {}
+    with open(os.path.join(workdir, "stderr.log"), "w") as ferr:
+        p = subprocess.Popen(cmd, cwd=workdir, stdout=subprocess.PIPE, stderr=ferr, text=True, env=env)
+        tail = []
+        try:
+            for line in p.stdout:
+                m = re.match(r"-> it=(\d+),", line)
+                if m:
+                    stamps.setdefault(int(m.group(1)), time.time() - t0)
+                tail.append(line)
+                if len(tail) > 200:
+                    del tail[:100]
+                if time.time() - t0 > timeout:
+                    p.kill()
+                    raise RuntimeError("%s: timeout after %.0f s" % (binary, timeout))
+            rc = p.wait()
+        finally:
+            if p.poll() is None:
+                p.kill()
+    wall = time.time() - t0
+    if rc != 0:
+        raise RuntimeError("%s failed (rc=%d)\nstdout tail:\n%s\nstderr tail:\n%s"
+                           % (binary, rc, "".join(tail)[-3000:], open(os.path.join(workdir, "stderr.log")).read()[-3000:]))
+    if not stdbuf or len(stamps) < 2 or max(stamps.values()) - min(stamps.values()) < 1e-3:
+        stamps = {}
+    return wall, stamps
+
+
 def read_sac(path: str) -> np.ndarray:
     return np.fromfile(path, dtype="<f4", offset=632)
 
