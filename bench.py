@@ -464,7 +464,7 @@ def _ref_program_step_stamps(size, px, py, nt, hill):
 
 def cpu_baseline(cores, steps=4, warm=1, size=REF_SIZE, hill=REF_HILL):
     """Gpoint-updates/s of the reference program on `cores` ranks over `steps` RK4 steps after `warm` untimed ones. One run of
-    warm + steps + 1 steps whose driver reports the start of every step (verbose > 10, forward/drv_rk_curv_col.c:172): the time
+    warm + steps + 1 steps (number_of_time_steps = warm + steps) whose driver reports the start of every step (verbose > 10, forward/drv_rk_curv_col.c:172): the time
     between the start of step `warm` and the start of step `warm + steps`, i.e. the time loop alone. Where the lines cannot be
     stamped on arrival: (wall of a run of warm + steps steps) - (wall of a run of warm steps) (the program's own timer has a
     resolution of one second)."""
@@ -473,7 +473,8 @@ def cpu_baseline(cores, steps=4, warm=1, size=REF_SIZE, hill=REF_HILL):
         return {"value": None, "unit": "Gpoint-updates/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}
     px, py = _rank_grid(cores)
     npts = size[0] * size[1] * size[2]
-    wall, stamps, ok = _ref_program_step_stamps(size, px, py, warm + steps + 1, hill)
+    # the reference runs number_of_time_steps + 1 steps (forward/main_curv_col_el_3d.c:615): steps 0 .. warm + steps start, the last one is untimed
+    wall, stamps, ok = _ref_program_step_stamps(size, px, py, warm + steps, hill)
     if warm in stamps and warm + steps in stamps:
         secs = max(stamps[warm + steps] - stamps[warm], 1e-6)
         per = sorted(stamps[n + 1] - stamps[n] for n in range(warm, warm + steps))

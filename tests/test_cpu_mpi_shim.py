@@ -70,3 +70,24 @@ def test_hill_ranks_match_one_rank():
     one = _run(size, 1, 1, nt, (600.0, 1200.0), **kw)
     w = _worst(one, _run(size, 3, 2, nt, (600.0, 1200.0), **kw))
     assert w <= 5e-5, w
+
+
+@need
+def test_reference_arm_times_the_loop_from_the_programs_own_step_lines():
+    """bench.py's reference arm: one run of the reference program with verbose > 10, the '-> it=' lines of its driver
+    (forward/drv_rk_curv_col.c:172) stamped on arrival. Every step must be seen, in order, and the outputs must be there."""
+    import bench
+    cb = bench.cpu_baseline(2, steps=3, warm=1, size=(48, 40, 24), hill=(400.0, 800.0))
+    assert cb["kind"] == "reference" and cb["cores"] == 2 and cb["ranks"] == "2x1" and cb["finite"]
+    assert cb["value"] > 0 and cb["seconds_per_step"] > 0
+    import shutil
+    if shutil.which("stdbuf"):
+        lo, hi = cb["seconds_per_step_min_max"]
+        assert 0 < lo <= cb["seconds_per_step"] <= hi
+        assert "stamped on arrival" in cb["sample"]
+    wd = tempfile.mkdtemp(prefix="cgfd_mpi_")
+    H.write_multirank_hill_case(wd, (48, 40, 24), 1, 1, 4, 0.015, hill=(400.0, 800.0), pml_layers=6, src=H.moment_src(24, 20, 8))
+    wall, stamps = H.run_timed(H.ref_binary("ref_main_zero"), wd, timeout=300, env=dict(os.environ, CGFD_SHIM_NPROCS="1"))
+    if shutil.which("stdbuf"):
+        # number_of_time_steps = 4 -> nt_total = 5 steps (forward/main_curv_col_el_3d.c:615)
+        assert sorted(stamps) == [0, 1, 2, 3, 4] and all(stamps[n + 1] > stamps[n] for n in range(4)) and stamps[4] < wall
